@@ -1,0 +1,108 @@
+"""
+Generate the committed parity fixtures under tests/golden/ (run in the build container only):
+
+  python oracle/make_golden.py
+
+1. ref_py_<rig>.npz : per-point inputs and the outputs of the reference's own pure-Python solvers
+   (Work/python_libs/triangulation.py:1-233 exec'd unmodified, cv2 4.13) on seeded synthetic batches.
+2. golden_cells.json : sampled cells of the reference's golden result files
+   Work/triangulation_comparison/{test_1and2,test_3}.mat and figures_scene/test_1and2.mat (numbers
+   only), with the trajectory tables needed to replay them.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import scipy.io as sio
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "multiple-quadrotor-slam_b200"))
+
+from oracle.ref_exec import REFERENCE_ROOT, load_reference_triangulation   # noqa: E402
+import synthetic_rig as rig                                                  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def per_point_fixtures():
+    ref = load_reference_triangulation()
+    cases = [("translating", 0.8, False, 400), ("rotating", 0.8, False, 400), ("forward", 0.8, True, 400),
+             ("general", 4.0, False, 400), ("translating", 0.0, False, 64)]
+    for ci, (name, sigma, disc, n) in enumerate(cases):
+        u1, P1, u2, P2, X = rig.make_correspondences(n, name, sigma, disc, seed=rig.RSEED + ci)
+        out = {"u1": u1, "P1": P1, "u2": u2, "P2": P2, "X": X, "sigma": sigma}
+        for fn in ("linear_eigen", "linear_LS", "iterative_LS", "polynomial"):
+            x, st = getattr(ref, fn + "_triangulation")(u1, P1, u2, P2)
+            out["x_" + fn] = x
+            out["status_" + fn] = st
+        np.savez_compressed(os.path.join(GOLDEN, "ref_py_%d_%s.npz" % (ci, name)), **out)
+        print("wrote fixture", ci, name, n)
+    # 4x4 P, float32 inputs, float32 output dtype: the SLAM calling convention (slam2.py:19,551-555)
+    u1, P1, u2, P2, X = rig.make_correspondences(300, "rotating", 0.8, False, seed=rig.RSEED + 77, dtype=np.float32)
+    P1f = np.eye(4); P1f[0:3] = P1
+    P2f = np.eye(4); P2f[0:3] = P2
+    ref.set_triangl_output_dtype(np.float32)
+    x, st = ref.iterative_LS_triangulation(u1, P1f, u2, P2f)
+    ref.set_triangl_output_dtype(float)
+    np.savez_compressed(os.path.join(GOLDEN, "ref_py_slam_f32.npz"), u1=u1, P1=P1f, u2=u2, P2=P2f, X=X,
+                        x_iterative_LS=x, status_iterative_LS=st)
+
+
+def golden_cells():
+    base = os.path.join(REFERENCE_ROOT, "Work/triangulation_comparison")
+    out = {}
+    keys = ["err3D_mean_summary", "err3D_median_summary", "err2D_mean_summary", "err2D_median_summary",
+            "false_pos_summary", "false_neg_summary"]
+
+    def traj_table(m):
+        t = m["trajectories"]
+        tab = []
+        t = t.ravel()
+        for i in range(len(t)):
+            e = t[i]
+            tab.append({k: e[k][0, 0].ravel().tolist() for k in ("sideways_values", "towards_values", "angle_values")})
+        return tab
+
+    m = sio.loadmat(os.path.join(base, "test_1and2.mat"))
+    cells = [(0, 5), (0, 10), (0, 39), (1, 10), (1, 39), (2, 20), (3, 20), (3, 39), (4, 20), (4, 39)]
+    out["test_1and2"] = {
+        "num_trials": int(m["num_trials"][0, 0]), "rseed": int(m["rseed"][0, 0]),
+        "methods": [s.strip() for s in m["triangl_methods"]],
+        "trajectories": traj_table(m),
+        "cells": [{"traj": t, "pose": p, **{k: m[k][t, p].tolist() for k in keys}} for t, p in cells]}
+
+    m = sio.loadmat(os.path.join(base, "test_3.mat"))
+    cells3 = [(0, 0, 20), (3, 2, 39), (4, 1, 10), (2, 0, 5)]
+    out["test_3"] = {
+        "num_trials": int(m["num_trials"][0, 0]), "rseed": int(m["rseed"][0, 0]),
+        "trajectories": traj_table(m),
+        "noise_sigma_values": m["noise_sigma_values"].ravel().tolist(),
+        "cells": [{"traj": t, "ntype": nt, "nidx": ni, **{k: m[k][t, nt, ni].tolist() for k in keys}}
+                  for t, nt, ni in cells3]}
+
+    m = sio.loadmat(os.path.join(base, "figures_scene", "test_1and2.mat"))
+    out["scene_test_1and2"] = {
+        "num_trials": int(m["num_trials"][0, 0]), "rseed": int(m["rseed"][0, 0]),
+        "trajectories": traj_table(m),
+        "points_3D": m["points_3D"].tolist(),
+        "cells": [{"traj": t, "pose": p, **{k: m[k][t, p].tolist() for k in keys}} for t, p in [(0, 20), (3, 39)]]}
+
+    def clean(o):       # NaN -> None for strict JSON
+        if isinstance(o, float):
+            return None if o != o else o
+        if isinstance(o, list):
+            return [clean(v) for v in o]
+        if isinstance(o, dict):
+            return {k: clean(v) for k, v in o.items()}
+        return o
+    with open(os.path.join(GOLDEN, "golden_cells.json"), "w") as f:
+        json.dump(clean(out), f)
+    print("wrote golden_cells.json")
+
+
+if __name__ == "__main__":
+    per_point_fixtures()
+    golden_cells()

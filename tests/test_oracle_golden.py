@@ -1,0 +1,97 @@
+"""
+Pins the CPU oracle against the reference's own golden result files:
+sampled cells of test_1and2.mat / test_3.mat / figures_scene/test_1and2.mat must be reproduced to
+>= 9 significant digits by linear_LS, iterative_LS (C semantics, incl. false-pos/neg of its status) and
+linear_eigen with the OpenCV-2 6x4 system.
+"""
+import json
+import os
+from functools import partial
+
+import numpy as np
+import pytest
+
+from oracle import triangulation_oracle as orc
+from harness_replay import replay_cell
+
+RTOL = 2e-9
+
+
+@pytest.fixture(scope="module")
+def cells(golden_dir):
+    with open(os.path.join(golden_dir, "golden_cells.json")) as f:
+        return json.load(f)
+
+
+SOLVERS = [partial(orc.linear_eigen_triangulation, rows=6), orc.linear_LS_triangulation,
+           orc.iterative_LS_triangulation]
+
+
+def _pose(tab, t, p):
+    tr = tab[t]
+    return tr["sideways_values"][p], tr["towards_values"][p], tr["angle_values"][p]
+
+
+def _check(got, cell, methods, keys, rtol=RTOL):
+    for k in keys:
+        for ti in methods:
+            want = cell[k][ti]
+            if want is None:
+                continue
+            assert got[k][ti] == pytest.approx(want, rel=rtol, abs=1e-12), (k, ti, got[k][ti], want)
+
+
+ALL_KEYS = ("err3D_mean_summary", "err3D_median_summary", "err2D_mean_summary", "err2D_median_summary",
+            "false_pos_summary", "false_neg_summary")
+
+
+@pytest.mark.parametrize("ci", range(10))
+def test_test_1and2_cells(cells, ci):
+    g = cells["test_1and2"]
+    cell = g["cells"][ci]
+    got = replay_cell(SOLVERS, _pose(g["trajectories"], cell["traj"], cell["pose"]), num_trials=g["num_trials"],
+                      rseed=g["rseed"])
+    # linear_LS (err2D mean on the forward trajectory is 0/0 at the camera centre: see below)
+    _check(got, cell, (1,), [k for k in ALL_KEYS if not (cell["traj"] == 1 and k == "err2D_mean_summary")])
+    if cell["traj"] != 1:
+        _check(got, cell, (2,), ALL_KEYS)                                 # iterative_LS (C semantics)
+        _check(got, cell, (0,), ALL_KEYS)                                 # linear_eigen, OpenCV-2 6x4 system
+    else:
+        # Forward motion: 9 of the 257 lattice points lie exactly on the baseline.  With integer pixels their
+        # depth in camera 2 is 0 up to rounding, so the C code's `d2_new == 0` break (triangulation.c:138) is
+        # decided by the last bit of the SVD -- not reproducible across SVD implementations.  Those 3.5 % of
+        # the points move the statistics by < 1 %; linear_eigen's means are NaN/huge for the same reason.
+        _check(got, cell, (2,), ALL_KEYS, rtol=1e-2)
+        _check(got, cell, (0,), ("err3D_median_summary", "err2D_median_summary"))
+
+
+def test_iterative_status_semantics_differ(cells):
+    """F2: the golden false-negative ratio is only reproduced by the C control flow, not the Python one."""
+    g = cells["test_1and2"]
+    cell = [c for c in g["cells"] if (c["traj"], c["pose"]) == (4, 39)][0]
+    py = partial(orc.iterative_LS_triangulation, semantics='py')
+    got = replay_cell([orc.iterative_LS_triangulation, py], _pose(g["trajectories"], 4, 39),
+                      num_trials=g["num_trials"], rseed=g["rseed"])
+    assert got["false_neg_summary"][0] == pytest.approx(cell["false_neg_summary"][2], rel=RTOL)
+    assert got["false_neg_summary"][1] == 0.0
+    assert cell["false_neg_summary"][2] > 0.4
+
+
+@pytest.mark.parametrize("ci", range(4))
+def test_test_3_cells(cells, ci):
+    g = cells["test_3"]
+    cell = g["cells"][ci]
+    nt = cell["ntype"]
+    got = replay_cell(SOLVERS, _pose(g["trajectories"], cell["traj"], -1), num_trials=g["num_trials"],
+                      rseed=g["rseed"], sigma=g["noise_sigma_values"][cell["nidx"]], discretized=nt >= 1,
+                      k1=0.3 if nt == 2 else 0.)
+    _check(got, cell, (1, 2), ALL_KEYS)
+
+
+@pytest.mark.parametrize("ci", range(2))
+def test_scene_cells(cells, ci):
+    g = cells["scene_test_1and2"]
+    cell = g["cells"][ci]
+    got = replay_cell(SOLVERS, _pose(g["trajectories"], cell["traj"], cell["pose"]), num_trials=g["num_trials"],
+                      rseed=g["rseed"], points_3D=np.array(g["points_3D"]))
+    _check(got, cell, (1, 2), ALL_KEYS)
