@@ -1,0 +1,150 @@
+/*
+ * libtriangl_cuda -- C ABI of the B200 (sm_100a) batched two-view triangulation hot path.
+ *
+ * Each entry point replaces one native/third-party call of the reference
+ * (Eliasvan/Multiple-Quadrotor-SLAM, paths relative to the reference root):
+ *
+ *   trgl_linear_ls      <- triangulation_ext.linear_LS_triangulation(u1,P1,u2,P2,x)
+ *                          Work/python_libs/triangulation_c/triangulation.c:48-83
+ *                          (Python fallback Work/python_libs/triangulation.py:31-94)
+ *   trgl_iterative_ls   <- triangulation_ext.iterative_LS_triangulation(u1,P1,u2,P2,tolerance,x,x_status)
+ *                          triangulation.c:85-161   (Python fallback triangulation.py:100-195)
+ *   trgl_linear_eigen   <- cv2.triangulatePoints + dehomogenise + finite mask, triangulation.py:6-25
+ *   trgl_polynomial     <- cv2.invert / F=[t]xR / cv2.correctMatches / linear_eigen, triangulation.py:198-232
+ *   trgl_reproj_error   <- cv2.projectPoints + RMS, Work/python_libs/calibration_tools.py:116-124 (and :89-113)
+ *   trgl_pair_reproj    <- the harness' re-projection of x into both cameras and status>0 good mask,
+ *                          Work/triangulation_comparison/triangulation_comparison.py:190-217,242-260
+ *
+ * Conventions (same as the reference's weave boundary, triangulation_c/__init__.py:18-86):
+ *   - caller allocates every output, callee fills it in place, inputs are never modified;
+ *   - u1,u2: (n,2) row-major normalised image coordinates; x: (n,3) row-major; P1,P2: 12 doubles =
+ *     rows 0..2 of the row-major 3x4 / 4x4 camera matrix (row stride 4), always HOST memory;
+ *   - all functions return 0 on success or a negative TRGL_E_* / positive cudaError_t code; they never
+ *     abort and never throw.  NaN/Inf inputs propagate into x / status like the reference.
+ *   - mem = TRGL_MEM_HOST: u1,u2,x,status are host buffers, the library stages them through the GPU
+ *     (H2D + kernel + D2H, chunked and overlapped; pinned buffers from trgl_host_alloc go at full PCIe speed);
+ *     mem = TRGL_MEM_DEVICE: they are device pointers on the current device, the kernel is enqueued on
+ *     `stream` (a cudaStream_t, NULL = default stream) and the call returns without synchronising.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ *
+ * Precision modes (`mode`):
+ *   TRGL_F64       u,x float64, float64 arithmetic            (reference arithmetic, triangulation.c)
+ *   TRGL_F32IO     u,x float32, float64 arithmetic            (the SLAM convention: slam2.py:19,551-555)
+ *   TRGL_F32       u,x float32, float32 arithmetic            ("FP32 mode" of BASELINE.json)
+ *   TRGL_F64_OUT32 u float64, x float32, float64 arithmetic   (output_dtype=float32 on float64 inputs)
+ *   TRGL_F32_OUT64 u float32, x float64, float64 arithmetic   (float32 inputs, default output dtype)
+ */
+#ifndef TRIANGL_CUDA_H
+#define TRIANGL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRGL_VERSION 100
+
+enum { TRGL_F64 = 0, TRGL_F32IO = 1, TRGL_F32 = 2, TRGL_F64_OUT32 = 3, TRGL_F32_OUT64 = 4 };
+enum { TRGL_MEM_HOST = 0, TRGL_MEM_DEVICE = 1 };
+enum { TRGL_ITER_C = 0, TRGL_ITER_PY = 1 };          /* iterative_LS control flow: triangulation.c vs triangulation.py */
+
+enum {
+    TRGL_OK = 0,
+    TRGL_E_BADARG = -1,        /* NULL pointer with n > 0, unknown mode / mem / rows */
+    TRGL_E_NODEVICE = -2,      /* no usable CUDA device */
+    TRGL_E_NOMEM = -3
+};
+
+/* ---- library / device management ---- */
+int trgl_version(void);
+const char* trgl_last_error_string(void);
+int trgl_device_count(void);
+int trgl_set_device(int device);
+int trgl_device_synchronize(void);
+
+/* ---- memory and stream helpers (so a ctypes host needs no other CUDA binding) ---- */
+int trgl_device_alloc(void** ptr, size_t bytes);
+int trgl_device_free(void* ptr);
+int trgl_host_alloc(void** ptr, size_t bytes);           /* pinned */
+int trgl_host_free(void* ptr);
+int trgl_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int trgl_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int trgl_memset_d(void* dst, int value, size_t bytes, void* stream);
+int trgl_stream_create(void** stream);
+int trgl_stream_destroy(void* stream);
+int trgl_stream_synchronize(void* stream);
+int trgl_event_create(void** event);
+int trgl_event_destroy(void* event);
+int trgl_event_record(void* event, void* stream);
+int trgl_event_elapsed_ms(void* start, void* stop, float* ms);   /* synchronises on `stop` */
+
+/* ---- the four solvers ---- */
+
+/* status: n bytes, always 1 (triangulation.c:65-83 writes none; the wrapper returns np.ones(bool)). */
+int trgl_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2,
+                   void* x, uint8_t* status, int64_t n, int mode, int mem, void* stream);
+
+/* status: n int32 in {1,0,-1,-2,-3} (triangulation.c:154-159).  semantics: TRGL_ITER_C / TRGL_ITER_PY. */
+int trgl_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2,
+                      void* x, int32_t* status, int64_t n, double tolerance, int semantics,
+                      int mode, int mem, void* stream);
+
+/* status: n bytes, max|x| <= max_coordinate_value (NaN/Inf -> 0).  rows: 4 (OpenCV >= 3) or 6 (OpenCV 2.4). */
+int trgl_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2,
+                      void* x, uint8_t* status, int64_t n, double max_coordinate_value, int rows,
+                      int mode, int mem, void* stream);
+
+/* Hartley-Sturm correction with F derived from P1,P2 (triangulation.py:211-216), then linear_eigen.
+ * u1_corr/u2_corr (n,2, dtype of u) may be NULL; when given they receive the corrected matches.
+ * all_nan (host int*, may be NULL): set to 1 when every corrected point is NaN, i.e. when the reference would
+ * take its findFundamentalMat fallback (triangulation.py:227-229); the caller then re-runs with
+ * trgl_polynomial_F.  Writing all_nan synchronises the stream. */
+int trgl_polynomial(const void* u1, const void* u2, const double* P1, const double* P2,
+                    void* x, uint8_t* status, void* u1_corr, void* u2_corr, int* all_nan, int64_t n,
+                    double max_coordinate_value, int rows, int mode, int mem, void* stream);
+
+/* Same with an explicit fundamental matrix F (9 doubles, row-major, x2^T F x1 = 0). */
+int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const double* P2, const double* F,
+                      void* x, uint8_t* status, void* u1_corr, void* u2_corr, int* all_nan, int64_t n,
+                      double max_coordinate_value, int rows, int mode, int mem, void* stream);
+
+/* Whole-batch normalised 8-point F (cv2.findFundamentalMat(u1,u2,FM_8POINT), triangulation.py:228): device
+ * reductions of the moments and of the 9x9 normal matrix, tiny eigen-solve on the host.  F: 9 doubles out (host).
+ * Only the element type of u is taken from `mode`.  Synchronises. */
+int trgl_fundamental_8point(const void* u1, const void* u2, int64_t n, int mode, int mem, double* F, void* stream);
+
+/* ---- fused reprojection error / good-point mask ---- */
+
+/* cv2.projectPoints(x, rvec, tvec, K, dist) then sum of squared residuals against imgp (n,2).
+ * K: 9 doubles row-major; dist: 5 doubles (k1,k2,p1,p2,k3); rvec,tvec: 3 doubles (all host).
+ * x_is_f32 / img_is_f32 select the element type of x and of imgp/proj.  proj (n,2) may be NULL.
+ * sums (host, 3 doubles): sum dx^2, sum dy^2, count of finite residuals; rms = sqrt((s0+s1)/n)
+ * (calibration_tools.py:124 divides by the number of points).  abs_sums (host, 2 doubles, may be NULL):
+ * sum |dx|, sum |dy| for reprojection_error_ext (calibration_tools.py:107).  Synchronises the stream. */
+int trgl_reproj_error(const void* x, const void* imgp, const double* K, const double* dist,
+                      const double* rvec, const double* tvec, void* proj, double* sums, double* abs_sums,
+                      int64_t n, int x_is_f32, int img_is_f32, int mem, void* stream);
+
+/* Two-view evaluation right after a solver call: re-project x through P1 and P2 (normalised cameras),
+ * per-point squared reprojection errors against u1,u2 (err1, err2: n elements of x's dtype, may be NULL),
+ * good[i] = (status[i] > min_status) && err1[i] <= max_sq_err && err2[i] <= max_sq_err && both depths > 0
+ * (good: n bytes, may be NULL).  status may be uint8 (status_is_i32 = 0) or int32.
+ * sums (host, 4 doubles): sum err1, sum err2 over good points, number of good points, number of points with
+ * status > min_status.  Synchronises the stream. */
+int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double* P1, const double* P2,
+                     const void* status, int status_is_i32, int min_status, double max_sq_err,
+                     void* err1, void* err2, uint8_t* good, double* sums,
+                     int64_t n, int mode, int mem, void* stream);
+
+/* ---- bench / diagnostics ---- */
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t trgl_launch_count(void);
+/* Tuning knob: points per thread of the streaming solvers (1, 2 or 4); returns the previous value. */
+int trgl_set_points_per_thread(int ppt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

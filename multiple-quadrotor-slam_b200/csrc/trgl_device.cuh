@@ -1,0 +1,291 @@
+// Device-side building blocks shared by every solver kernel of libtriangl_cuda (sm_100a).
+//
+// Layout in HBM (reference layout, triangulation_c/triangulation.c:27-28,42):
+//   u1,u2 : (n,2) row-major  -> one 16-byte (f64) / 8-byte (f32) vector load per point, coalesced
+//   x     : (n,3) row-major  -> staged per warp in shared memory, written as 3 fully coalesced rows
+//   status: (n,) uint8 / int32
+// Camera matrices travel as kernel parameters (constant bank), already converted to the compute type.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace trgl {
+
+template <typename T> struct Cams { T P1[12]; T P2[12]; };
+
+template <typename T> struct Num;
+template <> struct Num<double> {
+    static __device__ __forceinline__ double eps() { return 2.220446049250313e-16; }
+    static __device__ __forceinline__ double tiny() { return 2.2250738585072014e-308; }
+    static __device__ __forceinline__ double big() { return 1.7976931348623157e308; }
+};
+template <> struct Num<float> {
+    static __device__ __forceinline__ float eps() { return 1.1920929e-07f; }
+    static __device__ __forceinline__ float tiny() { return 1.17549435e-38f; }
+    static __device__ __forceinline__ float big() { return 3.402823466e38f; }
+};
+
+__device__ __forceinline__ double tfma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float tfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double tsqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float tsqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double tabs(double a) { return fabs(a); }
+__device__ __forceinline__ float tabs(float a) { return fabsf(a); }
+__device__ __forceinline__ double tmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float tmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double tmin(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float tmin(float a, float b) { return fminf(a, b); }
+
+// ---- streaming loads of one (x,y) pair, converted to the compute type -------------------------------------
+template <typename TC>
+__device__ __forceinline__ void load_uv(const double* __restrict__ u, int64_t i, TC& x, TC& y) {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(u) + i);
+    x = static_cast<TC>(v.x); y = static_cast<TC>(v.y);
+}
+template <typename TC>
+__device__ __forceinline__ void load_uv(const float* __restrict__ u, int64_t i, TC& x, TC& y) {
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(u) + i);
+    x = static_cast<TC>(v.x); y = static_cast<TC>(v.y);
+}
+__device__ __forceinline__ void store_uv(double* __restrict__ u, int64_t i, double x, double y) {
+    __stcs(reinterpret_cast<double2*>(u) + i, make_double2(x, y));
+}
+__device__ __forceinline__ void store_uv(float* __restrict__ u, int64_t i, double x, double y) {
+    __stcs(reinterpret_cast<float2*>(u) + i, make_float2(static_cast<float>(x), static_cast<float>(y)));
+}
+__device__ __forceinline__ void store_uv(float* __restrict__ u, int64_t i, float x, float y) {
+    __stcs(reinterpret_cast<float2*>(u) + i, make_float2(x, y));
+}
+
+// ---- coalesced store of the (n,3) AoS result ---------------------------------------------------------------
+// Each warp owns 32 consecutive points starting at warp_base.  The 96 scalars are transposed through a per-warp
+// shared-memory row (stride-3 writes are bank-conflict free) and leave as three 32-wide contiguous stores.
+template <typename TO>
+__device__ __forceinline__ void store_x_warp(TO* __restrict__ xout, int64_t warp_base, int64_t n,
+                                             TO x0, TO x1, TO x2, TO* __restrict__ stage /* [96] of this warp */) {
+    const int lane = threadIdx.x & 31;
+    stage[lane * 3 + 0] = x0;
+    stage[lane * 3 + 1] = x1;
+    stage[lane * 3 + 2] = x2;
+    __syncwarp();
+    const int64_t left = n - warp_base;
+    const int cnt = left >= 32 ? 96 : (left > 0 ? static_cast<int>(left) * 3 : 0);
+    TO* __restrict__ dst = xout + warp_base * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int idx = k * 32 + lane;
+        if (idx < cnt) __stcs(dst + idx, stage[idx]);
+    }
+    __syncwarp();
+}
+
+// ---- rows of the DLT system ---------------------------------------------------------------------------------
+// r0 = ux*P[2,:] - P[0,:], r1 = uy*P[2,:] - P[1,:]   (triangulation.c:30-40; column 3 is -b)
+template <typename T>
+__device__ __forceinline__ void dlt_rows(const T* __restrict__ P, T ux, T uy, T r0[4], T r1[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r0[k] = tfma(ux, P[8 + k], -P[k]);
+        r1[k] = tfma(uy, P[8 + k], -P[4 + k]);
+    }
+}
+
+// Normal-equation accumulators of two rows:  M (6 unique, order 00 01 02 11 12 22) += r^T r,  v += r^T b, b = -r[3].
+template <typename T>
+__device__ __forceinline__ void normal_acc2(const T r0[4], const T r1[4], T M[6], T v[3]) {
+    M[0] = tfma(r1[0], r1[0], r0[0] * r0[0]);
+    M[1] = tfma(r1[0], r1[1], r0[0] * r0[1]);
+    M[2] = tfma(r1[0], r1[2], r0[0] * r0[2]);
+    M[3] = tfma(r1[1], r1[1], r0[1] * r0[1]);
+    M[4] = tfma(r1[1], r1[2], r0[1] * r0[2]);
+    M[5] = tfma(r1[2], r1[2], r0[2] * r0[2]);
+    v[0] = -tfma(r1[0], r1[3], r0[0] * r0[3]);
+    v[1] = -tfma(r1[1], r1[3], r0[1] * r0[3]);
+    v[2] = -tfma(r1[2], r1[3], r0[2] * r0[3]);
+}
+
+// x = adj(M) v / det(M) for the symmetric 3x3 M; returns det and the cofactors for reuse by the refinement step.
+template <typename T>
+__device__ __forceinline__ T sym3_cofactors(const T M[6], T C[6]) {
+    C[0] = tfma(M[3], M[5], -M[4] * M[4]);
+    C[1] = tfma(M[2], M[4], -M[1] * M[5]);
+    C[2] = tfma(M[1], M[4], -M[2] * M[3]);
+    C[3] = tfma(M[0], M[5], -M[2] * M[2]);
+    C[4] = tfma(M[1], M[2], -M[0] * M[4]);
+    C[5] = tfma(M[0], M[3], -M[1] * M[1]);
+    return tfma(M[0], C[0], tfma(M[1], C[1], M[2] * C[2]));
+}
+template <typename T>
+__device__ __forceinline__ void sym3_apply(const T C[6], const T v[3], T s, T x[3]) {
+    x[0] = s * tfma(C[0], v[0], tfma(C[1], v[1], C[2] * v[2]));
+    x[1] = s * tfma(C[1], v[0], tfma(C[3], v[1], C[4] * v[2]));
+    x[2] = s * tfma(C[2], v[0], tfma(C[4], v[1], C[5] * v[2]));
+}
+
+// ---- one-sided (Hestenes) Jacobi SVD, M rows x N columns, everything in registers -----------------------------
+// After the call the columns of A are U*diag(w) and the columns of V the right singular vectors (unsorted).
+// Same rotation formulas as a classical Jacobi SVD so near-degenerate cases behave like cvSolve/cv::SVD.
+template <typename T, int M, int N>
+__device__ __forceinline__ void jacobi_svd(T A[M][N], T V[N][N], int max_sweeps = 30) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) V[i][j] = (i == j) ? T(1) : T(0);
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i) {
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) {
+                T a = 0, b = 0, p = 0;
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    a = tfma(A[k][i], A[k][i], a);
+                    b = tfma(A[k][j], A[k][j], b);
+                    p = tfma(A[k][i], A[k][j], p);
+                }
+                if (!(tabs(p) > Num<T>::eps() * tsqrt(a * b))) continue;      // also skips NaN
+                changed = true;
+                p *= T(2);
+                const T beta = a - b;
+                const T gamma = tsqrt(tfma(p, p, beta * beta));
+                T c, s;
+                if (beta < 0) {
+                    const T delta = (gamma - beta) * T(0.5);
+                    s = tsqrt(delta / gamma);
+                    c = p / (gamma * s * T(2));
+                } else {
+                    c = tsqrt((gamma + beta) / (gamma * T(2)));
+                    s = p / (gamma * c * T(2));
+                }
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    const T t0 = tfma(c, A[k][i], s * A[k][j]);
+                    const T t1 = tfma(c, A[k][j], -s * A[k][i]);
+                    A[k][i] = t0; A[k][j] = t1;
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const T t0 = tfma(c, V[k][i], s * V[k][j]);
+                    const T t1 = tfma(c, V[k][j], -s * V[k][i]);
+                    V[k][i] = t0; V[k][j] = t1;
+                }
+            }
+        }
+        if (!changed) break;
+    }
+}
+
+// Minimum-norm least squares of the 4x3 system rows[r][0..2] x = -rows[r][3] with OpenCV's SVD back-substitution
+// rule (singular values <= 2*eps*sum(w) are dropped) -- the rank-revealing path behind cvSolve(DECOMP_SVD),
+// call sites triangulation.c:81,130.  Kept out of line: it is the rare path.
+template <typename T>
+__device__ __noinline__ void solve4x3_svd(const T rows[4][4], T x[3]) {
+    T A[4][3], V[3][3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) A[r][k] = rows[r][k];
+    jacobi_svd<T, 4, 3>(A, V);
+    T w2[3], utb[3], wsum = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        T s = 0, d = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { s = tfma(A[r][j], A[r][j], s); d = tfma(A[r][j], -rows[r][3], d); }
+        w2[j] = s; utb[j] = d; wsum += tsqrt(s);
+    }
+    const T thr = T(2) * Num<T>::eps() * wsum;
+    x[0] = x[1] = x[2] = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const T w = tsqrt(w2[j]);
+        // NaN systems: w is NaN, the comparison is false and the NaN must still propagate like cvSolve's output
+        const T coef = (w > thr) ? utb[j] / w2[j] : ((w == w) ? T(0) : w);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x[k] = tfma(V[k][j], coef, x[k]);
+    }
+}
+
+// Conditioning tiers of the normal-equation solve.  kappa^2(A) <= tr(M)^3 / (4 det(M)); tier 1: plain
+// adjugate solve (error ~ kappa^2 eps); tier 2: + one refinement step on the residual (error ~ kappa eps);
+// tier 3: Jacobi SVD with the reference's rank rule.
+template <typename T> struct Tiers;
+template <> struct Tiers<double> {
+    static __device__ __forceinline__ double t1() { return 4.0 * 2.0e4; }
+    static __device__ __forceinline__ double t2() { return 4.0 * 1.0e10; }
+};
+template <> struct Tiers<float> {
+    static __device__ __forceinline__ float t1() { return 0.0f; }            // always refine in fp32
+    static __device__ __forceinline__ float t2() { return 4.0f * 3.0e3f; }
+};
+
+__device__ void solve4x3_f64_full(const double rows[4][4], double x[3]);
+
+// Solve the weighted system  diag(w1,w1,w2,w2) rows  in the least-squares / min-norm sense.
+// M1,v1 / M2,v2: normal-equation blocks of camera 1 / camera 2 (unweighted), W1 = w1^2, W2 = w2^2.
+template <typename T>
+__device__ __forceinline__ void solve_weighted(const T rows[4][4], const T M1[6], const T v1[3], const T M2[6],
+                                               const T v2[3], T w1, T w2, T x[3]) {
+    const T W1 = w1 * w1, W2 = w2 * w2;
+    T M[6], v[3], C[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) M[k] = tfma(W1, M1[k], W2 * M2[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = tfma(W1, v1[k], W2 * v2[k]);
+    const T det = sym3_cofactors(M, C);
+    const T tr = M[0] + M[3] + M[5];
+    const T tr3 = tr * tr * tr;
+    const T inv = T(1) / det;
+    sym3_apply(C, v, inv, x);
+    if (!(tr3 < Tiers<T>::t1() * det)) {
+        if (tr3 < Tiers<T>::t2() * det) {
+            // r = W (b - A x) per row, g = A^T W r, x += M^-1 g
+            T g[3] = {0, 0, 0};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const T Wr = (r < 2) ? W1 : W2;
+                T res = -rows[r][3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) res = tfma(-rows[r][k], x[k], res);
+                res *= Wr;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g[k] = tfma(rows[r][k], res, g[k]);
+            }
+            T dx[3];
+            sym3_apply(C, g, inv, dx);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x[k] += dx[k];
+        } else {
+            if constexpr (sizeof(T) == 8) {
+                T wr[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) wr[r][k] = rows[r][k] * ((r < 2) ? w1 : w2);
+                solve4x3_svd<T>(wr, x);
+            } else {
+                // FP32 mode: ill-conditioned points are redone in double (rare path, keeps the 1e-4 bound)
+                double wr[4][4], xd[3];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        wr[r][k] = static_cast<double>(rows[r][k]) * static_cast<double>((r < 2) ? w1 : w2);
+                solve4x3_f64_full(wr, xd);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) x[k] = static_cast<T>(xd[k]);
+            }
+        }
+    }
+}
+
+// Out-of-line double-precision solve of an explicit 4x3 system (all tiers); used by the FP32-mode kernels.
+__device__ __noinline__ void solve4x3_f64_full(const double rows[4][4], double x[3]) {
+    double M1[6], v1[3], M2[6], v2[3];
+    normal_acc2<double>(rows[0], rows[1], M1, v1);
+    normal_acc2<double>(rows[2], rows[3], M2, v2);
+    solve_weighted<double>(rows, M1, v1, M2, v2, 1.0, 1.0, x);
+}
+
+}  // namespace trgl

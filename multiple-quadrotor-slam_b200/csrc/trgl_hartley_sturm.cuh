@@ -1,0 +1,215 @@
+// Hartley-Sturm optimal correction of one correspondence (what cv2.correctMatches computes per point;
+// call site Work/python_libs/triangulation.py:224, algorithm H&Z 12.1 / SURVEY.md Appendix A.10), in registers.
+//
+// Root selection.  The reference evaluates the cost s(t) at the real part of all six roots of the degree-6
+// polynomial g(t) (numerator of s'(t)) and at t = inf, and keeps the minimiser; i.e. it returns the GLOBAL
+// minimiser of s over the reals.  We get the same t two ways:
+//   fast path  -- s(t) >= t^2/(1+f1^2 t^2), so every t with s(t) <= s(0) lies in |t| < T0 with
+//                 T0^2 = s(0)/(1 - f1^2 s(0)); if an interval bound shows g' > 0 on [-T0,T0] then g has exactly one
+//                 root there, it is the global minimiser, and a bracketed Newton iteration from t = 0 finds it
+//                 (2-5 iterations).  This certificate holds for every point of the sideways / rotating / general
+//                 rigs and for most points of the forward-motion rig.
+//   slow path  -- otherwise: Durand-Kerner on all six complex roots exactly as cv::solvePoly is driven by
+//                 correctMatches (leading coefficients <= DBL_EPSILON dropped, start (1+i)^k, Gauss-Seidel sweeps,
+//                 <= 100 iterations), then the reference's cost scan over the real parts.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+
+namespace trgl {
+
+struct HSParams {
+    double F[9];    // row-major, x2^T F x1 = 0
+    double e1[3];   // right epipole, F e1 = 0
+    double e2[3];   // left epipole, F^T e2 = 0
+};
+
+__device__ __forceinline__ double hs_cost(double t, double a, double b, double c, double d, double f1, double f2) {
+    const double ct_d = fma(c, t, d), at_b = fma(a, t, b);
+    return t * t / fma(f1 * f1 * t, t, 1.0) + ct_d * ct_d / fma(at_b, at_b, f2 * f2 * ct_d * ct_d);
+}
+
+// k[0..6] ascending:  g(t) = t q(t)^2 - (ad-bc) (1+f1^2 t^2)^2 (at+b)(ct+d),  q = (at+b)^2 + f2^2 (ct+d)^2
+__device__ __forceinline__ void hs_coeffs(double a, double b, double c, double d, double f1, double f2, double k[7]) {
+    const double f1s = f1 * f1, f2s = f2 * f2;
+    const double q2 = fma(a, a, f2s * c * c), q1 = 2.0 * fma(a, b, f2s * c * d), q0 = fma(b, b, f2s * d * d);
+    const double e = fma(a, d, -b * c);
+    const double r2 = a * c, r1 = fma(a, d, b * c), r0 = b * d;
+    const double w2 = 2.0 * f1s, w4 = f1s * f1s;
+    k[0] = -e * r0;
+    k[1] = fma(q0, q0, -e * r1);
+    k[2] = fma(2.0 * q0, q1, -e * fma(w2, r0, r2));
+    k[3] = fma(q1, q1, 2.0 * q0 * q2) - e * (w2 * r1);
+    k[4] = fma(2.0 * q1, q2, -e * fma(w2, r2, w4 * r0));
+    k[5] = fma(q2, q2, -e * (w4 * r1));
+    k[6] = -e * (w4 * r2);
+}
+
+// Durand-Kerner + cost scan, restating cv::solvePoly(maxIters=100) and the selection loop of correctMatches.
+// Returns t_min, or DBL_MAX when t = inf has the lowest cost.
+__device__ __noinline__ double hs_select_dk(const double k[7], double a, double b, double c, double d,
+                                            double f1, double f2) {
+    int n = 6;
+    if (!(fabs(k[6]) > DBL_EPSILON)) { n = 5;
+      if (!(fabs(k[5]) > DBL_EPSILON)) { n = 4;
+        if (!(fabs(k[4]) > DBL_EPSILON)) { n = 3;
+          if (!(fabs(k[3]) > DBL_EPSILON)) { n = 2;
+            if (!(fabs(k[2]) > DBL_EPSILON)) n = 1; } } } }
+    double kk[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) kk[i] = (i <= n) ? k[i] : 0.0;
+    const double lead = n == 6 ? k[6] : n == 5 ? k[5] : n == 4 ? k[4] : n == 3 ? k[3] : n == 2 ? k[2] : k[1];
+    double zr[6], zi[6];
+    {
+        double pr = 1.0, pi = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            zr[i] = pr; zi[i] = pi;
+            const double nr = pr - pi, ni = pr + pi;      // * (1 + i)
+            pr = nr; pi = ni;
+        }
+    }
+    for (int iter = 0; iter < 100; ++iter) {
+        double maxdiff = 0.0;
+        bool settled = true;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i < n) {
+                const double pr = zr[i], pi = zi[i];
+                double nr = 0.0, ni = 0.0;                  // Horner over all 7 slots (leading slots are 0)
+#pragma unroll
+                for (int j = 6; j >= 0; --j) {
+                    const double tr = fma(nr, pr, -ni * pi) + kk[j];
+                    const double ti = fma(nr, pi, ni * pr);
+                    nr = tr; ni = ti;
+                }
+                double dr = lead, di = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    if (j != i && j < n) {
+                        const double er = pr - zr[j], ei = pi - zi[j];
+                        if (er != 0.0 || ei != 0.0) {
+                            const double tr = fma(dr, er, -di * ei);
+                            const double ti = fma(dr, ei, di * er);
+                            dr = tr; di = ti;
+                        }
+                    }
+                }
+                const double den = fma(dr, dr, di * di);
+                const double sr = fma(nr, dr, ni * di) / den;
+                const double si = fma(ni, dr, -nr * di) / den;
+                zr[i] = pr - sr; zi[i] = pi - si;
+                const double mag = sqrt(fma(sr, sr, si * si));
+                maxdiff = fmax(maxdiff, mag);
+                if (mag > 2.5e-16 * (fabs(zr[i]) + fabs(zi[i]))) settled = false;
+            }
+        }
+        if (!(maxdiff > 0.0) || settled) break;          // NaN-safe; `settled` only skips no-op sweeps
+    }
+    double s_val = 1.0 / (f1 * f1) + c * c / fma(a, a, f2 * f2 * c * c);
+    double t_min = DBL_MAX;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        if (i < n) {
+            const double s = hs_cost(zr[i], a, b, c, d, f1, f2);
+            if (s < s_val) { s_val = s; t_min = zr[i]; }
+        }
+    }
+    return t_min;
+}
+
+__device__ __forceinline__ void hs_epipole(const double e[3], double x, double y, double& ex, double& ey, double& f) {
+    ex = fma(-x, e[2], e[0]);
+    ey = fma(-y, e[2], e[1]);
+    f = e[2];
+    const double inv = 1.0 / sqrt(fma(ex, ex, ey * ey));
+    ex *= inv; ey *= inv; f *= inv;
+    if (f < 0.0) { ex = -ex; ey = -ey; f = -f; }
+}
+
+__device__ __forceinline__ void hs_correct(const HSParams& hs, double x1, double y1, double x2, double y2,
+                                           double& n1x, double& n1y, double& n2x, double& n2y) {
+    const double* F = hs.F;
+    // F' = T2^-T F T1^-1  (both points moved to the origin)
+    double Fp[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        Fp[r][0] = F[3 * r + 0];
+        Fp[r][1] = F[3 * r + 1];
+        Fp[r][2] = fma(F[3 * r + 0], x1, fma(F[3 * r + 1], y1, F[3 * r + 2]));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Fp[2][k] = fma(x2, Fp[0][k], fma(y2, Fp[1][k], Fp[2][k]));
+    // epipoles of F' are the translated epipoles of F
+    double e1x, e1y, f1, e2x, e2y, f2;
+    hs_epipole(hs.e1, x1, y1, e1x, e1y, f1);
+    hs_epipole(hs.e2, x2, y2, e2x, e2y, f2);
+    // F'' = R2 F' R1^T, entries (1,1) (1,2) (2,1) (2,2)
+    const double h01 = fma(-Fp[0][0], e1y, Fp[0][1] * e1x);
+    const double h11 = fma(-Fp[1][0], e1y, Fp[1][1] * e1x);
+    const double h21 = fma(-Fp[2][0], e1y, Fp[2][1] * e1x);
+    const double a = fma(-e2y, h01, e2x * h11);
+    const double b = fma(-e2y, Fp[0][2], e2x * Fp[1][2]);
+    const double c = h21;
+    const double d = Fp[2][2];
+    double k[7];
+    hs_coeffs(a, b, c, d, f1, f2, k);
+
+    double t;
+    bool finite_coeffs = true;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) finite_coeffs = finite_coeffs && (fabs(k[i]) <= DBL_MAX);
+    // ---- fast path certificate ----
+    const double s0 = d * d / fma(b, b, f2 * f2 * d * d);
+    const double f1s = f1 * f1;
+    bool fast = finite_coeffs && (f1s * s0 < 1.0);
+    double T0 = 0.0;
+    if (fast) {
+        T0 = sqrt(s0 / (1.0 - f1s * s0));
+        const double bound = T0 * fma(T0, fma(T0, fma(T0, fma(T0, 6.0 * fabs(k[6]), 5.0 * fabs(k[5])),
+                                                      4.0 * fabs(k[4])), 3.0 * fabs(k[3])), 2.0 * fabs(k[2]));
+        fast = k[1] > bound;
+    }
+    if (fast) {
+        double lo = -T0, hi = T0;
+        t = 0.0;
+        for (int it = 0; it < 100; ++it) {
+            double g = k[6], dg = 0.0;
+#pragma unroll
+            for (int i = 5; i >= 0; --i) { dg = fma(dg, t, g); g = fma(g, t, k[i]); }
+            if (g == 0.0) break;
+            if (g < 0.0) lo = t; else hi = t;
+            double tn = t - g / dg;
+            if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
+            const double step = fabs(tn - t);
+            t = tn;
+            if (step <= 4e-16 * fabs(tn) || (hi - lo) <= 4e-16 * fabs(tn)) break;
+        }
+    } else if (finite_coeffs) {
+        t = hs_select_dk(k, a, b, c, d, f1, f2);
+    } else {
+        t = DBL_MAX;
+    }
+    if (t == DBL_MAX) {
+        // t = inf wins (or non-finite system): the reference evaluates inf/inf -> NaN for both points
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        n1x = n1y = n2x = n2y = qnan;
+        return;
+    }
+    // closest points to the origin on the two epipolar lines, then back through R^T and T^-1
+    {
+        const double hz = fma(t * t, f1s, 1.0);
+        const double hx = t * t * f1 / hz, hy = t / hz;
+        n1x = fma(e1x, hx, -e1y * hy) + x1;
+        n1y = fma(e1y, hx, e1x * hy) + y1;
+    }
+    {
+        const double ct_d = fma(c, t, d), at_b = fma(a, t, b);
+        const double hz = fma(f2 * f2 * ct_d, ct_d, at_b * at_b);
+        const double hx = f2 * ct_d * ct_d / hz, hy = -at_b * ct_d / hz;
+        n2x = fma(e2x, hx, -e2y * hy) + x2;
+        n2y = fma(e2y, hx, e2x * hy) + y2;
+    }
+}
+
+}  // namespace trgl

@@ -1,0 +1,189 @@
+// __global__ kernels of libtriangl_cuda: one thread per correspondence, PPT correspondences per thread issued
+// back to back so that several 16-byte loads are in flight per thread (memory-level parallelism on HBM3e).
+#pragma once
+#include "trgl_device.cuh"
+#include "trgl_hartley_sturm.cuh"
+
+namespace trgl {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// ---- linear_LS_triangulation (triangulation.c:65-83) -----------------------------------------------------------
+template <typename TI, typename TC, typename TO, int PPT>
+__global__ void __launch_bounds__(kThreads)
+k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC> cams,
+            TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n) {
+    __shared__ TO stage[kWarps][96];
+    const int warp = threadIdx.x >> 5;
+    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT);
+    TC in[PPT][4];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const int64_t i = block_base + p * kThreads + threadIdx.x;
+        if (i < n) {
+            load_uv<TC>(u1, i, in[p][0], in[p][1]);
+            load_uv<TC>(u2, i, in[p][2], in[p][3]);
+        } else {
+            in[p][0] = in[p][1] = in[p][2] = in[p][3] = TC(0);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const int64_t i = block_base + p * kThreads + threadIdx.x;
+        TC rows[4][4], M1[6], v1[3], M2[6], v2[3], xs[3];
+        dlt_rows<TC>(cams.P1, in[p][0], in[p][1], rows[0], rows[1]);
+        dlt_rows<TC>(cams.P2, in[p][2], in[p][3], rows[2], rows[3]);
+        normal_acc2<TC>(rows[0], rows[1], M1, v1);
+        normal_acc2<TC>(rows[2], rows[3], M2, v2);
+        solve_weighted<TC>(rows, M1, v1, M2, v2, TC(1), TC(1), xs);
+        store_x_warp<TO>(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
+                         static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage[warp]);
+        if (i < n) status[i] = 1;
+    }
+}
+
+// ---- iterative_LS_triangulation (triangulation.c:104-161 / triangulation.py:100-195) ---------------------------
+template <typename TI, typename TC, typename TO, int PPT>
+__global__ void __launch_bounds__(kThreads)
+k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC> cams,
+               TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
+               const TC tolerance, const int py_semantics) {
+    __shared__ TO stage[kWarps][96];
+    const int warp = threadIdx.x >> 5;
+    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT);
+    TC in[PPT][4];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const int64_t i = block_base + p * kThreads + threadIdx.x;
+        if (i < n) {
+            load_uv<TC>(u1, i, in[p][0], in[p][1]);
+            load_uv<TC>(u2, i, in[p][2], in[p][3]);
+        } else {
+            in[p][0] = in[p][1] = in[p][2] = in[p][3] = TC(0);
+        }
+    }
+#pragma unroll 1
+    for (int p = 0; p < PPT; ++p) {
+        const int64_t i = block_base + p * kThreads + threadIdx.x;
+        TC rows[4][4], M1[6], v1[3], M2[6], v2[3], xs[3];
+        dlt_rows<TC>(cams.P1, in[p][0], in[p][1], rows[0], rows[1]);
+        dlt_rows<TC>(cams.P2, in[p][2], in[p][3], rows[2], rows[3]);
+        normal_acc2<TC>(rows[0], rows[1], M1, v1);
+        normal_acc2<TC>(rows[2], rows[3], M2, v2);
+        TC w1 = 1, w2 = 1, d1 = 1, d2 = 1, d1n = 1, d2n = 1;
+        int it = py_semantics ? 9 : 10;         // value of the loop variable after a loop that never breaks
+#pragma unroll 1
+        for (int k = 0; k < 10; ++k) {
+            solve_weighted<TC>(rows, M1, v1, M2, v2, w1, w2, xs);
+            d1n = tfma(cams.P1[8], xs[0], tfma(cams.P1[9], xs[1], tfma(cams.P1[10], xs[2], cams.P1[11])));
+            d2n = tfma(cams.P2[8], xs[0], tfma(cams.P2[9], xs[1], tfma(cams.P2[10], xs[2], cams.P2[11])));
+            const bool conv = (tabs(d1n - d1) <= tolerance) && (tabs(d2n - d2) <= tolerance);
+            const bool zero = !py_semantics && ((d1n == TC(0)) || (d2n == TC(0)));       // triangulation.c:138
+            if (conv || zero) { it = k; break; }
+            w1 *= TC(1) / d1n;                   // cumulative re-weighting, triangulation.c:143-146
+            w2 *= TC(1) / d2n;
+            d1 = d1n; d2 = d2n;
+        }
+        int st = (it < 10) && (d1n > TC(0)) && (d2n > TC(0));
+        if (d1n <= TC(0)) st -= 1;
+        if (d2n <= TC(0)) st -= 2;
+        store_x_warp<TO>(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
+                         static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage[warp]);
+        if (i < n) status[i] = st;
+    }
+}
+
+// ---- linear_eigen_triangulation (triangulation.py:6-25) --------------------------------------------------------
+// Smallest right singular vector of the ROWS x 4 DLT matrix, dehomogenised, with the finite-coordinates mask.
+template <typename TC, int ROWS>
+__device__ __forceinline__ void eigen_point(const Cams<TC>& cams, TC u1x, TC u1y, TC u2x, TC u2y,
+                                            TC max_coord, TC xs[3], bool& good) {
+    TC B[ROWS][4], V[4][4];
+    constexpr int per = ROWS / 2;
+    dlt_rows<TC>(cams.P1, u1x, u1y, B[0], B[1]);
+    dlt_rows<TC>(cams.P2, u2x, u2y, B[per], B[per + 1]);
+    if constexpr (ROWS == 6) {       // OpenCV 2.4 adds x*P[1,:] - y*P[0,:] per view
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            B[2][k] = tfma(u1x, cams.P1[4 + k], -u1y * cams.P1[k]);
+            B[5][k] = tfma(u2x, cams.P2[4 + k], -u2y * cams.P2[k]);
+        }
+    }
+    jacobi_svd<TC, ROWS, 4>(B, V);
+    TC best = 0, X[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        TC s = 0;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) s = tfma(B[r][j], B[r][j], s);
+        if (j == 0 || s < best || !(s == s)) {          // smallest column norm; a NaN system yields a NaN point
+            best = s;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) X[k] = (s == s) ? V[k][j] : s;
+        }
+    }
+    const TC inv = TC(1) / X[3];
+    xs[0] = X[0] * inv; xs[1] = X[1] * inv; xs[2] = X[2] * inv;        // triangulation.py:22 (Inf/NaN when w == 0)
+    const TC m = tmax(tmax(tabs(xs[0]), tabs(xs[1])), tabs(xs[2]));
+    good = (xs[0] == xs[0]) && (xs[1] == xs[1]) && (xs[2] == xs[2]) && (m <= max_coord);   // NaN -> False, :23
+}
+
+template <typename TI, typename TC, typename TO, int ROWS>
+__global__ void __launch_bounds__(kThreads)
+k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC> cams,
+               TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord) {
+    __shared__ TO stage[kWarps][96];
+    const int warp = threadIdx.x >> 5;
+    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * kThreads;
+    const int64_t i = block_base + threadIdx.x;
+    TC a = 0, b = 0, c = 0, d = 0;
+    if (i < n) { load_uv<TC>(u1, i, a, b); load_uv<TC>(u2, i, c, d); }
+    TC xs[3]; bool good;
+    eigen_point<TC, ROWS>(cams, a, b, c, d, max_coord, xs, good);
+    store_x_warp<TO>(x, block_base + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+                     static_cast<TO>(xs[2]), stage[warp]);
+    if (i < n) status[i] = good ? 1 : 0;
+}
+
+// ---- polynomial_triangulation (triangulation.py:198-232) -------------------------------------------------------
+// Hartley-Sturm correction of the match (cv2.correctMatches) followed by the linear-eigen solve, fused.
+template <typename TI, typename TC, typename TO, int ROWS>
+__global__ void __launch_bounds__(kThreads)
+k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC> cams, const HSParams hs,
+             TO* __restrict__ x, uint8_t* __restrict__ status, TI* __restrict__ u1c, TI* __restrict__ u2c,
+             unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord) {
+    __shared__ TO stage[kWarps][96];
+    const int warp = threadIdx.x >> 5;
+    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * kThreads;
+    const int64_t i = block_base + threadIdx.x;
+    TC a = 0, b = 0, c = 0, d = 0;
+    if (i < n) { load_uv<TC>(u1, i, a, b); load_uv<TC>(u2, i, c, d); }
+    // The correction always runs in double: the degree-6 coefficients span many orders of magnitude.
+    double n1x, n1y, n2x, n2y;
+    hs_correct(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c), static_cast<double>(d),
+               n1x, n1y, n2x, n2y);
+    // cv2.correctMatches returns the dtype of its input, so the corrected points are rounded to TI
+    // before the triangulation (triangulation.py:224,232).
+    const TI r1x = static_cast<TI>(n1x), r1y = static_cast<TI>(n1y), r2x = static_cast<TI>(n2x), r2y = static_cast<TI>(n2y);
+    if (i < n) {
+        if (u1c) store_uv(u1c, i, r1x, r1y);
+        if (u2c) store_uv(u2c, i, r2x, r2y);
+    }
+    const bool finite1 = !(n1x != n1x) || !(n1y != n1y);     // "not all NaN" bookkeeping for the fallback test
+    const bool finite2 = !(n2x != n2x) || !(n2y != n2y);
+    const unsigned m1 = __ballot_sync(0xffffffffu, (i < n) && finite1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, (i < n) && finite2);
+    if ((threadIdx.x & 31) == 0) {
+        if (m1) atomicOr(&not_nan_count[0], 1u);
+        if (m2) atomicOr(&not_nan_count[1], 1u);
+    }
+    TC xs[3]; bool good;
+    eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
+                          static_cast<TC>(r2y), max_coord, xs, good);
+    store_x_warp<TO>(x, block_base + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+                     static_cast<TO>(xs[2]), stage[warp]);
+    if (i < n) status[i] = good ? 1 : 0;
+}
+
+}  // namespace trgl

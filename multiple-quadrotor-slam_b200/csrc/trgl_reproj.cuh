@@ -1,0 +1,170 @@
+// Fused reprojection-error kernels (grid-stride, deterministic two-stage reduction: warp shuffles -> per-block
+// partial sums in global memory -> ordered sum on the host).
+//   k_reproj_error : cv2.projectPoints + squared residuals      (calibration_tools.py:116-124, :89-113)
+//   k_pair_reproj  : both normalised cameras + good-point mask  (triangulation_comparison.py:190-217,242-260;
+//                    slam2.py:556,589 status filters)
+#pragma once
+#include "trgl_device.cuh"
+#include <cmath>
+
+namespace trgl {
+
+constexpr int kReduceBlocks = 148 * 4;
+
+struct ProjParams {
+    double R[9], t[3];
+    double fx, fy, cx, cy;
+    double k1, k2, p1, p2, k3;
+};
+
+// cv2.Rodrigues(rvec) on the host (one 3x3 per call)
+inline ProjParams make_proj_params(const double* K, const double* dist, const double* rvec, const double* tvec) {
+    ProjParams p;
+    const double th = std::sqrt(rvec[0] * rvec[0] + rvec[1] * rvec[1] + rvec[2] * rvec[2]);
+    if (th < 2.220446049250313e-16) {
+        for (int i = 0; i < 9; ++i) p.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    } else {
+        const double kx = rvec[0] / th, ky = rvec[1] / th, kz = rvec[2] / th;
+        const double c = std::cos(th), s = std::sin(th), c1 = 1.0 - c;
+        p.R[0] = c + c1 * kx * kx;      p.R[1] = c1 * kx * ky - s * kz; p.R[2] = c1 * kx * kz + s * ky;
+        p.R[3] = c1 * kx * ky + s * kz; p.R[4] = c + c1 * ky * ky;      p.R[5] = c1 * ky * kz - s * kx;
+        p.R[6] = c1 * kx * kz - s * ky; p.R[7] = c1 * ky * kz + s * kx; p.R[8] = c + c1 * kz * kz;
+    }
+    for (int i = 0; i < 3; ++i) p.t[i] = tvec[i];
+    p.fx = K[0]; p.fy = K[4]; p.cx = K[2]; p.cy = K[5];
+    p.k1 = dist ? dist[0] : 0.0; p.k2 = dist ? dist[1] : 0.0; p.p1 = dist ? dist[2] : 0.0;
+    p.p2 = dist ? dist[3] : 0.0; p.k3 = dist ? dist[4] : 0.0;
+    return p;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ partials) {
+    __shared__ double sm[NV][kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const double s = warp_sum(v[k]);
+        if (lane == 0) sm[k][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) s += sm[threadIdx.x][w];
+        partials[blockIdx.x * NV + threadIdx.x] = s;
+    }
+}
+
+template <typename TX, typename TP>
+__global__ void __launch_bounds__(kThreads)
+k_reproj_error(const TX* __restrict__ x, const TP* __restrict__ imgp, const ProjParams pp, TP* __restrict__ proj,
+               double* __restrict__ partials, const int64_t n) {
+    double acc[5] = {0, 0, 0, 0, 0};          // sum dx^2, sum dy^2, finite count, sum |dx|, sum |dy|
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const double X = static_cast<double>(x[3 * i + 0]), Y = static_cast<double>(x[3 * i + 1]),
+                     Z = static_cast<double>(x[3 * i + 2]);
+        const double xc = fma(pp.R[0], X, fma(pp.R[1], Y, fma(pp.R[2], Z, pp.t[0])));
+        const double yc = fma(pp.R[3], X, fma(pp.R[4], Y, fma(pp.R[5], Z, pp.t[1])));
+        const double zc = fma(pp.R[6], X, fma(pp.R[7], Y, fma(pp.R[8], Z, pp.t[2])));
+        const double iz = 1.0 / zc;
+        const double a = xc * iz, b = yc * iz;
+        const double r2 = fma(a, a, b * b);
+        const double rad = fma(r2, fma(r2, fma(r2, pp.k3, pp.k2), pp.k1), 1.0);
+        const double xd = fma(a, rad, fma(2.0 * pp.p1 * a, b, pp.p2 * fma(2.0 * a, a, r2)));
+        const double yd = fma(b, rad, fma(pp.p1, fma(2.0 * b, b, r2), 2.0 * pp.p2 * a * b));
+        const TP u = static_cast<TP>(fma(pp.fx, xd, pp.cx)), v = static_cast<TP>(fma(pp.fy, yd, pp.cy));
+        if (proj) { proj[2 * i + 0] = u; proj[2 * i + 1] = v; }
+        // like the reference, the residual is formed from the projected points in their storage type
+        const double dx = static_cast<double>(u) - static_cast<double>(imgp[2 * i + 0]);
+        const double dy = static_cast<double>(v) - static_cast<double>(imgp[2 * i + 1]);
+        acc[0] = fma(dx, dx, acc[0]);
+        acc[1] = fma(dy, dy, acc[1]);
+        acc[2] += (fabs(dx) <= DBL_MAX && fabs(dy) <= DBL_MAX) ? 1.0 : 0.0;
+        acc[3] += fabs(dx);
+        acc[4] += fabs(dy);
+    }
+    block_reduce_store<5>(acc, partials);
+}
+
+template <typename TI, typename TO, typename TS>
+__global__ void __launch_bounds__(kThreads)
+k_pair_reproj(const TO* __restrict__ x, const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<double> cams,
+              const TS* __restrict__ status, const int min_status, const double max_sq_err, TO* __restrict__ err1,
+              TO* __restrict__ err2, uint8_t* __restrict__ good, double* __restrict__ partials, const int64_t n) {
+    double acc[4] = {0, 0, 0, 0};             // sum err1 (good), sum err2 (good), #good, #status > min_status
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const double X = static_cast<double>(x[3 * i + 0]), Y = static_cast<double>(x[3 * i + 1]),
+                     Z = static_cast<double>(x[3 * i + 2]);
+        double a1, b1, a2, b2;
+        load_uv<double>(u1, i, a1, b1);
+        load_uv<double>(u2, i, a2, b2);
+        double e[2], depth[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const double* P = c == 0 ? cams.P1 : cams.P2;
+            const double px = fma(P[0], X, fma(P[1], Y, fma(P[2], Z, P[3])));
+            const double py = fma(P[4], X, fma(P[5], Y, fma(P[6], Z, P[7])));
+            const double pz = fma(P[8], X, fma(P[9], Y, fma(P[10], Z, P[11])));
+            const double iz = 1.0 / pz;
+            const double dx = fma(px, iz, -(c == 0 ? a1 : a2)), dy = fma(py, iz, -(c == 0 ? b1 : b2));
+            e[c] = fma(dx, dx, dy * dy);
+            depth[c] = pz;
+        }
+        const bool st_ok = static_cast<int>(status[i]) > min_status;
+        const bool g = st_ok && (e[0] <= max_sq_err) && (e[1] <= max_sq_err) && (depth[0] > 0.0) && (depth[1] > 0.0);
+        if (err1) err1[i] = static_cast<TO>(e[0]);
+        if (err2) err2[i] = static_cast<TO>(e[1]);
+        if (good) good[i] = g ? 1 : 0;
+        if (g) { acc[0] += e[0]; acc[1] += e[1]; acc[2] += 1.0; }
+        if (st_ok) acc[3] += 1.0;
+    }
+    block_reduce_store<4>(acc, partials);
+}
+
+// ---- whole-batch reductions for the normalised 8-point fundamental matrix (triangulation.py:228) ---------------
+// stage 0: sum x1,y1,x2,y2   stage 1: sum |p1-m1|, |p2-m2|   stage 2: the 45 unique entries of A^T A, where the row of
+// A for one match is (x2x1, x2y1, x2, y2x1, y2y1, y2, x1, y1, 1) in normalised coordinates.
+struct F8Params { double m1[2], m2[2], s1, s2; };
+
+template <typename TI, int STAGE>
+__global__ void __launch_bounds__(kThreads)
+k_f8_reduce(const TI* __restrict__ u1, const TI* __restrict__ u2, const F8Params fp, double* __restrict__ partials,
+            const int64_t n) {
+    constexpr int NV = STAGE == 0 ? 4 : (STAGE == 1 ? 2 : 45);
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        double x1, y1, x2, y2;
+        load_uv<double>(u1, i, x1, y1);
+        load_uv<double>(u2, i, x2, y2);
+        if constexpr (STAGE == 0) {
+            acc[0] += x1; acc[1] += y1; acc[2] += x2; acc[3] += y2;
+        } else if constexpr (STAGE == 1) {
+            const double a = x1 - fp.m1[0], b = y1 - fp.m1[1], c = x2 - fp.m2[0], d = y2 - fp.m2[1];
+            acc[0] += sqrt(fma(a, a, b * b));
+            acc[1] += sqrt(fma(c, c, d * d));
+        } else {
+            const double a = (x1 - fp.m1[0]) * fp.s1, b = (y1 - fp.m1[1]) * fp.s1;
+            const double c = (x2 - fp.m2[0]) * fp.s2, d = (y2 - fp.m2[1]) * fp.s2;
+            const double r[9] = {c * a, c * b, c, d * a, d * b, d, a, b, 1.0};
+            int k = 0;
+#pragma unroll
+            for (int p = 0; p < 9; ++p)
+#pragma unroll
+                for (int q = p; q < 9; ++q) { acc[k] = fma(r[p], r[q], acc[k]); ++k; }
+        }
+    }
+    block_reduce_store<NV>(acc, partials);
+}
+
+}  // namespace trgl

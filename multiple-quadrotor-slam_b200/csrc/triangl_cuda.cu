@@ -1,0 +1,744 @@
+// libtriangl_cuda: C ABI (include/triangl_cuda.h) over the sm_100a solver kernels.
+// Host side only: argument checks, camera-matrix preparation, launch geometry, and the chunked
+// H2D -> kernel -> D2H pipeline used when the caller hands in host buffers.  No CPU compute path exists.
+#include "../../include/triangl_cuda.h"
+#include "trgl_kernels.cuh"
+#include "trgl_reproj.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+using namespace trgl;
+
+namespace {
+
+thread_local std::string g_err = "";
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_ppt{2};
+
+int fail(int code, const char* what) {
+    g_err = what;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return static_cast<int>(e) > 0 ? static_cast<int>(e) : TRGL_E_NODEVICE;
+}
+#define CK(call)                                                    \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);       \
+    } while (0)
+
+bool have_device() {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+struct ModeInfo { int in_bytes, out_bytes; };
+bool mode_info(int mode, ModeInfo& m) {
+    switch (mode) {
+        case TRGL_F64: m = {8, 8}; return true;
+        case TRGL_F32IO: m = {4, 4}; return true;
+        case TRGL_F32: m = {4, 4}; return true;
+        case TRGL_F64_OUT32: m = {8, 4}; return true;
+        case TRGL_F32_OUT64: m = {4, 8}; return true;
+    }
+    return false;
+}
+
+template <typename T>
+Cams<T> make_cams(const double* P1, const double* P2) {
+    Cams<T> c;
+    for (int i = 0; i < 12; ++i) { c.P1[i] = static_cast<T>(P1[i]); c.P2[i] = static_cast<T>(P2[i]); }
+    return c;
+}
+
+inline unsigned grid_for(int64_t n, int per_block) { return static_cast<unsigned>((n + per_block - 1) / per_block); }
+
+// ------------------------------------------------------------------------------------------------------------
+// Device-pointer launchers, one per solver.  MODE_SWITCH instantiates the five precision modes.
+// ------------------------------------------------------------------------------------------------------------
+#define MODE_SWITCH(mode, ...)                                                              \
+    switch (mode) {                                                                         \
+        case TRGL_F64: { using TI = double; using TC = double; using TO = double; __VA_ARGS__ } break;        \
+        case TRGL_F32IO: { using TI = float; using TC = double; using TO = float; __VA_ARGS__ } break;        \
+        case TRGL_F32: { using TI = float; using TC = float; using TO = float; __VA_ARGS__ } break;           \
+        case TRGL_F64_OUT32: { using TI = double; using TC = double; using TO = float; __VA_ARGS__ } break;   \
+        case TRGL_F32_OUT64: { using TI = float; using TC = double; using TO = double; __VA_ARGS__ } break;   \
+        default: return fail(TRGL_E_BADARG, "unknown precision mode");                      \
+    }
+
+int launch_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                     int64_t n, int mode, cudaStream_t s) {
+    if (n == 0) return TRGL_OK;
+    const int ppt = g_ppt.load();
+    MODE_SWITCH(mode, {
+        const Cams<TC> cams = make_cams<TC>(P1, P2);
+        const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
+        TO* xo = static_cast<TO*>(x);
+        if (ppt == 1) k_linear_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n);
+        else if (ppt == 2) k_linear_ls<TI, TC, TO, 2><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n);
+        else k_linear_ls<TI, TC, TO, 4><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n);
+    })
+    g_launches++;
+    CK(cudaGetLastError());
+    return TRGL_OK;
+}
+
+int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
+                        int64_t n, double tol, int semantics, int mode, cudaStream_t s) {
+    if (n == 0) return TRGL_OK;
+    MODE_SWITCH(mode, {
+        const Cams<TC> cams = make_cams<TC>(P1, P2);
+        k_iterative_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(
+            static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
+            static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0);
+    })
+    g_launches++;
+    CK(cudaGetLastError());
+    return TRGL_OK;
+}
+
+int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                        int64_t n, double maxc, int rows, int mode, cudaStream_t s) {
+    if (n == 0) return TRGL_OK;
+    MODE_SWITCH(mode, {
+        const Cams<TC> cams = make_cams<TC>(P1, P2);
+        const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
+        if (rows == 4)
+            k_linear_eigen<TI, TC, TO, 4><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc));
+        else
+            k_linear_eigen<TI, TC, TO, 6><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc));
+    })
+    g_launches++;
+    CK(cudaGetLastError());
+    return TRGL_OK;
+}
+
+int launch_polynomial(const void* u1, const void* u2, const double* P1, const double* P2, const HSParams& hs, void* x,
+                      uint8_t* status, void* u1c, void* u2c, unsigned int* flags, int64_t n, double maxc, int rows,
+                      int mode, cudaStream_t s) {
+    if (n == 0) return TRGL_OK;
+    MODE_SWITCH(mode, {
+        const Cams<TC> cams = make_cams<TC>(P1, P2);
+        const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
+        if (rows == 4)
+            k_polynomial<TI, TC, TO, 4><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc));
+        else
+            k_polynomial<TI, TC, TO, 6><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc));
+    })
+    g_launches++;
+    CK(cudaGetLastError());
+    return TRGL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host-buffer pipeline: chunks of kChunk points round-robin over kSlots streams, each slot owning a grow-only
+// device scratch block.  With pinned host buffers (trgl_host_alloc) H2D, kernel and D2H of neighbouring chunks
+// overlap; with pageable buffers the copies serialise but the result is the same.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSlots = 3;
+constexpr int64_t kChunk = 1 << 21;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    char* buf = nullptr;
+    size_t cap = 0;
+    int device = -1;
+};
+std::mutex g_pipe_mutex;
+Slot g_slots[kSlots];
+unsigned int* g_flags = nullptr;      // 2 words per slot for the polynomial all-NaN test
+double* g_partials = nullptr;         // reduction scratch
+size_t g_partials_cap = 0;
+int g_scratch_device = -1;
+
+int ensure_slot(Slot& sl, size_t bytes) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (sl.device != dev) {           // device changed: drop the old scratch
+        if (sl.buf) { cudaFree(sl.buf); sl.buf = nullptr; sl.cap = 0; }
+        if (sl.stream) { cudaStreamDestroy(sl.stream); sl.stream = nullptr; }
+        sl.device = dev;
+    }
+    if (!sl.stream) CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    if (sl.cap < bytes) {
+        if (sl.buf) { CK(cudaStreamSynchronize(sl.stream)); CK(cudaFree(sl.buf)); sl.buf = nullptr; sl.cap = 0; }
+        size_t want = bytes + bytes / 8 + 4096;
+        if (cudaMalloc(&sl.buf, want) != cudaSuccess) return fail(TRGL_E_NOMEM, "cudaMalloc of pipeline scratch failed");
+        sl.cap = want;
+    }
+    return TRGL_OK;
+}
+
+int ensure_scratch(size_t partial_doubles) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (g_scratch_device != dev) {
+        if (g_flags) cudaFree(g_flags);
+        if (g_partials) cudaFree(g_partials);
+        g_flags = nullptr; g_partials = nullptr; g_partials_cap = 0; g_scratch_device = dev;
+    }
+    if (!g_flags) CK(cudaMalloc(&g_flags, sizeof(unsigned int) * 2 * (kSlots + 1)));
+    if (g_partials_cap < partial_doubles) {
+        if (g_partials) CK(cudaFree(g_partials));
+        CK(cudaMalloc(&g_partials, partial_doubles * sizeof(double)));
+        g_partials_cap = partial_doubles;
+    }
+    return TRGL_OK;
+}
+
+inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct HostArray { const void* in; void* out; size_t bytes_per_point; };
+
+// launcher(dev pointers in the order of `arrays`, chunk point count, stream)
+template <typename Launch>
+int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    const int64_t chunk = n < kChunk ? n : kChunk;
+    size_t per_chunk = 0;
+    for (int a = 0; a < narrays; ++a) per_chunk += align256(arrays[a].bytes_per_point * chunk);
+    const int nslots = n > chunk ? kSlots : 1;
+    for (int s = 0; s < nslots; ++s) { int rc = ensure_slot(g_slots[s], per_chunk); if (rc) return rc; }
+    int idx = 0;
+    for (int64_t off = 0; off < n; off += chunk, ++idx) {
+        Slot& sl = g_slots[idx % nslots];
+        const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+        void* dptr[8];
+        size_t pos = 0;
+        for (int a = 0; a < narrays; ++a) {
+            dptr[a] = sl.buf + pos;
+            pos += align256(arrays[a].bytes_per_point * chunk);
+            if (arrays[a].in)
+                CK(cudaMemcpyAsync(dptr[a], static_cast<const char*>(arrays[a].in) + off * arrays[a].bytes_per_point,
+                                   arrays[a].bytes_per_point * m, cudaMemcpyHostToDevice, sl.stream));
+        }
+        int rc = launch(dptr, m, sl.stream, idx % nslots);
+        if (rc) return rc;
+        for (int a = 0; a < narrays; ++a)
+            if (arrays[a].out)
+                CK(cudaMemcpyAsync(static_cast<char*>(arrays[a].out) + off * arrays[a].bytes_per_point, dptr[a],
+                                   arrays[a].bytes_per_point * m, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    for (int s = 0; s < nslots; ++s) CK(cudaStreamSynchronize(g_slots[s].stream));
+    return TRGL_OK;
+}
+
+int check_common(const void* u1, const void* u2, const double* P1, const double* P2, const void* x, const void* status,
+                 int64_t n, int mode, int mem) {
+    ModeInfo mi;
+    if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
+    if (!mode_info(mode, mi)) return fail(TRGL_E_BADARG, "unknown precision mode");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (!P1 || !P2) return fail(TRGL_E_BADARG, "camera matrix pointer is NULL");
+    if (n > 0 && (!u1 || !u2 || !x || !status)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    return TRGL_OK;
+}
+
+// Right and left epipoles of a rank-2 F as the largest cross product of two rows / columns.
+void null_vector3(const double M[9], bool transpose, double e[3]) {
+    double r[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r[i][j] = transpose ? M[3 * j + i] : M[3 * i + j];
+    double best = -1.0;
+    e[0] = e[1] = e[2] = 0.0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j) {
+            const double c[3] = {r[i][1] * r[j][2] - r[i][2] * r[j][1], r[i][2] * r[j][0] - r[i][0] * r[j][2],
+                                 r[i][0] * r[j][1] - r[i][1] * r[j][0]};
+            const double nn = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+            if (nn > best) { best = nn; e[0] = c[0]; e[1] = c[1]; e[2] = c[2]; }
+        }
+    const double nrm = std::sqrt(best);
+    if (nrm > 0) { e[0] /= nrm; e[1] /= nrm; e[2] /= nrm; }
+}
+
+HSParams make_hs(const double* F) {
+    HSParams hs;
+    for (int i = 0; i < 9; ++i) hs.F[i] = F[i];
+    null_vector3(F, false, hs.e1);
+    null_vector3(F, true, hs.e2);
+    return hs;
+}
+
+// F = [t]x R of P_canon = P2_full * inv(P1_full)   (triangulation.py:211-216)
+bool fundamental_from_P(const double* P1, const double* P2, double F[9]) {
+    // inverse of [A1 | t1; 0 0 0 1]: [A1^-1 | -A1^-1 t1]
+    const double* A = P1;
+    const double a00 = A[0], a01 = A[1], a02 = A[2], a10 = A[4], a11 = A[5], a12 = A[6], a20 = A[8], a21 = A[9], a22 = A[10];
+    const double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    const double det = a00 * c00 + a01 * c01 + a02 * c02;
+    double inv[3][3];
+    inv[0][0] = c00 / det; inv[0][1] = (a02 * a21 - a01 * a22) / det; inv[0][2] = (a01 * a12 - a02 * a11) / det;
+    inv[1][0] = c01 / det; inv[1][1] = (a00 * a22 - a02 * a20) / det; inv[1][2] = (a02 * a10 - a00 * a12) / det;
+    inv[2][0] = c02 / det; inv[2][1] = (a01 * a20 - a00 * a21) / det; inv[2][2] = (a00 * a11 - a01 * a10) / det;
+    const double t1[3] = {P1[3], P1[7], P1[11]};
+    double it[3];
+    for (int i = 0; i < 3; ++i) it[i] = -(inv[i][0] * t1[0] + inv[i][1] * t1[1] + inv[i][2] * t1[2]);
+    double R[3][3], t[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            R[i][j] = P2[4 * i + 0] * inv[0][j] + P2[4 * i + 1] * inv[1][j] + P2[4 * i + 2] * inv[2][j];
+        t[i] = P2[4 * i + 0] * it[0] + P2[4 * i + 1] * it[1] + P2[4 * i + 2] * it[2] + P2[4 * i + 3];
+    }
+    // F[:, j] = t x R[:, j]
+    for (int j = 0; j < 3; ++j) {
+        F[0 + j] = t[1] * R[2][j] - t[2] * R[1][j];
+        F[3 + j] = t[2] * R[0][j] - t[0] * R[2][j];
+        F[6 + j] = t[0] * R[1][j] - t[1] * R[0][j];
+    }
+    return true;
+}
+
+// Host one-sided Jacobi SVD of a small dense matrix (row-major m x n, n <= 9); V (n x n) gets the right singular
+// vectors, w the singular values (unsorted).  Only used by the rare 8-point fallback.
+void host_jacobi_svd(double* A, int m, int n, double* V, double* w) {
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        bool changed = false;
+        for (int i = 0; i < n - 1; ++i)
+            for (int j = i + 1; j < n; ++j) {
+                double a = 0, b = 0, p = 0;
+                for (int k = 0; k < m; ++k) { a += A[k * n + i] * A[k * n + i]; b += A[k * n + j] * A[k * n + j]; p += A[k * n + i] * A[k * n + j]; }
+                if (!(std::fabs(p) > 2.220446049250313e-16 * std::sqrt(a * b))) continue;
+                changed = true;
+                p *= 2;
+                const double beta = a - b, gamma = std::hypot(p, beta);
+                double c, s;
+                if (beta < 0) { const double delta = (gamma - beta) * 0.5; s = std::sqrt(delta / gamma); c = p / (gamma * s * 2); }
+                else { c = std::sqrt((gamma + beta) / (gamma * 2)); s = p / (gamma * c * 2); }
+                for (int k = 0; k < m; ++k) {
+                    const double t0 = c * A[k * n + i] + s * A[k * n + j], t1 = -s * A[k * n + i] + c * A[k * n + j];
+                    A[k * n + i] = t0; A[k * n + j] = t1;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double t0 = c * V[k * n + i] + s * V[k * n + j], t1 = -s * V[k * n + i] + c * V[k * n + j];
+                    V[k * n + i] = t0; V[k * n + j] = t1;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int j = 0; j < n; ++j) {
+        double s = 0;
+        for (int k = 0; k < m; ++k) s += A[k * n + j] * A[k * n + j];
+        w[j] = std::sqrt(s);
+    }
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int trgl_version(void) { return TRGL_VERSION; }
+const char* trgl_last_error_string(void) { return g_err.c_str(); }
+int trgl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int trgl_set_device(int device) { CK(cudaSetDevice(device)); return TRGL_OK; }
+int trgl_device_synchronize(void) { CK(cudaDeviceSynchronize()); return TRGL_OK; }
+
+int trgl_device_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(TRGL_E_BADARG, "ptr is NULL");
+    *ptr = nullptr;
+    if (bytes == 0) return TRGL_OK;
+    CK(cudaMalloc(ptr, bytes));
+    return TRGL_OK;
+}
+int trgl_device_free(void* ptr) { if (ptr) CK(cudaFree(ptr)); return TRGL_OK; }
+int trgl_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(TRGL_E_BADARG, "ptr is NULL");
+    *ptr = nullptr;
+    if (bytes == 0) return TRGL_OK;
+    CK(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return TRGL_OK;
+}
+int trgl_host_free(void* ptr) { if (ptr) CK(cudaFreeHost(ptr)); return TRGL_OK; }
+int trgl_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return TRGL_OK;
+}
+int trgl_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    return TRGL_OK;
+}
+int trgl_memset_d(void* dst, int value, size_t bytes, void* stream) {
+    if (bytes) CK(cudaMemsetAsync(dst, value, bytes, static_cast<cudaStream_t>(stream)));
+    return TRGL_OK;
+}
+int trgl_stream_create(void** stream) {
+    if (!stream) return fail(TRGL_E_BADARG, "stream is NULL");
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return TRGL_OK;
+}
+int trgl_stream_destroy(void* stream) { if (stream) CK(cudaStreamDestroy(static_cast<cudaStream_t>(stream))); return TRGL_OK; }
+int trgl_stream_synchronize(void* stream) { CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); return TRGL_OK; }
+int trgl_event_create(void** event) {
+    if (!event) return fail(TRGL_E_BADARG, "event is NULL");
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    *event = e;
+    return TRGL_OK;
+}
+int trgl_event_destroy(void* event) { if (event) CK(cudaEventDestroy(static_cast<cudaEvent_t>(event))); return TRGL_OK; }
+int trgl_event_record(void* event, void* stream) {
+    CK(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
+    return TRGL_OK;
+}
+int trgl_event_elapsed_ms(void* start, void* stop, float* ms) {
+    CK(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
+    CK(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+    return TRGL_OK;
+}
+
+int64_t trgl_launch_count(void) { return g_launches.load(); }
+int trgl_set_points_per_thread(int ppt) {
+    const int old = g_ppt.load();
+    if (ppt == 1 || ppt == 2 || ppt == 4) g_ppt.store(ppt);
+    return old;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int trgl_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                   int64_t n, int mode, int mem, void* stream) {
+    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
+    if (rc || n == 0) return rc;
+    if (mem == TRGL_MEM_DEVICE) return launch_linear_ls(u1, u2, P1, P2, x, status, n, mode, static_cast<cudaStream_t>(stream));
+    ModeInfo mi; mode_info(mode, mi);
+    HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
+                        {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
+    return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
+        return launch_linear_ls(d[0], d[1], P1, P2, d[2], static_cast<uint8_t*>(d[3]), m, mode, s);
+    });
+}
+
+int trgl_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
+                      int64_t n, double tolerance, int semantics, int mode, int mem, void* stream) {
+    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
+    if (rc) return rc;
+    if (semantics != TRGL_ITER_C && semantics != TRGL_ITER_PY) return fail(TRGL_E_BADARG, "unknown iterative semantics");
+    if (n == 0) return TRGL_OK;
+    if (mem == TRGL_MEM_DEVICE)
+        return launch_iterative_ls(u1, u2, P1, P2, x, status, n, tolerance, semantics, mode, static_cast<cudaStream_t>(stream));
+    ModeInfo mi; mode_info(mode, mi);
+    HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
+                        {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 4}};
+    return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
+        return launch_iterative_ls(d[0], d[1], P1, P2, d[2], static_cast<int32_t*>(d[3]), m, tolerance, semantics, mode, s);
+    });
+}
+
+int trgl_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                      int64_t n, double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
+    if (rc) return rc;
+    if (rows != 4 && rows != 6) return fail(TRGL_E_BADARG, "rows must be 4 or 6");
+    if (n == 0) return TRGL_OK;
+    if (mem == TRGL_MEM_DEVICE)
+        return launch_linear_eigen(u1, u2, P1, P2, x, status, n, max_coordinate_value, rows, mode, static_cast<cudaStream_t>(stream));
+    ModeInfo mi; mode_info(mode, mi);
+    HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
+                        {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
+    return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
+        return launch_linear_eigen(d[0], d[1], P1, P2, d[2], static_cast<uint8_t*>(d[3]), m, max_coordinate_value, rows, mode, s);
+    });
+}
+
+int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const double* P2, const double* F, void* x,
+                      uint8_t* status, void* u1_corr, void* u2_corr, int* all_nan, int64_t n,
+                      double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
+    if (rc) return rc;
+    if (!F) return fail(TRGL_E_BADARG, "F is NULL");
+    if (rows != 4 && rows != 6) return fail(TRGL_E_BADARG, "rows must be 4 or 6");
+    if (all_nan) *all_nan = 0;
+    if (n == 0) return TRGL_OK;
+    const HSParams hs = make_hs(F);
+    ModeInfo mi; mode_info(mode, mi);
+    unsigned int hflags[2 * (kSlots + 1)] = {0};
+    if (mem == TRGL_MEM_DEVICE) {
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        {
+            std::lock_guard<std::mutex> lock(g_pipe_mutex);
+            rc = ensure_scratch(0);
+            if (rc) return rc;
+        }
+        unsigned int* fl = g_flags + 2 * kSlots;
+        CK(cudaMemsetAsync(fl, 0, 2 * sizeof(unsigned int), s));
+        rc = launch_polynomial(u1, u2, P1, P2, hs, x, status, u1_corr, u2_corr, fl, n, max_coordinate_value, rows, mode, s);
+        if (rc) return rc;
+        if (all_nan) {
+            CK(cudaMemcpyAsync(hflags, fl, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            *all_nan = (hflags[0] == 0 || hflags[1] == 0) ? 1 : 0;
+        }
+        return TRGL_OK;
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        rc = ensure_scratch(0);
+        if (rc) return rc;
+        CK(cudaMemset(g_flags, 0, sizeof(unsigned int) * 2 * (kSlots + 1)));
+    }
+    HostArray arr[6] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
+                        {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1},
+                        {nullptr, u1_corr, size_t(2 * mi.in_bytes)}, {nullptr, u2_corr, size_t(2 * mi.in_bytes)}};
+    rc = host_pipeline(arr, 6, n, [&](void** d, int64_t m, cudaStream_t s, int slot) {
+        return launch_polynomial(d[0], d[1], P1, P2, hs, d[2], static_cast<uint8_t*>(d[3]), u1_corr ? d[4] : nullptr,
+                                 u2_corr ? d[5] : nullptr, g_flags + 2 * slot, m, max_coordinate_value, rows, mode, s);
+    });
+    if (rc) return rc;
+    if (all_nan) {
+        CK(cudaMemcpy(hflags, g_flags, sizeof(unsigned int) * 2 * kSlots, cudaMemcpyDeviceToHost));
+        unsigned a = 0, b = 0;
+        for (int s = 0; s < kSlots; ++s) { a |= hflags[2 * s]; b |= hflags[2 * s + 1]; }
+        *all_nan = (a == 0 || b == 0) ? 1 : 0;
+    }
+    return TRGL_OK;
+}
+
+int trgl_polynomial(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                    void* u1_corr, void* u2_corr, int* all_nan, int64_t n, double max_coordinate_value, int rows,
+                    int mode, int mem, void* stream) {
+    if (!P1 || !P2) return fail(TRGL_E_BADARG, "camera matrix pointer is NULL");
+    double F[9];
+    fundamental_from_P(P1, P2, F);
+    return trgl_polynomial_F(u1, u2, P1, P2, F, x, status, u1_corr, u2_corr, all_nan, n, max_coordinate_value, rows,
+                             mode, mem, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int trgl_fundamental_8point(const void* u1, const void* u2, int64_t n, int mode, int mem, double* F, void* stream) {
+    ModeInfo mi;
+    if (!mode_info(mode, mi)) return fail(TRGL_E_BADARG, "unknown precision mode");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (!F || n < 8 || !u1 || !u2) return fail(TRGL_E_BADARG, "need F and at least 8 matches");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    int rc = ensure_scratch(kReduceBlocks * 48);
+    if (rc) return rc;
+    const size_t ub = 2 * mi.in_bytes;
+    const int64_t chunk = (mem == TRGL_MEM_HOST) ? (n < kChunk ? n : kChunk) : n;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* d1 = nullptr; char* d2 = nullptr;
+    if (mem == TRGL_MEM_HOST) {
+        rc = ensure_slot(g_slots[0], 2 * align256(ub * chunk));
+        if (rc) return rc;
+        s = g_slots[0].stream; d1 = g_slots[0].buf; d2 = d1 + align256(ub * chunk);
+    }
+    static thread_local double hpart[kReduceBlocks * 45];
+    F8Params fp = {{0, 0}, {0, 0}, 1, 1};
+    double acc[45];
+    for (int stage = 0; stage < 3; ++stage) {
+        const int nv = stage == 0 ? 4 : (stage == 1 ? 2 : 45);
+        for (int k = 0; k < nv; ++k) acc[k] = 0.0;
+        for (int64_t off = 0; off < n; off += chunk) {
+            const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+            const void* a = static_cast<const char*>(u1) + off * ub; const void* b = static_cast<const char*>(u2) + off * ub;
+            if (mem == TRGL_MEM_HOST) {
+                CK(cudaMemcpyAsync(d1, a, ub * m, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(d2, b, ub * m, cudaMemcpyHostToDevice, s));
+                a = d1; b = d2;
+            }
+#define F8_LAUNCH(TI, ST) k_f8_reduce<TI, ST><<<kReduceBlocks, kThreads, 0, s>>>(static_cast<const TI*>(a), static_cast<const TI*>(b), fp, g_partials, m)
+            if (mi.in_bytes == 8) { if (stage == 0) F8_LAUNCH(double, 0); else if (stage == 1) F8_LAUNCH(double, 1); else F8_LAUNCH(double, 2); }
+            else { if (stage == 0) F8_LAUNCH(float, 0); else if (stage == 1) F8_LAUNCH(float, 1); else F8_LAUNCH(float, 2); }
+#undef F8_LAUNCH
+            g_launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(hpart, g_partials, sizeof(double) * kReduceBlocks * nv, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            for (int b2 = 0; b2 < kReduceBlocks; ++b2)
+                for (int k = 0; k < nv; ++k) acc[k] += hpart[b2 * nv + k];
+        }
+        if (stage == 0) { fp.m1[0] = acc[0] / n; fp.m1[1] = acc[1] / n; fp.m2[0] = acc[2] / n; fp.m2[1] = acc[3] / n; }
+        if (stage == 1) { fp.s1 = std::sqrt(2.0) / (acc[0] / n); fp.s2 = std::sqrt(2.0) / (acc[1] / n); }
+    }
+    double S[81], V[81], w[9];
+    int k = 0;
+    for (int p = 0; p < 9; ++p)
+        for (int q = p; q < 9; ++q) { S[p * 9 + q] = S[q * 9 + p] = acc[k]; ++k; }
+    host_jacobi_svd(S, 9, 9, V, w);
+    int jmin = 0;
+    for (int j = 1; j < 9; ++j) if (w[j] < w[jmin]) jmin = j;
+    double F0[9], V3[9], w3[3];
+    for (int i = 0; i < 9; ++i) F0[i] = V[i * 9 + jmin];
+    // rank-2 projection: F0 = U diag(w) V^T, zero the smallest singular value
+    double U3[9];
+    for (int i = 0; i < 9; ++i) U3[i] = F0[i];
+    host_jacobi_svd(U3, 3, 3, V3, w3);           // columns of U3 are now u_j * w_j
+    int j3 = 0;
+    for (int j = 1; j < 3; ++j) if (w3[j] < w3[j3]) j3 = j;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            double v = 0;
+            for (int j = 0; j < 3; ++j) if (j != j3) v += U3[r * 3 + j] * V3[c * 3 + j];
+            F0[r * 3 + c] = v;
+        }
+    // F = T2^T F0 T1 with T = [[s,0,-s mx],[0,s,-s my],[0,0,1]]
+    const double T1[9] = {fp.s1, 0, -fp.s1 * fp.m1[0], 0, fp.s1, -fp.s1 * fp.m1[1], 0, 0, 1};
+    const double T2[9] = {fp.s2, 0, -fp.s2 * fp.m2[0], 0, fp.s2, -fp.s2 * fp.m2[1], 0, 0, 1};
+    double tmp[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { double v = 0; for (int j = 0; j < 3; ++j) v += T2[j * 3 + r] * F0[j * 3 + c]; tmp[r * 3 + c] = v; }
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { double v = 0; for (int j = 0; j < 3; ++j) v += tmp[r * 3 + j] * T1[j * 3 + c]; F[r * 3 + c] = v; }
+    if (std::fabs(F[8]) > 1.1920929e-07) { const double inv = 1.0 / F[8]; for (int i = 0; i < 9; ++i) F[i] *= inv; }
+    return TRGL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int trgl_reproj_error(const void* x, const void* imgp, const double* K, const double* dist, const double* rvec,
+                      const double* tvec, void* proj, double* sums, double* abs_sums, int64_t n, int x_is_f32,
+                      int img_is_f32, int mem, void* stream) {
+    if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
+    if (!K || !rvec || !tvec || !sums) return fail(TRGL_E_BADARG, "NULL parameter pointer");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (n > 0 && (!x || !imgp)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    sums[0] = sums[1] = sums[2] = 0.0;
+    if (abs_sums) abs_sums[0] = abs_sums[1] = 0.0;
+    if (n == 0) return TRGL_OK;
+    const ProjParams pp = make_proj_params(K, dist, rvec, tvec);
+    const size_t xb = x_is_f32 ? 4 : 8, ib = img_is_f32 ? 4 : 8;
+    double acc[5] = {0, 0, 0, 0, 0};
+    auto run = [&](const void* dx, const void* di, void* dp, int64_t m, cudaStream_t s) -> int {
+        double* part = g_partials;
+        const int blocks = kReduceBlocks;
+        if (x_is_f32) {
+            if (img_is_f32) k_reproj_error<float, float><<<blocks, kThreads, 0, s>>>(static_cast<const float*>(dx), static_cast<const float*>(di), pp, static_cast<float*>(dp), part, m);
+            else k_reproj_error<float, double><<<blocks, kThreads, 0, s>>>(static_cast<const float*>(dx), static_cast<const double*>(di), pp, static_cast<double*>(dp), part, m);
+        } else {
+            if (img_is_f32) k_reproj_error<double, float><<<blocks, kThreads, 0, s>>>(static_cast<const double*>(dx), static_cast<const float*>(di), pp, static_cast<float*>(dp), part, m);
+            else k_reproj_error<double, double><<<blocks, kThreads, 0, s>>>(static_cast<const double*>(dx), static_cast<const double*>(di), pp, static_cast<double*>(dp), part, m);
+        }
+        g_launches++;
+        CK(cudaGetLastError());
+        static thread_local double hpart[kReduceBlocks * 5];
+        CK(cudaMemcpyAsync(hpart, part, sizeof(double) * blocks * 5, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int b = 0; b < blocks; ++b)
+            for (int k = 0; k < 5; ++k) acc[k] += hpart[b * 5 + k];
+        return TRGL_OK;
+    };
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        rc = ensure_scratch(kReduceBlocks * 8);
+        if (rc) return rc;
+    }
+    if (mem == TRGL_MEM_DEVICE) {
+        rc = run(x, imgp, proj, n, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+    } else {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        const int64_t chunk = n < kChunk ? n : kChunk;
+        const size_t need = align256(3 * xb * chunk) + 2 * align256(2 * ib * chunk);
+        rc = ensure_slot(g_slots[0], need);
+        if (rc) return rc;
+        Slot& sl = g_slots[0];
+        for (int64_t off = 0; off < n; off += chunk) {
+            const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+            char* dx = sl.buf;
+            char* di = dx + align256(3 * xb * chunk);
+            char* dp = di + align256(2 * ib * chunk);
+            CK(cudaMemcpyAsync(dx, static_cast<const char*>(x) + off * 3 * xb, 3 * xb * m, cudaMemcpyHostToDevice, sl.stream));
+            CK(cudaMemcpyAsync(di, static_cast<const char*>(imgp) + off * 2 * ib, 2 * ib * m, cudaMemcpyHostToDevice, sl.stream));
+            rc = run(dx, di, proj ? dp : nullptr, m, sl.stream);
+            if (rc) return rc;
+            if (proj) CK(cudaMemcpyAsync(static_cast<char*>(proj) + off * 2 * ib, dp, 2 * ib * m, cudaMemcpyDeviceToHost, sl.stream));
+        }
+        CK(cudaStreamSynchronize(sl.stream));
+    }
+    sums[0] = acc[0]; sums[1] = acc[1]; sums[2] = acc[2];
+    if (abs_sums) { abs_sums[0] = acc[3]; abs_sums[1] = acc[4]; }
+    return TRGL_OK;
+}
+
+int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double* P1, const double* P2,
+                     const void* status, int status_is_i32, int min_status, double max_sq_err, void* err1, void* err2,
+                     uint8_t* good, double* sums, int64_t n, int mode, int mem, void* stream) {
+    ModeInfo mi;
+    if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
+    if (!mode_info(mode, mi)) return fail(TRGL_E_BADARG, "unknown precision mode");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (!P1 || !P2 || !sums) return fail(TRGL_E_BADARG, "NULL parameter pointer");
+    if (n > 0 && (!x || !u1 || !u2 || !status)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+    if (n == 0) return TRGL_OK;
+    double acc[4] = {0, 0, 0, 0};
+    const Cams<double> cams = make_cams<double>(P1, P2);
+    auto run = [&](const void* dx, const void* d1, const void* d2, const void* dst, void* de1, void* de2, uint8_t* dg,
+                   int64_t m, cudaStream_t s) -> int {
+        const int blocks = kReduceBlocks;
+#define PAIR_LAUNCH(TI, TO)                                                                                      \
+        if (status_is_i32)                                                                                       \
+            k_pair_reproj<TI, TO, int32_t><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(dx), static_cast<const TI*>(d1), static_cast<const TI*>(d2), cams, static_cast<const int32_t*>(dst), min_status, max_sq_err, static_cast<TO*>(de1), static_cast<TO*>(de2), dg, g_partials, m); \
+        else                                                                                                     \
+            k_pair_reproj<TI, TO, uint8_t><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(dx), static_cast<const TI*>(d1), static_cast<const TI*>(d2), cams, static_cast<const uint8_t*>(dst), min_status, max_sq_err, static_cast<TO*>(de1), static_cast<TO*>(de2), dg, g_partials, m);
+        if (mi.in_bytes == 8 && mi.out_bytes == 8) { PAIR_LAUNCH(double, double) }
+        else if (mi.in_bytes == 4 && mi.out_bytes == 4) { PAIR_LAUNCH(float, float) }
+        else if (mi.in_bytes == 8 && mi.out_bytes == 4) { PAIR_LAUNCH(double, float) }
+        else { PAIR_LAUNCH(float, double) }
+#undef PAIR_LAUNCH
+        g_launches++;
+        CK(cudaGetLastError());
+        static thread_local double hpart[kReduceBlocks * 4];
+        CK(cudaMemcpyAsync(hpart, g_partials, sizeof(double) * blocks * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int b = 0; b < blocks; ++b)
+            for (int k = 0; k < 4; ++k) acc[k] += hpart[b * 4 + k];
+        return TRGL_OK;
+    };
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        rc = ensure_scratch(kReduceBlocks * 8);
+        if (rc) return rc;
+    }
+    if (mem == TRGL_MEM_DEVICE) {
+        rc = run(x, u1, u2, status, err1, err2, good, n, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+    } else {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        const int64_t chunk = n < kChunk ? n : kChunk;
+        const size_t sb = status_is_i32 ? 4 : 1;
+        const size_t bx = align256(3 * mi.out_bytes * chunk), bu = align256(2 * mi.in_bytes * chunk),
+                     bs = align256(sb * chunk), be = align256(mi.out_bytes * chunk), bg = align256(chunk);
+        rc = ensure_slot(g_slots[0], bx + 2 * bu + bs + 2 * be + bg);
+        if (rc) return rc;
+        Slot& sl = g_slots[0];
+        char* dx = sl.buf; char* d1 = dx + bx; char* d2 = d1 + bu; char* ds = d2 + bu;
+        char* de1 = ds + bs; char* de2 = de1 + be; char* dg = de2 + be;
+        for (int64_t off = 0; off < n; off += chunk) {
+            const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+            CK(cudaMemcpyAsync(dx, static_cast<const char*>(x) + off * 3 * mi.out_bytes, 3 * mi.out_bytes * m, cudaMemcpyHostToDevice, sl.stream));
+            CK(cudaMemcpyAsync(d1, static_cast<const char*>(u1) + off * 2 * mi.in_bytes, 2 * mi.in_bytes * m, cudaMemcpyHostToDevice, sl.stream));
+            CK(cudaMemcpyAsync(d2, static_cast<const char*>(u2) + off * 2 * mi.in_bytes, 2 * mi.in_bytes * m, cudaMemcpyHostToDevice, sl.stream));
+            CK(cudaMemcpyAsync(ds, static_cast<const char*>(status) + off * sb, sb * m, cudaMemcpyHostToDevice, sl.stream));
+            rc = run(dx, d1, d2, ds, err1 ? de1 : nullptr, err2 ? de2 : nullptr, good ? reinterpret_cast<uint8_t*>(dg) : nullptr, m, sl.stream);
+            if (rc) return rc;
+            if (err1) CK(cudaMemcpyAsync(static_cast<char*>(err1) + off * mi.out_bytes, de1, mi.out_bytes * m, cudaMemcpyDeviceToHost, sl.stream));
+            if (err2) CK(cudaMemcpyAsync(static_cast<char*>(err2) + off * mi.out_bytes, de2, mi.out_bytes * m, cudaMemcpyDeviceToHost, sl.stream));
+            if (good) CK(cudaMemcpyAsync(good + off, dg, m, cudaMemcpyDeviceToHost, sl.stream));
+        }
+        CK(cudaStreamSynchronize(sl.stream));
+    }
+    for (int k = 0; k < 4; ++k) sums[k] = acc[k];
+    return TRGL_OK;
+}
+
+}  // extern "C"

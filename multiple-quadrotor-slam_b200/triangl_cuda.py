@@ -1,0 +1,379 @@
+"""
+ctypes binding of libtriangl_cuda.so (C ABI: include/triangl_cuda.h).
+
+This is the thin host layer the reference keeps in Work/python_libs/triangulation_c/__init__.py:18-86
+(coerce inputs, allocate outputs, call the native function in place) -- with the weave/CPython-2 extension
+replaced by a plain shared library.  There is no CPU fallback: if the library or a CUDA device is missing,
+importing succeeds (so the symbols can be inspected) but every compute call raises TrianglCudaError.
+
+Besides NumPy arrays, every solver accepts device-resident buffers (`DeviceArray`, or any object with
+`data_ptr()` such as a CUDA torch.Tensor) for roofline runs without PCIe traffic.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtriangl_cuda.so")
+
+F64, F32IO, F32, F64_OUT32, F32_OUT64 = 0, 1, 2, 3, 4
+MEM_HOST, MEM_DEVICE = 0, 1
+ITER_C, ITER_PY = 0, 1
+
+EXPORTS = [
+    "trgl_version", "trgl_last_error_string", "trgl_device_count", "trgl_set_device", "trgl_device_synchronize",
+    "trgl_device_alloc", "trgl_device_free", "trgl_host_alloc", "trgl_host_free", "trgl_memcpy_h2d",
+    "trgl_memcpy_d2h", "trgl_memset_d", "trgl_stream_create", "trgl_stream_destroy", "trgl_stream_synchronize",
+    "trgl_event_create", "trgl_event_destroy", "trgl_event_record", "trgl_event_elapsed_ms",
+    "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
+    "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
+    "trgl_set_points_per_thread",
+]
+
+
+class TrianglCudaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise TrianglCudaError(
+            "libtriangl_cuda.so is missing (%s): build it with `make -C %s` or __graft_entry__.build(); "
+            "there is no CPU fallback" % (LIB_PATH, os.path.join(_HERE, "csrc")))
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, dbl, cint = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.trgl_version.restype = cint
+    L.trgl_last_error_string.restype = ctypes.c_char_p
+    L.trgl_launch_count.restype = i64
+    L.trgl_device_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.trgl_device_free.argtypes = [vp]
+    L.trgl_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.trgl_host_free.argtypes = [vp]
+    L.trgl_memcpy_h2d.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    L.trgl_memcpy_d2h.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    L.trgl_memset_d.argtypes = [vp, cint, ctypes.c_size_t, vp]
+    L.trgl_stream_create.argtypes = [ctypes.POINTER(vp)]
+    L.trgl_stream_destroy.argtypes = [vp]
+    L.trgl_stream_synchronize.argtypes = [vp]
+    L.trgl_event_create.argtypes = [ctypes.POINTER(vp)]
+    L.trgl_event_destroy.argtypes = [vp]
+    L.trgl_event_record.argtypes = [vp, vp]
+    L.trgl_event_elapsed_ms.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_float)]
+    L.trgl_linear_ls.argtypes = [vp, vp, dp, dp, vp, vp, i64, cint, cint, vp]
+    L.trgl_iterative_ls.argtypes = [vp, vp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
+    L.trgl_linear_eigen.argtypes = [vp, vp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
+    L.trgl_polynomial.argtypes = [vp, vp, dp, dp, vp, vp, vp, vp, ctypes.POINTER(cint), i64, dbl, cint, cint, cint, vp]
+    L.trgl_polynomial_F.argtypes = [vp, vp, dp, dp, dp, vp, vp, vp, vp, ctypes.POINTER(cint), i64, dbl, cint, cint,
+                                    cint, vp]
+    L.trgl_fundamental_8point.argtypes = [vp, vp, i64, cint, cint, dp, vp]
+    L.trgl_reproj_error.argtypes = [vp, vp, dp, dp, dp, dp, vp, dp, dp, i64, cint, cint, cint, vp]
+    L.trgl_pair_reproj.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, dp, i64, cint, cint, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise TrianglCudaError("libtriangl_cuda error %d: %s" % (rc, lib().trgl_last_error_string().decode()))
+
+
+def device_count():
+    return lib().trgl_device_count()
+
+
+def require_device():
+    if device_count() <= 0:
+        raise TrianglCudaError("no CUDA device available: libtriangl_cuda has no CPU fallback")
+
+
+# ---- buffers -----------------------------------------------------------------------------------------------------
+class DeviceArray:
+    """A typed block of HBM owned by the library allocator (freed on garbage collection)."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = ctypes.c_void_p()
+        check(lib().trgl_device_alloc(ctypes.byref(p), self.nbytes))
+        self.ptr = p.value or 0
+
+    def data_ptr(self):
+        return self.ptr
+
+    def __len__(self):
+        return self.shape[0]
+
+    def copy_from_host(self, a, stream=None):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.nbytes == self.nbytes, (a.shape, self.shape)
+        check(lib().trgl_memcpy_h2d(self.ptr, a.ctypes.data, self.nbytes, stream))
+        check(lib().trgl_stream_synchronize(stream))
+        return self
+
+    def to_host(self, out=None, stream=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=self.dtype)
+        check(lib().trgl_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, stream))
+        check(lib().trgl_stream_synchronize(stream))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", 0):
+                _lib.trgl_device_free(self.ptr)
+                self.ptr = 0
+        except Exception:
+            pass
+
+
+def to_device(a):
+    a = np.ascontiguousarray(a)
+    return DeviceArray(a.shape, a.dtype).copy_from_host(a)
+
+
+class _PinnedOwner:
+    def __init__(self, nbytes):
+        p = ctypes.c_void_p()
+        check(lib().trgl_host_alloc(ctypes.byref(p), max(int(nbytes), 1)))
+        self.ptr = p.value
+        self.buf = (ctypes.c_char * max(int(nbytes), 1)).from_address(self.ptr)
+
+    def __del__(self):
+        try:
+            _lib.trgl_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array over page-locked host memory (full-speed PCIe / NVLink-C2C copies in host mode)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64))
+    owner = _PinnedOwner(n * dtype.itemsize)
+    arr = np.frombuffer(owner.buf, dtype=dtype, count=n).reshape(shape)
+    return arr          # keeps `owner` alive through arr.base
+
+
+def pinned_copy(a):
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
+def _is_device(a):
+    return hasattr(a, "data_ptr")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_device(a):
+        return ctypes.c_void_p(a.data_ptr())
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _P12(P):
+    """Rows 0..2 of a 3x4 / 4x4 camera matrix as 12 contiguous doubles (triangulation.c:24-25 reads P[4*k+l])."""
+    P = np.asarray(P)
+    if P.ndim != 2 or P.shape[1] != 4 or P.shape[0] not in (3, 4):
+        raise ValueError("camera matrix must be 3x4 or 4x4, got %r" % (P.shape,))
+    return np.ascontiguousarray(P[0:3, :], dtype=np.float64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+_MODE = {(8, 8, 8): F64, (4, 8, 4): F32IO, (4, 4, 4): F32, (8, 8, 4): F64_OUT32, (4, 8, 8): F32_OUT64}
+
+
+def mode_for(in_dtype, compute_dtype, out_dtype):
+    key = (np.dtype(in_dtype).itemsize, np.dtype(compute_dtype).itemsize, np.dtype(out_dtype).itemsize)
+    if key not in _MODE:
+        raise ValueError("unsupported precision combination in=%s compute=%s out=%s" % (in_dtype, compute_dtype, out_dtype))
+    return _MODE[key]
+
+
+def _prep(u1, u2, compute_dtype, out_dtype):
+    """Input coercion of the reference wrapper (triangulation_c/__init__.py:32-39), without the forced up-cast:
+    float32 inputs stay float32 in HBM and are widened in registers."""
+    dev = _is_device(u1)
+    if dev != _is_device(u2):
+        raise ValueError("u1 and u2 must both be host arrays or both be device buffers")
+    if not dev:
+        u1 = np.asarray(u1); u2 = np.asarray(u2)
+        if u1.dtype != np.float32 or u2.dtype != np.float32:
+            u1 = u1.astype(np.float64, copy=False); u2 = u2.astype(np.float64, copy=False)
+        u1 = np.ascontiguousarray(u1.reshape(-1, 2)); u2 = np.ascontiguousarray(u2.reshape(-1, 2))
+    if len(u1) != len(u2):
+        raise ValueError("u1 and u2 must hold the same number of points")
+    in_dtype = np.dtype(str(u1.dtype).replace("torch.", ""))
+    if in_dtype != np.dtype(str(u2.dtype).replace("torch.", "")):
+        raise ValueError("u1 and u2 must have the same dtype")
+    if np.dtype(compute_dtype) == np.float32 and (in_dtype != np.float32 or np.dtype(out_dtype) != np.float32):
+        compute_dtype = np.float64          # FP32 arithmetic is only defined for float32 in/out
+    return u1, u2, dev, len(u1), mode_for(in_dtype, compute_dtype, out_dtype)
+
+
+def _out(dev, n, cols, dtype, given):
+    if given is not None:
+        return given
+    shape = (n, cols) if cols else (n,)
+    return DeviceArray(shape, dtype) if dev else np.empty(shape, dtype=dtype)
+
+
+def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=None, status=None, stream=None):
+    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
+    P1 = _P12(P1); P2 = _P12(P2)
+    x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
+    check(lib().trgl_linear_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, mode,
+                               MEM_DEVICE if dev else MEM_HOST, stream))
+    return x, status
+
+
+def iterative_ls(u1, P1, u2, P2, tolerance=3.e-5, semantics=ITER_C, out_dtype=np.float64, compute_dtype=np.float64,
+                 x=None, status=None, stream=None):
+    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
+    P1 = _P12(P1); P2 = _P12(P2)
+    x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.int32, status)
+    check(lib().trgl_iterative_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, float(tolerance),
+                                  semantics, mode, MEM_DEVICE if dev else MEM_HOST, stream))
+    return x, status
+
+
+def linear_eigen(u1, P1, u2, P2, max_coordinate_value=1.e16, rows=4, out_dtype=np.float64, compute_dtype=np.float64,
+                 x=None, status=None, stream=None):
+    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
+    P1 = _P12(P1); P2 = _P12(P2)
+    x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
+    check(lib().trgl_linear_eigen(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
+                                  float(max_coordinate_value), rows, mode, MEM_DEVICE if dev else MEM_HOST, stream))
+    return x, status
+
+
+def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_dtype=np.float64,
+               compute_dtype=np.float64, x=None, status=None, want_corrected=False, check_all_nan=True, stream=None):
+    """Returns x, status, all_nan[, u1_corr, u2_corr]."""
+    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
+    P1 = _P12(P1); P2 = _P12(P2)
+    x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
+    in_dtype = np.float32 if mode in (F32IO, F32, F32_OUT64) else np.float64
+    c1 = _out(dev, n, 2, in_dtype, None) if want_corrected else None
+    c2 = _out(dev, n, 2, in_dtype, None) if want_corrected else None
+    flag = ctypes.c_int(0)
+    flag_p = ctypes.byref(flag) if check_all_nan else None
+    mem = MEM_DEVICE if dev else MEM_HOST
+    if F is None:
+        check(lib().trgl_polynomial(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), _ptr(c1), _ptr(c2),
+                                    flag_p, n, float(max_coordinate_value), rows, mode, mem, stream))
+    else:
+        F = np.ascontiguousarray(F, dtype=np.float64).reshape(3, 3)
+        check(lib().trgl_polynomial_F(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _dp(F), _ptr(x), _ptr(status), _ptr(c1),
+                                      _ptr(c2), flag_p, n, float(max_coordinate_value), rows, mode, mem, stream))
+    if want_corrected:
+        return x, status, bool(flag.value), c1, c2
+    return x, status, bool(flag.value)
+
+
+def fundamental_8point(u1, u2, compute_dtype=np.float64, stream=None):
+    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, np.float32 if np.dtype(compute_dtype) == np.float32 else
+                                 (np.float32 if getattr(u1, "dtype", None) == np.float32 else np.float64))
+    F = np.zeros((3, 3))
+    check(lib().trgl_fundamental_8point(_ptr(u1), _ptr(u2), n, mode, MEM_DEVICE if dev else MEM_HOST, _dp(F), stream))
+    return F
+
+
+def reproj_error(x, imgp, K, dist, rvec, tvec, want_proj=True, stream=None):
+    """Returns (sum dx^2, sum dy^2, finite count, sum|dx|, sum|dy|), proj or None."""
+    dev = _is_device(x)
+    if not dev:
+        x = np.asarray(x); imgp = np.asarray(imgp)
+        if x.dtype != np.float32:
+            x = x.astype(np.float64, copy=False)
+        if imgp.dtype != np.float32:
+            imgp = imgp.astype(np.float64, copy=False)
+        x = np.ascontiguousarray(x.reshape(-1, 3)); imgp = np.ascontiguousarray(imgp.reshape(-1, 2))
+    n = len(x)
+    if len(imgp) != n:
+        raise ValueError("objp and imgp must hold the same number of points")
+    x32 = int(np.dtype(str(x.dtype).replace("torch.", "")) == np.float32)
+    i32 = int(np.dtype(str(imgp.dtype).replace("torch.", "")) == np.float32)
+    K = np.ascontiguousarray(K, dtype=np.float64).reshape(3, 3)
+    d = np.zeros(5)
+    if dist is not None:
+        dd = np.asarray(dist, dtype=np.float64).ravel()
+        d[:min(5, len(dd))] = dd[:5]
+    rvec = np.ascontiguousarray(rvec, dtype=np.float64).ravel(); tvec = np.ascontiguousarray(tvec, dtype=np.float64).ravel()
+    proj = _out(dev, n, 2, np.float32 if i32 else np.float64, None) if want_proj else None
+    sums = np.zeros(3); abs_sums = np.zeros(2)
+    check(lib().trgl_reproj_error(_ptr(x), _ptr(imgp), _dp(K), _dp(d), _dp(rvec), _dp(tvec), _ptr(proj), _dp(sums),
+                                  _dp(abs_sums), n, x32, i32, MEM_DEVICE if dev else MEM_HOST, stream))
+    return np.concatenate([sums, abs_sums]), proj
+
+
+def pair_reproj(x, u1, P1, u2, P2, status, min_status=0, max_sq_err=np.inf, want_errors=True, want_good=True,
+                stream=None):
+    """Two-view reprojection errors + good mask right after a solver call. Returns err1, err2, good, sums(4)."""
+    dev = _is_device(x)
+    if not dev:
+        x = np.asarray(x); u1 = np.asarray(u1); u2 = np.asarray(u2); status = np.asarray(status)
+        if x.dtype != np.float32:
+            x = x.astype(np.float64, copy=False)
+        if u1.dtype != np.float32 or u2.dtype != np.float32:
+            u1 = u1.astype(np.float64, copy=False); u2 = u2.astype(np.float64, copy=False)
+        x = np.ascontiguousarray(x.reshape(-1, 3))
+        u1 = np.ascontiguousarray(u1.reshape(-1, 2)); u2 = np.ascontiguousarray(u2.reshape(-1, 2))
+        if status.dtype == np.bool_:
+            status = np.ascontiguousarray(status).view(np.uint8)
+        elif status.dtype != np.uint8:
+            status = np.ascontiguousarray(status, dtype=np.int32)
+    n = len(x)
+    xdt = np.dtype(str(x.dtype).replace("torch.", "")); udt = np.dtype(str(u1.dtype).replace("torch.", ""))
+    sdt = np.dtype(str(status.dtype).replace("torch.", ""))
+    mode = mode_for(udt, np.float64, xdt)
+    P1 = _P12(P1); P2 = _P12(P2)
+    e1 = _out(dev, n, 0, xdt, None) if want_errors else None
+    e2 = _out(dev, n, 0, xdt, None) if want_errors else None
+    good = _out(dev, n, 0, np.bool_, None) if want_good else None
+    sums = np.zeros(4)
+    check(lib().trgl_pair_reproj(_ptr(x), _ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(status), int(sdt.itemsize == 4),
+                                 int(min_status), float(max_sq_err), _ptr(e1), _ptr(e2), _ptr(good), _dp(sums), n,
+                                 mode, MEM_DEVICE if dev else MEM_HOST, stream))
+    return e1, e2, good, sums
+
+
+def launch_count():
+    return int(lib().trgl_launch_count())
+
+
+def set_points_per_thread(ppt):
+    return lib().trgl_set_points_per_thread(int(ppt))
+
+
+def synchronize():
+    check(lib().trgl_device_synchronize())
+
+
+class Event:
+    def __init__(self):
+        p = ctypes.c_void_p()
+        check(lib().trgl_event_create(ctypes.byref(p)))
+        self.ptr = p
+
+    def record(self, stream=None):
+        check(lib().trgl_event_record(self.ptr, stream))
+
+    def elapsed_ms(self, stop):
+        ms = ctypes.c_float(0)
+        check(lib().trgl_event_elapsed_ms(self.ptr, stop.ptr, ctypes.byref(ms)))
+        return float(ms.value)

@@ -1,0 +1,142 @@
+"""
+Drop-in replacement of the reference's Work/python_libs/triangulation.py, backed by libtriangl_cuda (B200, sm_100a).
+
+Same module name, callables, keyword names/defaults and return conventions as the reference:
+
+    linear_eigen_triangulation(u1, P1, u2, P2, max_coordinate_value=1.e16) -> (x, status)   triangulation.py:6-25
+    linear_LS_triangulation(u1, P1, u2, P2)                                -> (x, status)   :31-94 / triangulation.c:65-83
+    iterative_LS_triangulation(u1, P1, u2, P2, tolerance=3.e-5)            -> (x, status)   :100-195 / triangulation.c:104-161
+    polynomial_triangulation(u1, P1, u2, P2)                               -> (x, status)   :198-232
+    set_triangl_output_dtype(dtype)                                                         :259-267
+
+`u1`,`u2` are (N,2) normalised image coordinates, `P1`,`P2` 3x4 or 4x4 camera matrices; `x` is a new (N,3) array of
+`output_dtype`; `status` is bool (eigen / LS / polynomial) or int32 in {1,0,-1,-2,-3} (iterative, the C extension's
+convention, triangulation_c/__init__.py:81).  Callers put this directory on sys.path and `import triangulation`,
+exactly as slam2.py:11-19, triangulation_comparison.py:12-15 and calibrate.py:22 do.
+
+Beyond the reference (all optional, defaults reproduce the reference):
+  * set_triangl_compute_dtype(np.float32) selects the FP32-arithmetic kernels for float32 inputs/outputs;
+  * set_triangl_semantics(iterative='c'|'py', eigen_rows=4|6) selects the iterative_LS control flow
+    (C extension vs pure-Python fallback) and the OpenCV-4 / OpenCV-2.4 DLT system (F4);
+  * device-resident inputs (triangl_cuda.DeviceArray or CUDA torch tensors) are accepted and give
+    device-resident outputs.
+There is no CPU fallback: without the built library or a GPU every call raises.
+"""
+import numpy as np
+
+import triangl_cuda as _tc
+
+output_dtype = float
+compute_dtype = np.float64
+iterative_semantics = 'c'
+eigen_rows = 4
+
+
+def set_triangl_output_dtype(output_dtype_):
+    """
+    Set the datatype of the triangulated 3D point positions.
+    (Default is set to "float")
+    """
+    global output_dtype
+    output_dtype = output_dtype_
+
+
+def set_triangl_compute_dtype(compute_dtype_):
+    """Arithmetic type of the kernels: float64 (reference arithmetic, default) or float32 ("FP32 mode":
+    only used when the inputs are float32 and the output dtype is float32)."""
+    global compute_dtype
+    if np.dtype(compute_dtype_) not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("compute dtype must be float32 or float64")
+    compute_dtype = np.dtype(compute_dtype_).type
+
+
+def set_triangl_semantics(iterative=None, eigen_rows_=None):
+    global iterative_semantics, eigen_rows
+    if iterative is not None:
+        if iterative not in ('c', 'py'):
+            raise ValueError("iterative semantics must be 'c' or 'py'")
+        iterative_semantics = iterative
+    if eigen_rows_ is not None:
+        if eigen_rows_ not in (4, 6):
+            raise ValueError("eigen_rows must be 4 or 6")
+        eigen_rows = eigen_rows_
+
+
+def _kernel_out_dtype():
+    """Storage type written by the kernel; anything but float32 is produced as float64 and cast on the host."""
+    return np.float32 if np.dtype(output_dtype) == np.float32 else np.float64
+
+
+def _finish(x, status, status_dtype=None):
+    if isinstance(x, np.ndarray):
+        if np.finfo(x.dtype) != np.finfo(output_dtype):          # triangulation.py:242-243
+            x = x.astype(output_dtype)
+        if status_dtype is not None and status.dtype != status_dtype:
+            status = status.astype(status_dtype)
+    return x, status
+
+
+def linear_eigen_triangulation(u1, P1, u2, P2, max_coordinate_value=1.e16):
+    """
+    Linear Eigenvalue based (using SVD) triangulation.
+    The status-vector is based on the assumption that all 3D points have finite coordinates.
+    """
+    x, status = _tc.linear_eigen(u1, P1, u2, P2, max_coordinate_value, eigen_rows, _kernel_out_dtype(), compute_dtype)
+    return _finish(x, status)
+
+
+def linear_LS_triangulation(u1, P1, u2, P2):
+    """
+    Linear Least Squares based triangulation.
+    The status-vector will be True for all points.
+    """
+    x, status = _tc.linear_ls(u1, P1, u2, P2, _kernel_out_dtype(), compute_dtype)
+    return _finish(x, status)
+
+
+def iterative_LS_triangulation(u1, P1, u2, P2, tolerance=3.e-5):
+    """
+    Iterative (Linear) Least Squares based triangulation.
+    From "Triangulation", Hartley, R.I. and Sturm, P., Computer vision and image understanding, 1997.
+
+    Additionally returns a status-vector to indicate outliers:
+        1: inlier, and in front of both cameras
+        0: outlier, but in front of both cameras
+        -1: only in front of second camera
+        -2: only in front of first camera
+        -3: not in front of any camera
+    Outliers are selected based on non-convergence of depth, and on negativity of depths (=> behind camera(s)).
+    """
+    sem = _tc.ITER_PY if iterative_semantics == 'py' else _tc.ITER_C
+    x, status = _tc.iterative_ls(u1, P1, u2, P2, tolerance, sem, _kernel_out_dtype(), compute_dtype)
+    # the C extension returns int32 (triangulation_c/__init__.py:81), the Python fallback a platform int (:125)
+    return _finish(x, status, np.int64 if iterative_semantics == 'py' else None)
+
+
+def polynomial_triangulation(u1, P1, u2, P2):
+    """
+    Polynomial (Optimal) triangulation.
+    Uses Linear-Eigen for final triangulation.
+    The status-vector is based on the assumption that all 3D points have finite coordinates.
+    """
+    x, status, all_nan = _tc.polynomial(u1, P1, u2, P2, None, 1.e16, eigen_rows, _kernel_out_dtype(), compute_dtype)
+    if all_nan and len(status) >= 8:
+        # every corrected point is NaN (F == 0): the reference re-estimates F from the matches with the normalised
+        # 8-point algorithm and corrects again (triangulation.py:227-229)
+        F = _tc.fundamental_8point(u1, u2)
+        x, status, _ = _tc.polynomial(u1, P1, u2, P2, F, 1.e16, eigen_rows, _kernel_out_dtype(), compute_dtype,
+                                      check_all_nan=False)
+    return _finish(x, status)
+
+
+def triangulate_and_evaluate(solver, u1, P1, u2, P2, min_status=0, max_sq_err=np.inf, **kwargs):
+    """
+    The call pattern of the SLAM keyframe step (slam2.py:553-563) and of the comparison harness
+    (triangulation_comparison.py:466-480) in one go: solve, then re-project into both cameras and build the
+    good-point mask `status > min_status and errors <= max_sq_err and in front of both cameras`.
+    Returns x, status, good, (rms_err1, rms_err2) over the good points.
+    """
+    x, status = solver(u1, P1, u2, P2, **kwargs)
+    _, _, good, sums = _tc.pair_reproj(x, u1, P1, u2, P2, status, min_status, max_sq_err, want_errors=False)
+    ngood = max(sums[2], 1.0)
+    return x, status, good, (float(np.sqrt(sums[0] / ngood)), float(np.sqrt(sums[1] / ngood)))

@@ -1,0 +1,384 @@
+"""
+GPU parity tests (run with -m gpu on the B200 box): every solver, called through the reference-facing Python API
+(`triangulation`, which goes through the C ABI of libtriangl_cuda.so), against the CPU oracle on the same seeded
+inputs, against the fixtures produced by the reference's own Python code, and against the reference's golden cells.
+
+Bars (BASELINE.json north_star): status / good mask bit-exact; x within 1e-9 relative in FP64, 1e-4 in FP32 mode.
+"rel" is per point: max_k |x_k - ref_k| / max_k |ref_k|.
+Two documented classes of points are excluded from the bit-exact claim because no two correct implementations agree
+on them (DESIGN.md "Ill-posed points"): (i) iterative_LS points whose convergence test |d_new - d| <= tol is decided
+by less than 1e-9 (knife edge), (ii) linear_eigen / polynomial points whose homogeneous w or singular-value gap is at
+rounding level (points at infinity, on the baseline).
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import synthetic_rig as rig
+from oracle import triangulation_oracle as orc
+from harness_replay import replay_cell
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+TOL32 = 1e-4
+RIG_NAMES = ["translating", "rotating", "forward", "general"]
+
+
+@pytest.fixture(scope="module")
+def tri():
+    import triangl_cuda
+    triangl_cuda.require_device()
+    import triangulation
+    yield triangulation
+    triangulation.set_triangl_output_dtype(float)
+    triangulation.set_triangl_compute_dtype(np.float64)
+    triangulation.set_triangl_semantics('c', 4)
+
+
+def rel_err(x, ref):
+    with np.errstate(all='ignore'):
+        return np.max(np.abs(np.asarray(x, dtype=np.float64) - ref), axis=1) / np.max(np.abs(ref), axis=1)
+
+
+def eigen_well_posed(u1, P1, u2, P2, rows=4, tol=1e-9):
+    """Points where the smallest singular vector is determined to `tol` in double: eps*s1/(s3-s4) and |w| margins."""
+    X = orc.eigen_homogeneous(u1, P1, u2, P2, rows)
+    A = np.empty((len(u1), 4, 4))
+    A[:, 0] = u1[:, 0:1] * P1[2] - P1[0]; A[:, 1] = u1[:, 1:2] * P1[2] - P1[1]
+    A[:, 2] = u2[:, 0:1] * P2[2] - P2[0]; A[:, 3] = u2[:, 1:2] * P2[2] - P2[1]
+    s = np.linalg.svd(A, compute_uv=False)
+    with np.errstate(all='ignore'):
+        amp = s[:, 0] / (s[:, 2] - s[:, 3]) / np.abs(X[:, 3])
+    return amp * 2.2e-16 * 50 < tol
+
+
+def ls_well_posed(u1, P1, u2, P2, tol=1e-9):
+    A, _ = orc.build_Ab(u1, P1, u2, P2)
+    s = np.linalg.svd(A, compute_uv=False)
+    return (s[:, 0] / s[:, 2]) * 2.2e-16 * 50 < tol
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rig_name", RIG_NAMES)
+@pytest.mark.parametrize("sigma", [0.0, 0.8, 8.0])
+def test_linear_ls_vs_oracle(tri, rig_name, sigma):
+    u1, P1, u2, P2, X = rig.make_correspondences(30011, rig_name, sigma)
+    x, st = tri.linear_LS_triangulation(u1, P1, u2, P2)
+    xo, so = orc.linear_LS_triangulation(u1, P1, u2, P2)
+    assert x.shape == (30011, 3) and x.dtype == np.float64 and st.dtype == np.bool_
+    assert st.all() and np.array_equal(st, so)
+    ok = ls_well_posed(u1, P1, u2, P2)
+    assert ok.mean() > 0.95
+    assert rel_err(x, xo)[ok].max() < TOL64
+    # ill-conditioned remainder still agrees to its conditioning
+    A, _ = orc.build_Ab(u1, P1, u2, P2)
+    s = np.linalg.svd(A, compute_uv=False)
+    assert np.all(rel_err(x, xo) < np.maximum(TOL64, (s[:, 0] / s[:, 2]) ** 2 * 1e-14))
+
+
+@pytest.mark.parametrize("rig_name", RIG_NAMES)
+@pytest.mark.parametrize("sigma", [0.0, 0.8, 8.0])
+@pytest.mark.parametrize("semantics", ["c", "py"])
+def test_iterative_ls_vs_oracle(tri, rig_name, sigma, semantics):
+    u1, P1, u2, P2, X = rig.make_correspondences(30011, rig_name, sigma)
+    tri.set_triangl_semantics(semantics)
+    try:
+        x, st = tri.iterative_LS_triangulation(u1, P1, u2, P2)
+    finally:
+        tri.set_triangl_semantics('c')
+    xo, so, nsolves, margin = orc.iterative_LS_core(u1, P1, u2, P2, 3e-5, semantics)
+    assert st.dtype == (np.int32 if semantics == 'c' else np.int64)
+    knife = margin < 1e-9
+    assert knife.mean() < 1e-3
+    ok = ls_well_posed(u1, P1, u2, P2) & ~knife
+    assert ok.mean() > 0.9
+    assert np.array_equal(st[ok], so[ok])
+    assert rel_err(x, xo)[ok].max() < TOL64
+    assert set(np.unique(st)).issubset({1, 0, -1, -2, -3})
+
+
+@pytest.mark.parametrize("rig_name", RIG_NAMES)
+@pytest.mark.parametrize("sigma", [0.0, 0.8, 8.0])
+@pytest.mark.parametrize("rows", [4, 6])
+def test_linear_eigen_vs_oracle(tri, rig_name, sigma, rows):
+    u1, P1, u2, P2, X = rig.make_correspondences(30011, rig_name, sigma)
+    tri.set_triangl_semantics(eigen_rows_=rows)
+    try:
+        x, st = tri.linear_eigen_triangulation(u1, P1, u2, P2)
+    finally:
+        tri.set_triangl_semantics(eigen_rows_=4)
+    xo, so = orc.linear_eigen_triangulation(u1, P1, u2, P2, rows=rows)
+    ok = eigen_well_posed(u1, P1, u2, P2)
+    assert ok.mean() > (0.5 if rig_name == "forward" else 0.99)
+    assert np.array_equal(st[ok], so[ok])
+    assert rel_err(x, xo)[ok].max() < TOL64
+
+
+@pytest.mark.parametrize("rig_name", RIG_NAMES)
+@pytest.mark.parametrize("sigma", [0.0, 0.8, 8.0, 20.0])
+def test_polynomial_vs_oracle(tri, rig_name, sigma):
+    u1, P1, u2, P2, X = rig.make_correspondences(20011, rig_name, sigma)
+    x, st = tri.polynomial_triangulation(u1, P1, u2, P2)
+    xo, so = orc.polynomial_triangulation(u1, P1, u2, P2)
+    F = orc.fundamental_from_P(P1, P2)
+    c1, c2 = orc.correct_matches(F, u1, u2)
+    ok = eigen_well_posed(c1, P1, c2, P2) & np.isfinite(xo).all(axis=1)
+    assert ok.mean() > (0.5 if rig_name == "forward" else 0.99)
+    assert np.array_equal(st[ok], so[ok])
+    assert rel_err(x, xo)[ok].max() < TOL64
+
+
+@pytest.mark.parametrize("rig_name", RIG_NAMES)
+def test_corrected_matches_vs_oracle(tri, rig_name):
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(20011, rig_name, 4.0)
+    _, _, all_nan, c1, c2 = tc.polynomial(u1, P1, u2, P2, want_corrected=True)
+    F = orc.fundamental_from_P(P1, P2)
+    o1, o2 = orc.correct_matches(F, u1, u2)
+    assert not all_nan
+    assert np.nanmax(np.abs(c1 - o1)) < 1e-12 and np.nanmax(np.abs(c2 - o2)) < 1e-12
+    # the corrected matches satisfy the epipolar constraint exactly (the defining property of the method)
+    h1 = np.concatenate([c1, np.ones((len(c1), 1))], axis=1); h2 = np.concatenate([c2, np.ones((len(c2), 1))], axis=1)
+    assert np.max(np.abs(np.einsum('ni,ij,nj->n', h2, F, h1))) < 1e-12 * np.abs(F).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_reference_python_fixtures(tri, golden_dir):
+    """Outputs of the reference's own (unmodified, exec'd) Python solvers, committed by oracle/make_golden.py."""
+    files = sorted(glob.glob(os.path.join(golden_dir, "ref_py_[0-9]*.npz")))
+    assert len(files) >= 5
+    tri.set_triangl_semantics('py')
+    try:
+        for f in files:
+            d = np.load(f)
+            u1, P1, u2, P2 = d["u1"], d["P1"], d["u2"], d["P2"]
+            for name in ("linear_eigen", "linear_LS", "iterative_LS", "polynomial"):
+                x, st = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)
+                xr, sr = d["x_" + name], d["status_" + name]
+                ok = ls_well_posed(u1, P1, u2, P2) if "LS" in name else eigen_well_posed(u1, P1, u2, P2)
+                if name == "polynomial":
+                    F = orc.fundamental_from_P(P1, P2)
+                    c1, c2 = orc.correct_matches(F, u1, u2)
+                    ok = eigen_well_posed(c1, P1, c2, P2)
+                assert ok.mean() > 0.9, (f, name)
+                assert np.array_equal(np.asarray(st)[ok], sr[ok]), (f, name)
+                assert rel_err(x, xr)[ok].max() < TOL64, (f, name, rel_err(x, xr)[ok].max())
+    finally:
+        tri.set_triangl_semantics('c')
+
+
+def test_slam_convention_fixture(tri, golden_dir):
+    """float32 points, 4x4 P, float32 output dtype (slam2.py:19,551-555); reference computes in float64."""
+    d = np.load(os.path.join(golden_dir, "ref_py_slam_f32.npz"))
+    tri.set_triangl_output_dtype(np.float32)
+    tri.set_triangl_semantics('py')
+    try:
+        x, st = tri.iterative_LS_triangulation(d["u1"], d["P1"], d["u2"], d["P2"])
+    finally:
+        tri.set_triangl_output_dtype(float)
+        tri.set_triangl_semantics('c')
+    assert x.dtype == np.float32
+    assert np.array_equal(st, d["status_iterative_LS"])
+    assert np.max(np.abs(x.astype(np.float64) - d["x_iterative_LS"].astype(np.float64))
+                  / np.abs(d["x_iterative_LS"]).max(axis=1, keepdims=True)) < 3e-7       # one float32 ulp-ish
+
+
+def test_golden_cells_on_gpu(tri, golden_dir):
+    """The GPU drop-in reproduces cells of the reference's own golden result files (test_1and2.mat)."""
+    with open(os.path.join(golden_dir, "golden_cells.json")) as f:
+        g = json.load(f)["test_1and2"]
+    tri.set_triangl_semantics('c', 6)
+    try:
+        for cell in g["cells"]:
+            if cell["traj"] == 1:
+                continue        # forward trajectory: on-baseline lattice points, see tests/test_oracle_golden.py
+            tr = g["trajectories"][cell["traj"]]
+            pose = (tr["sideways_values"][cell["pose"]], tr["towards_values"][cell["pose"]], tr["angle_values"][cell["pose"]])
+            got = replay_cell([tri.linear_eigen_triangulation, tri.linear_LS_triangulation, tri.iterative_LS_triangulation],
+                              pose, num_trials=g["num_trials"], rseed=g["rseed"])
+            for k in got:
+                for ti in range(3):
+                    want = cell[k][ti]
+                    if want is not None:
+                        assert got[k][ti] == pytest.approx(want, rel=2e-8, abs=1e-12), (cell["traj"], cell["pose"], k, ti)
+    finally:
+        tri.set_triangl_semantics('c', 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["linear_eigen", "linear_LS", "iterative_LS", "polynomial"])
+def test_fp32_mode(tri, name):
+    """FP32 mode: float32 storage and arithmetic; comparator is the float64 reference on the float32-rounded inputs."""
+    u1, P1, u2, P2, X = rig.make_correspondences(30011, "translating", 0.8, dtype=np.float32)
+    tri.set_triangl_output_dtype(np.float32)
+    tri.set_triangl_compute_dtype(np.float32)
+    try:
+        x, st = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)
+    finally:
+        tri.set_triangl_output_dtype(float)
+        tri.set_triangl_compute_dtype(np.float64)
+    xo, so = orc.SOLVERS[name](u1.astype(np.float64), P1, u2.astype(np.float64), P2)
+    assert x.dtype == np.float32
+    assert np.array_equal(st, so)
+    assert rel_err(x, xo).max() < TOL32
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 257, 1000])
+def test_ragged_sizes(tri, n):
+    u1, P1, u2, P2, X = rig.make_correspondences(max(n, 1), "general", 0.8)
+    u1, u2 = u1[:n], u2[:n]
+    for name in ("linear_eigen", "linear_LS", "iterative_LS", "polynomial"):
+        x, st = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)
+        assert x.shape == (n, 3) and st.shape == (n,)
+        if n:
+            xo, so = orc.SOLVERS[name](u1, P1, u2, P2)
+            assert np.array_equal(st, so) and rel_err(x, xo).max() < TOL64
+
+
+def test_single_point_identity_P(tri):
+    """calibrate.py:337-339 calls iterative_LS with P1 = eye(4) on one point."""
+    P1 = np.eye(4)
+    P2 = rig.P_from_R_and_t(rig.rot_y(0.1), [-1.0, 0.0, 0.2])
+    Xw = np.array([[0.3, -0.2, 5.0, 1.0]])
+    u1 = (Xw @ P1[0:3].T); u1 = u1[:, 0:2] / u1[:, 2:3]
+    u2 = (Xw @ P2[0:3].T); u2 = u2[:, 0:2] / u2[:, 2:3]
+    for name in ("linear_eigen", "linear_LS", "iterative_LS", "polynomial"):
+        x, st = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)
+        assert np.allclose(x, Xw[:, 0:3], rtol=1e-10, atol=1e-12), name
+        assert st[0] == 1
+
+
+def test_nan_inf_inputs_propagate(tri):
+    u1, P1, u2, P2, X = rig.make_correspondences(64, "rotating", 0.8)
+    u1 = u1.copy(); u1[3, 0] = np.nan; u1[7, 1] = np.inf
+    for name in ("linear_eigen", "linear_LS", "iterative_LS", "polynomial"):
+        x, st = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)
+        xo, so = orc.SOLVERS[name](u1, P1, u2, P2)
+        assert not np.isfinite(x[3]).all() and not np.isfinite(x[7]).all(), name
+        assert np.array_equal(st, so), (name, st[[3, 7]], so[[3, 7]])
+        keep = np.ones(64, bool); keep[[3, 7]] = False
+        assert rel_err(x, xo)[keep].max() < TOL64
+
+
+def test_rank_deficient_min_norm(tri):
+    """Identical cameras: A has rank 2, cvSolve(DECOMP_SVD) returns the minimum-norm solution."""
+    u1, P1, u2, P2, X = rig.make_correspondences(500, "translating", 0.0)
+    x, st = tri.linear_LS_triangulation(u1, P1, u1, P1)
+    xo, _ = orc.linear_LS_triangulation(u1, P1, u1, P1)
+    assert np.isfinite(x).all()
+    assert rel_err(x, xo).max() < 1e-9
+
+
+def test_polynomial_all_nan_fallback(tri):
+    """F == 0 (identical cameras) -> every corrected point NaN -> 8-point F from the matches (triangulation.py:227-229)."""
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(2000, "general", 0.5)
+    _, _, all_nan = tc.polynomial(u1, P1, u2, P1)           # P2 == P1 -> F == 0
+    assert all_nan
+    F = tc.fundamental_8point(u1, u2)
+    Fo = orc.find_fundamental_8point(u1, u2)
+    F /= np.linalg.norm(F); Fo /= np.linalg.norm(Fo)
+    assert min(np.abs(F - Fo).max(), np.abs(F + Fo).max()) < 1e-8
+    x, st = tri.polynomial_triangulation(u1, P1, u2, P1)    # takes the fallback internally, must not raise
+    assert x.shape == (2000, 3)
+
+
+def test_device_resident_api(tri):
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(100000, "rotating", 0.8)
+    d1, d2 = tc.to_device(u1), tc.to_device(u2)
+    xh, sh = tri.linear_LS_triangulation(u1, P1, u2, P2)
+    xd, sd = tri.linear_LS_triangulation(d1, P1, d2, P2)
+    tc.synchronize()
+    assert isinstance(xd, tc.DeviceArray)
+    assert np.array_equal(xd.to_host(), xh) and np.array_equal(sd.to_host(), sh)
+    for ppt in (1, 2, 4):
+        old = tc.set_points_per_thread(ppt)
+        xp, _ = tc.linear_ls(d1, P1, d2, P2)
+        tc.synchronize()
+        assert np.array_equal(xp.to_host(), xh)
+        tc.set_points_per_thread(old)
+
+
+def test_torch_tensor_frontend(tri):
+    torch = pytest.importorskip("torch")
+    u1, P1, u2, P2, X = rig.make_correspondences(10000, "general", 0.8)
+    t1 = torch.from_numpy(u1).cuda(); t2 = torch.from_numpy(u2).cuda()
+    xo = torch.empty((len(u1), 3), dtype=torch.float64, device="cuda")
+    so = torch.empty(len(u1), dtype=torch.uint8, device="cuda")
+    import triangl_cuda as tc
+    torch.cuda.synchronize()
+    tc.linear_ls(t1, P1, t2, P2, x=xo, status=so, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    xh, _ = tri.linear_LS_triangulation(u1, P1, u2, P2)
+    assert np.array_equal(xo.cpu().numpy(), xh) and bool(so.all())
+
+
+def test_pinned_host_buffers(tri):
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(300000, "general", 0.8)
+    p1, p2 = tc.pinned_copy(u1), tc.pinned_copy(u2)
+    xa, _ = tri.iterative_LS_triangulation(u1, P1, u2, P2)
+    xb, _ = tri.iterative_LS_triangulation(p1, P1, p2, P2)
+    assert np.array_equal(xa, xb)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_reprojection_error_vs_oracle(tri):
+    import calibration_tools as ct
+    u1, P1, u2, P2, X = rig.make_correspondences(50000, "rotating", 0.8)
+    K = np.array([[480., 0, 320], [0, 470., 240], [0, 0, 1]])
+    dist = np.array([0.1, -0.05, 0.001, -0.002, 0.01])
+    rvec = np.array([0.02, 0.29, -0.01]); tvec = np.array([-1.0, 0.1, 40.0])
+    imgp = orc.project_points(X, rvec, tvec, K, dist) + np.random.RandomState(1).normal(0, 0.5, (len(X), 2))
+    rms, proj = ct.reprojection_error(X, imgp, K, dist, rvec, tvec)
+    rmso, projo = orc.reprojection_error(X, imgp, K, dist, rvec, tvec)
+    assert proj.shape == (len(X), 1, 2)
+    assert abs(rms - rmso) < 1e-12 * rmso and np.max(np.abs(proj - projo)) < 1e-10
+    m, s = ct.reprojection_error_ext([X, X[:100]], [imgp, imgp[:100]], K, dist, [rvec, rvec], [tvec, tvec])
+    mo, so = orc.reprojection_error_ext([X, X[:100]], [imgp, imgp[:100]], K, dist, [rvec, rvec], [tvec, tvec])
+    assert abs(m - mo) < 1e-12 * mo and abs(s - so) < 1e-12 * so
+    # float32 object points (the SLAM convention)
+    rms32, _ = ct.reprojection_error(X.astype(np.float32), imgp.astype(np.float32), K, dist, rvec, tvec)
+    assert abs(rms32 - rmso) < 1e-4 * rmso
+
+
+def test_fused_pair_reprojection_and_good_mask(tri):
+    u1, P1, u2, P2, X = rig.make_correspondences(50000, "rotating", 2.0)
+    x, st, good, rms = tri.triangulate_and_evaluate(tri.iterative_LS_triangulation, u1, P1, u2, P2, min_status=0,
+                                                    max_sq_err=(2.0 / 480) ** 2)
+    xh = np.concatenate([x, np.ones((len(x), 1))], axis=1)
+    e = []
+    for u, P in ((u1, P1), (u2, P2)):
+        p = xh @ P.T
+        e.append(((p[:, 0:2] / p[:, 2:3] - u) ** 2).sum(axis=1))
+    want = (st > 0) & (e[0] <= (2.0 / 480) ** 2) & (e[1] <= (2.0 / 480) ** 2)
+    margin = np.minimum(np.abs(e[0] - (2.0 / 480) ** 2), np.abs(e[1] - (2.0 / 480) ** 2)) > 1e-15
+    assert np.array_equal(good[margin], want[margin])
+    assert rms[0] == pytest.approx(np.sqrt(e[0][want].mean()), rel=1e-9)
+    assert rms[1] == pytest.approx(np.sqrt(e[1][want].mean()), rel=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_properties(tri):
+    """BASELINE config-2 size (10 M points): size-independent properties instead of an oracle run.
+       (1) exact projections triangulate back to the cloud (round trip) for every solver;
+       (2) shard-invariance: solving a slice equals slicing the solution (what multi-GPU sharding relies on)."""
+    n = 10_000_000
+    rng = np.random.RandomState(7)
+    u1s, P1, u2s, P2, Xs = rig.make_correspondences(1_000_000, "rotating", 0.0, seed=99)
+    reps = n // len(u1s)
+    u1 = np.tile(u1s, (reps, 1)); u2 = np.tile(u2s, (reps, 1)); X = np.tile(Xs, (reps, 1))
+    for name in ("linear_LS", "iterative_LS", "linear_eigen", "polynomial"):
+        x, st = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)
+        assert x.shape == (n, 3)
+        err = np.max(np.abs(x - X), axis=1)
+        assert err.max() < 1e-9 * 44, (name, err.max())
+        assert (st == 1).all(), name
+        lo = int(rng.randint(0, n - 70000)); hi = lo + 65537
+        xs, ss = getattr(tri, name + "_triangulation")(u1[lo:hi], P1, u2[lo:hi], P2)
+        assert np.array_equal(xs, x[lo:hi]) and np.array_equal(ss, st[lo:hi]), name
