@@ -142,11 +142,10 @@ def to_device(a):
 
 
 class _PinnedOwner:
-    def __init__(self, nbytes):
-        p = ctypes.c_void_p()
-        check(lib().trgl_host_alloc(ctypes.byref(p), max(int(nbytes), 1)))
-        self.ptr = p.value
-        self.buf = (ctypes.c_char * max(int(nbytes), 1)).from_address(self.ptr)
+    """Frees one cudaHostAlloc block when the last NumPy view of it is gone."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
 
     def __del__(self):
         try:
@@ -159,9 +158,12 @@ def pinned_empty(shape, dtype):
     """NumPy array over page-locked host memory (full-speed PCIe / NVLink-C2C copies in host mode)."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape, dtype=np.int64))
-    owner = _PinnedOwner(n * dtype.itemsize)
-    arr = np.frombuffer(owner.buf, dtype=dtype, count=n).reshape(shape)
-    return arr          # keeps `owner` alive through arr.base
+    nbytes = max(n * dtype.itemsize, 1)
+    p = ctypes.c_void_p()
+    check(lib().trgl_host_alloc(ctypes.byref(p), nbytes))
+    buf = (ctypes.c_char * nbytes).from_address(p.value)
+    buf._trgl_owner = _PinnedOwner(p.value)       # arr.base -> buf -> owner: freed with the last view
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
 def pinned_copy(a):
