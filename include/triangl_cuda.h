@@ -141,7 +141,11 @@ int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double
 /* ---- bench / diagnostics ---- */
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t trgl_launch_count(void);
-/* Tuning knob: points per thread of the streaming solvers (1, 2 or 4); returns the previous value. */
+/* Tuning knob: input path of linear_LS.  -1 = auto (default), 0 = per-thread vector loads; 1..6 = cp.async.bulk (TMA
+ * engine) shared-memory ring with (points per thread, stages) = (2,4) (4,3) (1,6) (2,6) (4,4) (1,8).  Returns the
+ * previous value. */
+int trgl_set_stream_variant(int variant);
+/* Tuning knob: points per thread of the per-thread-load linear_LS kernel (1, 2 or 4, default 4); returns the previous value. */
 int trgl_set_points_per_thread(int ppt);
 
 #ifdef __cplusplus

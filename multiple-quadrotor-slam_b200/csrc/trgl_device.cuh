@@ -64,6 +64,7 @@ template <typename TO>
 __device__ __forceinline__ void store_x_warp(TO* __restrict__ xout, int64_t warp_base, int64_t n,
                                              TO x0, TO x1, TO x2, TO* __restrict__ stage /* [96] of this warp */) {
     const int lane = threadIdx.x & 31;
+
     stage[lane * 3 + 0] = x0;
     stage[lane * 3 + 1] = x1;
     stage[lane * 3 + 2] = x2;
@@ -207,6 +208,17 @@ __device__ __noinline__ void solve4x3_svd(const T rows[4][4], T x[3]) {
     }
 }
 
+// Reciprocal without the IEEE special-case slow path: MUFU.RCP64H seed + two Newton steps (<= 2 ulp).
+// Only used where the argument is known to be a well-scaled, non-zero determinant (tier-1 results).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
+
 // Conditioning tiers of the normal-equation solve.  kappa^2(A) <= tr(M)^3 / (4 det(M)); tier 1: plain
 // adjugate solve (error ~ kappa^2 eps); tier 2: + one refinement step on the residual (error ~ kappa eps);
 // tier 3: Jacobi SVD with the reference's rank rule.
@@ -216,17 +228,137 @@ template <> struct Tiers<double> {
     static __device__ __forceinline__ double t2() { return 4.0 * 1.0e10; }
 };
 template <> struct Tiers<float> {
-    static __device__ __forceinline__ float t1() { return 0.0f; }            // always refine in fp32
+    static __device__ __forceinline__ float t1() { return 4.0f * 30.0f; }
     static __device__ __forceinline__ float t2() { return 4.0f * 3.0e3f; }
 };
 
-__device__ void solve4x3_f64_full(const double rows[4][4], double x[3]);
-
-// Solve the weighted system  diag(w1,w1,w2,w2) rows  in the least-squares / min-norm sense.
-// M1,v1 / M2,v2: normal-equation blocks of camera 1 / camera 2 (unweighted), W1 = w1^2, W2 = w2^2.
+// Rows of the weighted 4x3 system diag(w1,w1,w2,w2) [A | -b], rebuilt from the four input scalars (cheap), so the
+// hot path does not have to keep 16 row entries alive across the conditioning branch.
 template <typename T>
-__device__ __forceinline__ void solve_weighted(const T rows[4][4], const T M1[6], const T v1[3], const T M2[6],
-                                               const T v2[3], T w1, T w2, T x[3]) {
+__device__ __forceinline__ void weighted_rows(const Cams<T>& cams, T a, T b, T c, T d, T w1, T w2, T rows[4][4]) {
+    dlt_rows<T>(cams.P1, a, b, rows[0], rows[1]);
+    dlt_rows<T>(cams.P2, c, d, rows[2], rows[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { rows[0][k] *= w1; rows[1][k] *= w1; rows[2][k] *= w2; rows[3][k] *= w2; }
+}
+
+// Tiers 2 and 3 in double precision on an explicit system (out of line: rare path).
+__device__ __noinline__ void solve4x3_careful_f64(const double rows[4][4], double x[3]) {
+    double M[6], v[3], M2[6], v2[3], C[6];
+    normal_acc2<double>(rows[0], rows[1], M, v);
+    normal_acc2<double>(rows[2], rows[3], M2, v2);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) M[k] += M2[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] += v2[k];
+    const double det = sym3_cofactors(M, C);
+    const double tr = M[0] + M[3] + M[5];
+    if (tr * tr * tr < Tiers<double>::t2() * det) {
+        const double inv = 1.0 / det;
+        sym3_apply(C, v, inv, x);
+        double g[3] = {0, 0, 0};                       // g = A^T (b - A x), x += M^-1 g
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double res = -rows[r][3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) res = fma(-rows[r][k], x[k], res);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g[k] = fma(rows[r][k], res, g[k]);
+        }
+        double dx[3];
+        sym3_apply(C, g, inv, dx);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x[k] += dx[k];
+    } else {
+        solve4x3_svd<double>(rows, x);
+    }
+}
+
+template <typename T>
+__device__ __noinline__ void solve_point_careful(const Cams<T>& cams, T a, T b, T c, T d, T w1, T w2, T x[3]) {
+    if constexpr (sizeof(T) == 8) {
+        double rows[4][4];
+        weighted_rows<double>(cams, a, b, c, d, w1, w2, rows);
+        solve4x3_careful_f64(rows, x);
+    } else {
+        // FP32 mode: one refinement step in float when mildly conditioned, otherwise redo the point in double
+        float rows[4][4], M[6], v[3], M2[6], v2[3], C[6];
+        weighted_rows<float>(cams, a, b, c, d, w1, w2, rows);
+        normal_acc2<float>(rows[0], rows[1], M, v);
+        normal_acc2<float>(rows[2], rows[3], M2, v2);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) M[k] += M2[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] += v2[k];
+        const float det = sym3_cofactors(M, C);
+        const float tr = M[0] + M[3] + M[5];
+        if (tr * tr * tr < Tiers<float>::t2() * det) {
+            const float inv = 1.0f / det;
+            sym3_apply(C, v, inv, x);
+            float g[3] = {0, 0, 0};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float res = -rows[r][3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) res = fmaf(-rows[r][k], x[k], res);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g[k] = fmaf(rows[r][k], res, g[k]);
+            }
+            float dx[3];
+            sym3_apply(C, g, inv, dx);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x[k] += dx[k];
+        } else {
+            double rd[4][4], xd[3];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) rd[r][k] = static_cast<double>(rows[r][k]);
+            solve4x3_careful_f64(rd, xd);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x[k] = static_cast<T>(xd[k]);
+        }
+    }
+}
+
+// Per-camera normal-equation blocks of one correspondence (unweighted): M_c = A_c^T A_c, v_c = A_c^T b_c.
+template <typename T>
+__device__ __forceinline__ void point_blocks(const Cams<T>& cams, T a, T b, T c, T d, T M1[6], T v1[3], T M2[6], T v2[3]) {
+    T r0[4], r1[4];
+    dlt_rows<T>(cams.P1, a, b, r0, r1);
+    normal_acc2<T>(r0, r1, M1, v1);
+    dlt_rows<T>(cams.P2, c, d, r0, r1);
+    normal_acc2<T>(r0, r1, M2, v2);
+}
+
+// One refinement step of the normal-equation solution: x += M^-1 A^T W (b - A x), rows rebuilt from the inputs.
+template <typename T>
+__device__ __forceinline__ void refine_inline(const Cams<T>& cams, T a, T b, T c, T d, T W1, T W2, const T C[6], T inv,
+                                              T x[3]) {
+    T g[3] = {0, 0, 0};
+#pragma unroll
+    for (int cam = 0; cam < 2; ++cam) {
+        T r0[4], r1[4];
+        dlt_rows<T>(cam == 0 ? cams.P1 : cams.P2, cam == 0 ? a : c, cam == 0 ? b : d, r0, r1);
+        const T W = cam == 0 ? W1 : W2;
+        T e0 = -r0[3], e1 = -r1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { e0 = tfma(-r0[k], x[k], e0); e1 = tfma(-r1[k], x[k], e1); }
+        e0 *= W; e1 *= W;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[k] = tfma(r0[k], e0, tfma(r1[k], e1, g[k]));
+    }
+    T dx[3];
+    sym3_apply(C, g, inv, dx);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[k] += dx[k];
+}
+
+// Fast solve of  (W1 M1 + W2 M2) x = W1 v1 + W2 v2.  FP64: tier-1 adjugate solve, anything else goes out of line.
+// FP32: the refinement step is always done inline (float normal equations alone are ~kappa^2 * 6e-8).
+template <typename T>
+__device__ __forceinline__ void solve_blocks(const Cams<T>& cams, T a, T b, T c, T d, const T M1[6], const T v1[3],
+                                             const T M2[6], const T v2[3], T w1, T w2, T x[3]) {
     const T W1 = w1 * w1, W2 = w2 * w2;
     T M[6], v[3], C[6];
 #pragma unroll
@@ -236,56 +368,22 @@ __device__ __forceinline__ void solve_weighted(const T rows[4][4], const T M1[6]
     const T det = sym3_cofactors(M, C);
     const T tr = M[0] + M[3] + M[5];
     const T tr3 = tr * tr * tr;
-    const T inv = T(1) / det;
+    const T inv = fast_rcp(det);
     sym3_apply(C, v, inv, x);
-    if (!(tr3 < Tiers<T>::t1() * det)) {
-        if (tr3 < Tiers<T>::t2() * det) {
-            // r = W (b - A x) per row, g = A^T W r, x += M^-1 g
-            T g[3] = {0, 0, 0};
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const T Wr = (r < 2) ? W1 : W2;
-                T res = -rows[r][3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) res = tfma(-rows[r][k], x[k], res);
-                res *= Wr;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) g[k] = tfma(rows[r][k], res, g[k]);
-            }
-            T dx[3];
-            sym3_apply(C, g, inv, dx);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) x[k] += dx[k];
-        } else {
-            if constexpr (sizeof(T) == 8) {
-                T wr[4][4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) wr[r][k] = rows[r][k] * ((r < 2) ? w1 : w2);
-                solve4x3_svd<T>(wr, x);
-            } else {
-                // FP32 mode: ill-conditioned points are redone in double (rare path, keeps the 1e-4 bound)
-                double wr[4][4], xd[3];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        wr[r][k] = static_cast<double>(rows[r][k]) * static_cast<double>((r < 2) ? w1 : w2);
-                solve4x3_f64_full(wr, xd);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) x[k] = static_cast<T>(xd[k]);
-            }
-        }
+    if constexpr (sizeof(T) == 8) {
+        if (!(tr3 < Tiers<T>::t1() * det)) solve_point_careful<T>(cams, a, b, c, d, w1, w2, x);
+    } else {
+        if (tr3 < Tiers<T>::t2() * det) refine_inline<T>(cams, a, b, c, d, W1, W2, C, inv, x);
+        else solve_point_careful<T>(cams, a, b, c, d, w1, w2, x);
     }
 }
 
-// Out-of-line double-precision solve of an explicit 4x3 system (all tiers); used by the FP32-mode kernels.
-__device__ __noinline__ void solve4x3_f64_full(const double rows[4][4], double x[3]) {
-    double M1[6], v1[3], M2[6], v2[3];
-    normal_acc2<double>(rows[0], rows[1], M1, v1);
-    normal_acc2<double>(rows[2], rows[3], M2, v2);
-    solve_weighted<double>(rows, M1, v1, M2, v2, 1.0, 1.0, x);
+// linear_LS point: unweighted system.
+template <typename T>
+__device__ __forceinline__ void ls_point(const Cams<T>& cams, T a, T b, T c, T d, T x[3]) {
+    T M1[6], v1[3], M2[6], v2[3];
+    point_blocks<T>(cams, a, b, c, d, M1, v1, M2, v2);
+    solve_blocks<T>(cams, a, b, c, d, M1, v1, M2, v2, T(1), T(1), x);
 }
 
 }  // namespace trgl

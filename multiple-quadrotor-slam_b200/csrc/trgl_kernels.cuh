@@ -3,6 +3,7 @@
 #pragma once
 #include "trgl_device.cuh"
 #include "trgl_hartley_sturm.cuh"
+#include "trgl_tma.cuh"
 
 namespace trgl {
 
@@ -31,15 +32,90 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC>
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
         const int64_t i = block_base + p * kThreads + threadIdx.x;
-        TC rows[4][4], M1[6], v1[3], M2[6], v2[3], xs[3];
-        dlt_rows<TC>(cams.P1, in[p][0], in[p][1], rows[0], rows[1]);
-        dlt_rows<TC>(cams.P2, in[p][2], in[p][3], rows[2], rows[3]);
-        normal_acc2<TC>(rows[0], rows[1], M1, v1);
-        normal_acc2<TC>(rows[2], rows[3], M2, v2);
-        solve_weighted<TC>(rows, M1, v1, M2, v2, TC(1), TC(1), xs);
+        TC xs[3];
+        ls_point<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs);
         store_x_warp<TO>(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
                          static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage[warp]);
         if (i < n) status[i] = 1;
+    }
+}
+
+// ---- linear_LS, bulk-async pipelined variant ------------------------------------------------------------------------
+// Persistent CTAs; tile = kThreads*PPT correspondences; ring of STAGES shared-memory stages filled by cp.async.bulk.
+// Dynamic shared memory layout: [STAGES][2][TILE*2] TI  |  kWarps*96 TO (store staging)  |  STAGES mbarriers.
+template <typename TI, typename TC, typename TO, int PPT, int STAGES, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_linear_ls_tma(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC> cams,
+                TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n) {
+    constexpr int TILE = kThreads * PPT;
+    constexpr uint32_t kTileBytes = TILE * 2 * sizeof(TI);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TI* in = reinterpret_cast<TI*>(smem_raw);                                  // [STAGES][2][TILE*2]
+    TO* stage_out = reinterpret_cast<TO*>(smem_raw + static_cast<size_t>(STAGES) * 2 * kTileBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(STAGES) * 2 * kTileBytes
+                                                 + kWarps * 96 * sizeof(TO));
+    const int warp = threadIdx.x >> 5;
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    const int64_t nfull = n / TILE;                                            // tiles [0, nfull) are complete
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            const int64_t t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(s) * gridDim.x;
+            if (t < nfull) {
+                mbar_expect_tx(&full[s], 2 * kTileBytes);
+                bulk_g2s(in + (s * 2 + 0) * TILE * 2, u1 + t * TILE * 2, kTileBytes, &full[s]);
+                bulk_g2s(in + (s * 2 + 1) * TILE * 2, u2 + t * TILE * 2, kTileBytes, &full[s]);
+            }
+        }
+    }
+    int s = 0;
+    uint32_t parity = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t tile_base = t * TILE;
+        const bool is_full = t < nfull;
+        if (is_full) mbar_wait(&full[s], parity);
+        const TI* s1 = in + (s * 2 + 0) * TILE * 2;
+        const TI* s2 = in + (s * 2 + 1) * TILE * 2;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const int j = p * kThreads + threadIdx.x;
+            const int64_t i = tile_base + j;
+            TC a, b, c, d;
+            if (is_full) {
+                if constexpr (sizeof(TI) == 8) {
+                    const double2 v1 = reinterpret_cast<const double2*>(s1)[j], v2 = reinterpret_cast<const double2*>(s2)[j];
+                    a = static_cast<TC>(v1.x); b = static_cast<TC>(v1.y); c = static_cast<TC>(v2.x); d = static_cast<TC>(v2.y);
+                } else {
+                    const float2 v1 = reinterpret_cast<const float2*>(s1)[j], v2 = reinterpret_cast<const float2*>(s2)[j];
+                    a = static_cast<TC>(v1.x); b = static_cast<TC>(v1.y); c = static_cast<TC>(v2.x); d = static_cast<TC>(v2.y);
+                }
+            } else if (i < n) {                 // ragged last tile: plain loads
+                load_uv<TC>(u1, i, a, b); load_uv<TC>(u2, i, c, d);
+            } else {
+                a = b = c = d = TC(0);
+            }
+            TC xs[3];
+            ls_point<TC>(cams, a, b, c, d, xs);
+            store_x_warp<TO>(x, tile_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
+                             static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage_out + warp * 96);
+            if (i < n) status[i] = 1;
+        }
+        __syncthreads();                        // every thread has consumed stage s
+        if (threadIdx.x == 0) {
+            const int64_t tn = t + static_cast<int64_t>(STAGES) * gridDim.x;
+            if (tn < nfull) {
+                mbar_expect_tx(&full[s], 2 * kTileBytes);
+                bulk_g2s(in + (s * 2 + 0) * TILE * 2, u1 + tn * TILE * 2, kTileBytes, &full[s]);
+                bulk_g2s(in + (s * 2 + 1) * TILE * 2, u2 + tn * TILE * 2, kTileBytes, &full[s]);
+            }
+        }
+        if (++s == STAGES) { s = 0; parity ^= 1; }
     }
 }
 
@@ -66,16 +142,13 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<
 #pragma unroll 1
     for (int p = 0; p < PPT; ++p) {
         const int64_t i = block_base + p * kThreads + threadIdx.x;
-        TC rows[4][4], M1[6], v1[3], M2[6], v2[3], xs[3];
-        dlt_rows<TC>(cams.P1, in[p][0], in[p][1], rows[0], rows[1]);
-        dlt_rows<TC>(cams.P2, in[p][2], in[p][3], rows[2], rows[3]);
-        normal_acc2<TC>(rows[0], rows[1], M1, v1);
-        normal_acc2<TC>(rows[2], rows[3], M2, v2);
+        TC M1[6], v1[3], M2[6], v2[3], xs[3];
+        point_blocks<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], M1, v1, M2, v2);
         TC w1 = 1, w2 = 1, d1 = 1, d2 = 1, d1n = 1, d2n = 1;
         int it = py_semantics ? 9 : 10;         // value of the loop variable after a loop that never breaks
 #pragma unroll 1
         for (int k = 0; k < 10; ++k) {
-            solve_weighted<TC>(rows, M1, v1, M2, v2, w1, w2, xs);
+            solve_blocks<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], M1, v1, M2, v2, w1, w2, xs);
             d1n = tfma(cams.P1[8], xs[0], tfma(cams.P1[9], xs[1], tfma(cams.P1[10], xs[2], cams.P1[11])));
             d2n = tfma(cams.P2[8], xs[0], tfma(cams.P2[9], xs[1], tfma(cams.P2[10], xs[2], cams.P2[11])));
             const bool conv = (tabs(d1n - d1) <= tolerance) && (tabs(d2n - d2) <= tolerance);

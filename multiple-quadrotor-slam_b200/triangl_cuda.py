@@ -28,7 +28,7 @@ EXPORTS = [
     "trgl_event_create", "trgl_event_destroy", "trgl_event_record", "trgl_event_elapsed_ms",
     "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
-    "trgl_set_points_per_thread",
+    "trgl_set_points_per_thread", "trgl_set_stream_variant",
 ]
 
 
@@ -360,6 +360,10 @@ def launch_count():
 
 def set_points_per_thread(ppt):
     return lib().trgl_set_points_per_thread(int(ppt))
+
+
+def set_stream_variant(v):
+    return lib().trgl_set_stream_variant(int(v))
 
 
 def synchronize():

@@ -1,0 +1,70 @@
+"""Device-resident kernel sweep: per solver / precision mode / points-per-thread timing with CUDA events.
+   python tools/sweep_kernels.py [--points N] [--solvers linear_LS,...] [--iters K] [--rig rotating]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multiple-quadrotor-slam_b200"))
+import synthetic_rig as rig          # noqa: E402
+import triangl_cuda as tc            # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--points", type=int, default=100_000_000)
+ap.add_argument("--solvers", default="linear_LS")
+ap.add_argument("--modes", default="f64,f32")
+ap.add_argument("--ppts", default="1,2,4")
+ap.add_argument("--variants", default="0")
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--rig", default="rotating")
+args = ap.parse_args()
+
+n = args.points
+base = min(n, 2_000_000)
+peak = 6543.1
+for mode in args.modes.split(","):
+    dt = np.float64 if mode == "f64" else np.float32
+    u1b, P1, u2b, P2, _ = rig.make_correspondences(base, args.rig, 0.8, dtype=dt)
+    reps = -(-n // base)
+    d1 = tc.to_device(np.tile(u1b, (reps, 1))[:n]); d2 = tc.to_device(np.tile(u2b, (reps, 1))[:n])
+    x = tc.DeviceArray((n, 3), dt); sb = tc.DeviceArray((n,), np.uint8); si = tc.DeviceArray((n,), np.int32)
+    isz = np.dtype(dt).itemsize
+    for solver in args.solvers.split(","):
+        cfgs = []
+        for v in [int(v) for v in args.variants.split(",")]:
+            if v == 0:
+                cfgs += [(0, int(p)) for p in args.ppts.split(",")] if solver == "linear_LS" else [(0, 1)]
+            elif solver == "linear_LS":
+                cfgs.append((v, 0))
+        for variant, ppt in cfgs:
+            tc.set_stream_variant(variant)
+            if ppt:
+                tc.set_points_per_thread(ppt)
+
+            def launch():
+                kw = dict(out_dtype=dt, compute_dtype=dt, x=x)
+                if solver == "linear_LS":
+                    tc.linear_ls(d1, P1, d2, P2, status=sb, **kw)
+                elif solver == "iterative_LS":
+                    tc.iterative_ls(d1, P1, d2, P2, status=si, **kw)
+                elif solver == "linear_eigen":
+                    tc.linear_eigen(d1, P1, d2, P2, status=sb, **kw)
+                else:
+                    tc.polynomial(d1, P1, d2, P2, status=sb, check_all_nan=False, **kw)
+            for _ in range(3):
+                launch()
+            tc.synchronize()
+            e = [tc.Event() for _ in range(args.iters + 1)]
+            for i in range(args.iters):
+                e[i].record(); launch()
+            e[args.iters].record(); tc.synchronize()
+            ms = np.array([e[i].elapsed_ms(e[i + 1]) for i in range(args.iters)])
+            bpp = 4 * isz + 3 * isz + (4 if solver == "iterative_LS" else 1)
+            gbs = bpp * n / (np.median(ms) * 1e-3) / 1e9
+            print(json.dumps({"solver": solver, "mode": mode, "variant": variant, "ppt": ppt, "n": n, "ms_median": float(np.median(ms)),
+                              "ms_min": float(ms.min()), "pts_per_s": n / (np.median(ms) * 1e-3), "alg_GBs": gbs,
+                              "frac_of_6543": gbs / peak}))
+    del d1, d2, x, sb, si
