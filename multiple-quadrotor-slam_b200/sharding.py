@@ -1,0 +1,128 @@
+"""
+Multi-GPU sharding of the triangulation hot path (one process per GPU, torch.distributed for the plumbing).
+
+Every correspondence is independent in all four solvers (the reference's loop bodies only touch index xi:
+Work/python_libs/triangulation_c/triangulation.c:71,110), so the path shards by contiguous point ranges with NO
+collective inside the solve.  The only shared inputs are the camera matrices (<= 28 pairs x 2 x 96 B), broadcast once
+from rank 0; results are gathered (all_gather over NCCL/NVLink, or gloo in the CPU tests) only when the caller asks
+for the assembled map.  The reference has no multi-process code at all; this module is the B200
+replacement for its disabled `#pragma omp parallel for` (triangulation_c/setup.py:12-13).
+"""
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """Contiguous range [lo, hi) of rank `rank`: r*ceil(n/G) .. min(n, (r+1)*ceil(n/G))."""
+    per = -(-n // world) if world > 0 else n
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def pair_segments(num_cams, total_points):
+    """Segment table of the multi-quadrotor scene: all camera pairs (i < j), equal share of the correspondences.
+    Returns a list of (cam_i, cam_j, offset, count) covering [0, total_points)."""
+    pairs = [(i, j) for i in range(num_cams) for j in range(i + 1, num_cams)]
+    per = -(-total_points // len(pairs))
+    segs, off = [], 0
+    for (i, j) in pairs:
+        cnt = max(0, min(per, total_points - off))
+        segs.append((i, j, off, cnt))
+        off += cnt
+    return segs
+
+
+def intersect_segments(segs, lo, hi):
+    """Pieces of the segment table that fall inside the shard [lo, hi): (cam_i, cam_j, global offset, count)."""
+    out = []
+    for (i, j, off, cnt) in segs:
+        a, b = max(off, lo), min(off + cnt, hi)
+        if b > a:
+            out.append((i, j, a, b - a))
+    return out
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def broadcast_cameras(cams, src=0, device=None):
+    """Broadcast a list/array of 3x4 (or 4x4) camera matrices from `src`; every rank passes an array of the same
+    shape (contents ignored on the other ranks).  Works with any initialised backend (NCCL on GPUs, gloo on CPU)."""
+    import torch
+    dist = _dist()
+    arr = np.ascontiguousarray(np.asarray(cams, dtype=np.float64))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return arr
+    t = torch.from_numpy(arr.copy())
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src)
+    return t.cpu().numpy()
+
+
+def gather_shards(x_shard, n_total, device=None):
+    """All-gather equally sized (padded) shards and cut the result back to n_total rows."""
+    import torch
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return np.asarray(x_shard)[:n_total]
+    world = dist.get_world_size()
+    per = -(-n_total // world)
+    x_shard = np.asarray(x_shard)
+    pad = np.zeros((per,) + x_shard.shape[1:], dtype=x_shard.dtype)
+    pad[:len(x_shard)] = x_shard
+    t = torch.from_numpy(pad.view(np.uint8) if pad.dtype == np.bool_ else pad)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    res = out.cpu().numpy()[:n_total]
+    return res.view(np.bool_) if x_shard.dtype == np.bool_ else res
+
+
+def triangulate_sharded(solve_fn, u1, P1, u2, P2, gather=True, device=None, **kwargs):
+    """
+    Shard one (u1, P1, u2, P2) batch over the ranks of the default process group.
+    `solve_fn` has the reference signature (e.g. triangulation.linear_LS_triangulation); every rank passes the same
+    full-size u1/u2 (or at least its own range filled in).  Returns (x, status) assembled on every rank when `gather`
+    is true, else this rank's shard and its (lo, hi).
+    """
+    dist = _dist()
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if on else 0
+    world = dist.get_world_size() if on else 1
+    n = len(u1)
+    cams = broadcast_cameras(np.stack([np.asarray(P1, dtype=np.float64)[0:3], np.asarray(P2, dtype=np.float64)[0:3]]),
+                             0, device)
+    lo, hi = shard_range(n, rank, world)
+    x, status = solve_fn(u1[lo:hi], cams[0], u2[lo:hi], cams[1], **kwargs)
+    if not gather:
+        return x, status, (lo, hi)
+    return gather_shards(x, n, device), gather_shards(status, n, device)
+
+
+def triangulate_pairs_sharded(solve_fn, u_by_cam, cams, segs, gather=True, device=None, **kwargs):
+    """
+    Multi-camera scene: `segs` from pair_segments(); u_by_cam[(i, j)] = (u_i, u_j) arrays of that pair's matches
+    (length = count).  The concatenated correspondence array is sharded by range, every rank holds all camera matrices.
+    """
+    dist = _dist()
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if on else 0
+    world = dist.get_world_size() if on else 1
+    cams = broadcast_cameras(np.stack([np.asarray(P, dtype=np.float64)[0:3] for P in cams]), 0, device)
+    total = sum(c for (_, _, _, c) in segs)
+    lo, hi = shard_range(total, rank, world)
+    xs, sts = [], []
+    seg_off = {(i, j): off for (i, j, off, _) in segs}
+    for (i, j, off, cnt) in intersect_segments(segs, lo, hi):
+        a = off - seg_off[(i, j)]
+        ui, uj = u_by_cam[(i, j)]
+        x, st = solve_fn(ui[a:a + cnt], cams[i], uj[a:a + cnt], cams[j], **kwargs)
+        xs.append(np.asarray(x)); sts.append(np.asarray(st))
+    x = np.concatenate(xs) if xs else np.zeros((0, 3))
+    st = np.concatenate(sts) if sts else np.zeros((0,), dtype=np.bool_)
+    if not gather:
+        return x, st, (lo, hi)
+    return gather_shards(x, total, device), gather_shards(st, total, device)

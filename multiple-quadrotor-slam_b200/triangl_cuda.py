@@ -11,6 +11,7 @@ Besides NumPy arrays, every solver accepts device-resident buffers (`DeviceArray
 """
 import ctypes
 import os
+import threading
 
 import numpy as np
 
@@ -19,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libtriangl_cuda.so")
 
 F64, F32IO, F32, F64_OUT32, F32_OUT64 = 0, 1, 2, 3, 4
 MEM_HOST, MEM_DEVICE = 0, 1
+PINNED_OUTPUT_MIN_POINTS = 1 << 16      # host-mode outputs at least this long are allocated page-locked
 ITER_C, ITER_PY = 0, 1
 
 EXPORTS = [
@@ -141,29 +143,67 @@ def to_device(a):
     return DeviceArray(a.shape, a.dtype).copy_from_host(a)
 
 
-class _PinnedOwner:
-    """Frees one cudaHostAlloc block when the last NumPy view of it is gone."""
+# Page-locked host memory comes from a small caching allocator: cudaHostAlloc costs ~0.3 ms per MB, far more than the
+# PCIe transfer it enables, so blocks are recycled when the last NumPy view of them is garbage collected (the same idea
+# as a framework's pinned-memory caching allocator).  Large solver outputs are allocated here so that the D2H copy of
+# the chunked pipeline runs asynchronously at full PCIe speed.
+_PIN_GRAIN = 1 << 21
+_PIN_CACHE_LIMIT = 16 << 30
+_pin_lock = threading.Lock()
+_pin_free = {}          # rounded size -> [ptr, ...]
+_pin_cached_bytes = 0
 
-    def __init__(self, ptr):
+
+class _PinnedOwner:
+    """Returns one cudaHostAlloc block to the cache when the last NumPy view of it is gone."""
+
+    def __init__(self, ptr, size):
         self.ptr = ptr
+        self.size = size
 
     def __del__(self):
+        global _pin_cached_bytes
         try:
+            with _pin_lock:
+                if _pin_cached_bytes + self.size <= _PIN_CACHE_LIMIT:
+                    _pin_free.setdefault(self.size, []).append(self.ptr)
+                    _pin_cached_bytes += self.size
+                    return
             _lib.trgl_host_free(self.ptr)
         except Exception:
             pass
 
 
 def pinned_empty(shape, dtype):
-    """NumPy array over page-locked host memory (full-speed PCIe / NVLink-C2C copies in host mode)."""
+    """NumPy array over page-locked host memory (full-speed asynchronous PCIe copies in host mode)."""
+    global _pin_cached_bytes
     dtype = np.dtype(dtype)
     n = int(np.prod(shape, dtype=np.int64))
     nbytes = max(n * dtype.itemsize, 1)
-    p = ctypes.c_void_p()
-    check(lib().trgl_host_alloc(ctypes.byref(p), nbytes))
-    buf = (ctypes.c_char * nbytes).from_address(p.value)
-    buf._trgl_owner = _PinnedOwner(p.value)       # arr.base -> buf -> owner: freed with the last view
+    size = (nbytes + _PIN_GRAIN - 1) // _PIN_GRAIN * _PIN_GRAIN
+    ptr = None
+    with _pin_lock:
+        lst = _pin_free.get(size)
+        if lst:
+            ptr = lst.pop()
+            _pin_cached_bytes -= size
+    if ptr is None:
+        p = ctypes.c_void_p()
+        check(lib().trgl_host_alloc(ctypes.byref(p), size))
+        ptr = p.value
+    buf = (ctypes.c_char * nbytes).from_address(ptr)
+    buf._trgl_owner = _PinnedOwner(ptr, size)       # arr.base -> buf -> owner: recycled with the last view
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def pinned_cache_clear():
+    global _pin_cached_bytes
+    with _pin_lock:
+        for lst in _pin_free.values():
+            for ptr in lst:
+                _lib.trgl_host_free(ptr)
+        _pin_free.clear()
+        _pin_cached_bytes = 0
 
 
 def pinned_copy(a):
@@ -231,7 +271,11 @@ def _out(dev, n, cols, dtype, given):
     if given is not None:
         return given
     shape = (n, cols) if cols else (n,)
-    return DeviceArray(shape, dtype) if dev else np.empty(shape, dtype=dtype)
+    if dev:
+        return DeviceArray(shape, dtype)
+    if n >= PINNED_OUTPUT_MIN_POINTS:
+        return pinned_empty(shape, dtype)
+    return np.empty(shape, dtype=dtype)
 
 
 def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=None, status=None, stream=None):
