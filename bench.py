@@ -192,14 +192,15 @@ def run_ours(args, rank, world, local_rank):
         P1 = c[:12].reshape(3, 4).copy(); P2 = c[12:].reshape(3, 4).copy()
 
     d_u1, d_u2 = tc.to_device(u1), tc.to_device(u2)
-    d_x = tc.DeviceArray((n, 3), np.float64)
-    d_sb = tc.DeviceArray((n,), np.uint8)
-    d_si = tc.DeviceArray((n,), np.int32)
+    # one result buffer per solver: the four kernels are enqueued back to back (no host sync in between, so the
+    # per-kernel CUDA events do not include Python launch latency), then the four fused reprojection passes run
+    d_x = {s: tc.DeviceArray((n, 3), np.float64) for s in SOLVERS}
+    d_st = {s: tc.DeviceArray((n,), np.int32 if s == "iterative_LS" else np.uint8) for s in SOLVERS}
     gather_buf = None
     if world > 1 and args.gather:
         import torch
-        # x lives in a torch tensor so NCCL can all-gather it; kernels and NCCL share the legacy default stream
-        d_x = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+        # x lives in torch tensors so NCCL can all-gather it; kernels and NCCL share the legacy default stream
+        d_x = {s: torch.empty((n, 3), dtype=torch.float64, device="cuda") for s in SOLVERS}
         gather_buf = torch.empty((world * n, 3), dtype=torch.float64, device="cuda")
 
     ev = [tc.Event() for _ in range(9)]
@@ -210,19 +211,20 @@ def run_ours(args, rank, world, local_rank):
         for name in SOLVERS:
             ev[k].record(); k += 1
             if name == "linear_eigen":
-                tc.linear_eigen(d_u1, P1, d_u2, P2, x=d_x, status=d_sb)
+                tc.linear_eigen(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name])
             elif name == "linear_LS":
-                tc.linear_ls(d_u1, P1, d_u2, P2, x=d_x, status=d_sb)
+                tc.linear_ls(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name])
             elif name == "iterative_LS":
-                tc.iterative_ls(d_u1, P1, d_u2, P2, x=d_x, status=d_si)
+                tc.iterative_ls(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name])
             else:
-                tc.polynomial(d_u1, P1, d_u2, P2, x=d_x, status=d_sb, check_all_nan=False)
+                tc.polynomial(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name], check_all_nan=False)
             ev[k].record(); k += 1
-            st = d_si if name == "iterative_LS" else d_sb
-            _, _, _, sums = tc.pair_reproj(d_x, d_u1, P1, d_u2, P2, st, 0, np.inf, want_errors=False, want_good=False)
+        for name in SOLVERS:
+            _, _, _, sums = tc.pair_reproj(d_x[name], d_u1, P1, d_u2, P2, d_st[name], 0, np.inf, want_errors=False,
+                                           want_good=False)
             sums_total += sums[0] + sums[1]
             if gather_buf is not None:
-                dist.all_gather_into_tensor(gather_buf, d_x)
+                dist.all_gather_into_tensor(gather_buf, d_x[name])
         ev[8].record()
         tc.synchronize()
         if timed is not None:

@@ -30,7 +30,10 @@
  * Precision modes (`mode`):
  *   TRGL_F64       u,x float64, float64 arithmetic            (reference arithmetic, triangulation.c)
  *   TRGL_F32IO     u,x float32, float64 arithmetic            (the SLAM convention: slam2.py:19,551-555)
- *   TRGL_F32       u,x float32, float32 arithmetic            ("FP32 mode" of BASELINE.json)
+ *   TRGL_F32       u,x float32, float32 arithmetic            ("FP32 mode" of BASELINE.json).  Only linear_LS, the
+ *                  HBM-bound solver, has float32 arithmetic; iterative_LS (absolute 3e-5 depth tolerance at depth ~40
+ *                  is 6 float ulps), linear_eigen and polynomial (smallest singular vector, degree-6 coefficients)
+ *                  keep float64 registers and only halve the bytes moved -- for them TRGL_F32 == TRGL_F32IO.
  *   TRGL_F64_OUT32 u float64, x float32, float64 arithmetic   (output_dtype=float32 on float64 inputs)
  *   TRGL_F32_OUT64 u float32, x float64, float64 arithmetic   (float32 inputs, default output dtype)
  */

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
+#include "trgl_device.cuh"
 
 namespace trgl {
 
@@ -122,7 +123,7 @@ __device__ __forceinline__ void hs_epipole(const double e[3], double x, double y
     ex = fma(-x, e[2], e[0]);
     ey = fma(-y, e[2], e[1]);
     f = e[2];
-    const double inv = 1.0 / sqrt(fma(ex, ex, ey * ey));
+    const double inv = rsqrt(fma(ex, ex, ey * ey));       // 0 -> inf -> NaN epipole -> NaN point, like the reference
     ex *= inv; ey *= inv; f *= inv;
     if (f < 0.0) { ex = -ex; ey = -ey; f = -f; }
 }
@@ -160,30 +161,36 @@ __device__ __forceinline__ void hs_correct(const HSParams& hs, double x1, double
 #pragma unroll
     for (int i = 0; i < 7; ++i) finite_coeffs = finite_coeffs && (fabs(k[i]) <= DBL_MAX);
     // ---- fast path certificate ----
-    const double s0 = d * d / fma(b, b, f2 * f2 * d * d);
+    const double s0 = d * d * fast_rcp(fma(b, b, f2 * f2 * d * d));      // 0/0 -> NaN -> certificate fails -> slow path
     const double f1s = f1 * f1;
     bool fast = finite_coeffs && (f1s * s0 < 1.0);
     double T0 = 0.0;
     if (fast) {
-        T0 = sqrt(s0 / (1.0 - f1s * s0));
+        T0 = sqrt(s0 * fast_rcp(1.0 - f1s * s0));
         const double bound = T0 * fma(T0, fma(T0, fma(T0, fma(T0, 6.0 * fabs(k[6]), 5.0 * fabs(k[5])),
                                                       4.0 * fabs(k[4])), 3.0 * fabs(k[3])), 2.0 * fabs(k[2]));
         fast = k[1] > bound;
     }
     if (fast) {
+        // Bracketed Newton on g (strictly increasing on [-T0, T0]).  Newton converges quadratically, so once a
+        // NEWTON step is below 1e-8 |t| the iterate it produced is exact to rounding (error ~ step^2); bisection steps
+        // only stop on a 2-ulp bracket.  (Demanding a 2-ulp Newton step made single lanes bisect for ~50 rounds.)
         double lo = -T0, hi = T0;
         t = 0.0;
-        for (int it = 0; it < 100; ++it) {
+#pragma unroll 1
+        for (int it = 0; it < 64; ++it) {
             double g = k[6], dg = 0.0;
 #pragma unroll
             for (int i = 5; i >= 0; --i) { dg = fma(dg, t, g); g = fma(g, t, k[i]); }
             if (g == 0.0) break;
             if (g < 0.0) lo = t; else hi = t;
-            double tn = t - g / dg;
-            if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
+            double tn = fma(-g, fast_rcp(dg), t);          // g' > 0 on the bracket (certificate)
+            if (tn == t) break;                            // Newton step below half an ulp: converged
+            const bool newton = (tn >= lo && tn <= hi);
+            if (!newton) tn = 0.5 * (lo + hi);
             const double step = fabs(tn - t);
             t = tn;
-            if (step <= 4e-16 * fabs(tn) || (hi - lo) <= 4e-16 * fabs(tn)) break;
+            if ((newton && step <= 1e-8 * fabs(tn)) || (hi - lo) <= 4e-16 * fabs(tn)) break;
         }
     } else if (finite_coeffs) {
         t = hs_select_dk(k, a, b, c, d, f1, f2);
@@ -198,15 +205,16 @@ __device__ __forceinline__ void hs_correct(const HSParams& hs, double x1, double
     }
     // closest points to the origin on the two epipolar lines, then back through R^T and T^-1
     {
-        const double hz = fma(t * t, f1s, 1.0);
-        const double hx = t * t * f1 / hz, hy = t / hz;
+        const double iz = fast_rcp(fma(t * t, f1s, 1.0));
+        const double hx = t * t * f1 * iz, hy = t * iz;
         n1x = fma(e1x, hx, -e1y * hy) + x1;
         n1y = fma(e1y, hx, e1x * hy) + y1;
     }
     {
         const double ct_d = fma(c, t, d), at_b = fma(a, t, b);
         const double hz = fma(f2 * f2 * ct_d, ct_d, at_b * at_b);
-        const double hx = f2 * ct_d * ct_d / hz, hy = -at_b * ct_d / hz;
+        const double iz = (hz > 0.0) ? fast_rcp(hz) : 1.0 / hz;
+        const double hx = f2 * ct_d * ct_d * iz, hy = -at_b * ct_d * iz;
         n2x = fma(e2x, hx, -e2y * hy) + x2;
         n2y = fma(e2y, hx, e2x * hy) + y2;
     }

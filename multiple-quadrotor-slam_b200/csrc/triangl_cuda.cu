@@ -137,6 +137,7 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
 int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
                         int64_t n, double tol, int semantics, int mode, cudaStream_t s) {
     if (n == 0) return TRGL_OK;
+    if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         k_iterative_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(
@@ -151,6 +152,7 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
 int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                         int64_t n, double maxc, int rows, int mode, cudaStream_t s) {
     if (n == 0) return TRGL_OK;
+    if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
@@ -168,6 +170,7 @@ int launch_polynomial(const void* u1, const void* u2, const double* P1, const do
                       uint8_t* status, void* u1c, void* u2c, unsigned int* flags, int64_t n, double maxc, int rows,
                       int mode, cudaStream_t s) {
     if (n == 0) return TRGL_OK;
+    if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
