@@ -29,6 +29,8 @@ __device__ __forceinline__ double tfma(double a, double b, double c) { return fm
 __device__ __forceinline__ float tfma(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double tsqrt(double a) { return sqrt(a); }
 __device__ __forceinline__ float tsqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double trsqrt(double a) { return rsqrt(a); }
+__device__ __forceinline__ float trsqrt(float a) { return rsqrtf(a); }
 __device__ __forceinline__ double tabs(double a) { return fabs(a); }
 __device__ __forceinline__ float tabs(float a) { return fabsf(a); }
 __device__ __forceinline__ double tmax(double a, double b) { return fmax(a, b); }

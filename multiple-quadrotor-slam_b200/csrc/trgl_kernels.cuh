@@ -120,50 +120,101 @@ k_linear_ls_tma(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams
 }
 
 // ---- iterative_LS_triangulation (triangulation.c:104-161 / triangulation.py:100-195) ---------------------------
+// One re-weighted solve + depth test.  Returns true when the reference's loop breaks at this iteration.
+template <typename TC>
+__device__ __forceinline__ bool iter_ls_step(const Cams<TC>& cams, TC a, TC b, TC c, TC d, const TC M1[6], const TC v1[3],
+                                             const TC M2[6], const TC v2[3], TC& w1, TC& w2, TC& d1, TC& d2, TC& d1n,
+                                             TC& d2n, TC xs[3], TC tolerance, int py_semantics) {
+    solve_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, xs);
+    d1n = tfma(cams.P1[8], xs[0], tfma(cams.P1[9], xs[1], tfma(cams.P1[10], xs[2], cams.P1[11])));    // triangulation.c:133
+    d2n = tfma(cams.P2[8], xs[0], tfma(cams.P2[9], xs[1], tfma(cams.P2[10], xs[2], cams.P2[11])));
+    const bool conv = (tabs(d1n - d1) <= tolerance) && (tabs(d2n - d2) <= tolerance);
+    const bool zero = !py_semantics && ((d1n == TC(0)) || (d2n == TC(0)));                             // triangulation.c:138
+    if (conv || zero) return true;
+    // cumulative re-weighting, triangulation.c:143-146 (1/0 keeps its IEEE meaning for the Python control flow)
+    w1 *= (d1n != TC(0)) ? fast_rcp(d1n) : TC(1) / d1n;
+    w2 *= (d2n != TC(0)) ? fast_rcp(d2n) : TC(1) / d2n;
+    d1 = d1n; d2 = d2n;
+    return false;
+}
+
+__device__ __forceinline__ int iter_ls_status(int it, double d1n, double d2n) {       // triangulation.c:154-159
+    int st = (it < 10) && (d1n > 0.0) && (d2n > 0.0);
+    if (d1n <= 0.0) st -= 1;
+    if (d2n <= 0.0) st -= 2;
+    return st;
+}
+
+// Two phases per block.  Phase 1: every thread runs the first kPhase1 iterations of its point (on translating rigs every
+// point converges at the second solve; on rotating rigs ~70 % do).  Points still running are compacted into shared
+// memory (their four input scalars and the loop state), and in phase 2 the block runs the remaining iterations on the
+// dense list, so warps stay full instead of idling on the ~30 % of lanes that need all 10 solves.
+constexpr int kPhase1 = 2;
+
 template <typename TI, typename TC, typename TO, int PPT>
 __global__ void __launch_bounds__(kThreads)
 k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC> cams,
                TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
                const TC tolerance, const int py_semantics) {
     __shared__ TO stage[kWarps][96];
-    const int warp = threadIdx.x >> 5;
-    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT);
-    TC in[PPT][4];
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        const int64_t i = block_base + p * kThreads + threadIdx.x;
-        if (i < n) {
-            load_uv<TC>(u1, i, in[p][0], in[p][1]);
-            load_uv<TC>(u2, i, in[p][2], in[p][3]);
-        } else {
-            in[p][0] = in[p][1] = in[p][2] = in[p][3] = TC(0);
-        }
-    }
-#pragma unroll 1
-    for (int p = 0; p < PPT; ++p) {
-        const int64_t i = block_base + p * kThreads + threadIdx.x;
-        TC M1[6], v1[3], M2[6], v2[3], xs[3];
-        point_blocks<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], M1, v1, M2, v2);
+    __shared__ TC s_state[8][kThreads];
+    __shared__ int s_src[kThreads];
+    __shared__ int s_count;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * kThreads;
+    const int64_t i = block_base + threadIdx.x;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    TC a = 0, b = 0, c = 0, d = 0;
+    if (i < n) { load_uv<TC>(u1, i, a, b); load_uv<TC>(u2, i, c, d); }
+    const int it_never = py_semantics ? 9 : 10;     // value of the loop variable after a loop that never breaks
+    {
+        TC M1[6], v1[3], M2[6], v2[3], xs[3] = {0, 0, 0};
+        point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
         TC w1 = 1, w2 = 1, d1 = 1, d2 = 1, d1n = 1, d2n = 1;
-        int it = py_semantics ? 9 : 10;         // value of the loop variable after a loop that never breaks
+        int it = -1;
 #pragma unroll 1
-        for (int k = 0; k < 10; ++k) {
-            solve_blocks<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], M1, v1, M2, v2, w1, w2, xs);
-            d1n = tfma(cams.P1[8], xs[0], tfma(cams.P1[9], xs[1], tfma(cams.P1[10], xs[2], cams.P1[11])));
-            d2n = tfma(cams.P2[8], xs[0], tfma(cams.P2[9], xs[1], tfma(cams.P2[10], xs[2], cams.P2[11])));
-            const bool conv = (tabs(d1n - d1) <= tolerance) && (tabs(d2n - d2) <= tolerance);
-            const bool zero = !py_semantics && ((d1n == TC(0)) || (d2n == TC(0)));       // triangulation.c:138
-            if (conv || zero) { it = k; break; }
-            w1 *= TC(1) / d1n;                   // cumulative re-weighting, triangulation.c:143-146
-            w2 *= TC(1) / d2n;
-            d1 = d1n; d2 = d2n;
+        for (int k = 0; k < kPhase1; ++k)
+            if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
+                it = k; break;
+            }
+        const bool pending = (it < 0) && (i < n);
+        const unsigned ball = __ballot_sync(0xffffffffu, pending);
+        if (ball) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_count, __popc(ball));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pending) {
+                const int slot = base + __popc(ball & ((1u << lane) - 1u));
+                s_state[0][slot] = a; s_state[1][slot] = b; s_state[2][slot] = c; s_state[3][slot] = d;
+                s_state[4][slot] = w1; s_state[5][slot] = w2; s_state[6][slot] = d1; s_state[7][slot] = d2;
+                s_src[slot] = threadIdx.x;
+            }
         }
-        int st = (it < 10) && (d1n > TC(0)) && (d2n > TC(0));
-        if (d1n <= TC(0)) st -= 1;
-        if (d2n <= TC(0)) st -= 2;
-        store_x_warp<TO>(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
-                         static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage[warp]);
-        if (i < n) status[i] = st;
+        // finished points leave through the coalesced path (pending lanes write a placeholder that phase 2 overwrites)
+        store_x_warp<TO>(x, block_base + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+                         static_cast<TO>(xs[2]), stage[warp]);
+        if (i < n && !pending) status[i] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+    }
+    __syncthreads();
+    const int count = s_count;
+    if (static_cast<int>(threadIdx.x) < count) {
+        const int slot = threadIdx.x;
+        a = s_state[0][slot]; b = s_state[1][slot]; c = s_state[2][slot]; d = s_state[3][slot];
+        TC w1 = s_state[4][slot], w2 = s_state[5][slot], d1 = s_state[6][slot], d2 = s_state[7][slot], d1n = d1, d2n = d2;
+        const int64_t dst = block_base + s_src[slot];
+        TC M1[6], v1[3], M2[6], v2[3], xs[3];
+        point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
+        int it = it_never;
+#pragma unroll 1
+        for (int k = kPhase1; k < 10; ++k)
+            if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
+                it = k; break;
+            }
+        x[3 * dst + 0] = static_cast<TO>(xs[0]);
+        x[3 * dst + 1] = static_cast<TO>(xs[1]);
+        x[3 * dst + 2] = static_cast<TO>(xs[2]);
+        status[dst] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
     }
 }
 
@@ -266,7 +317,7 @@ __device__ __forceinline__ bool eigen_point_fast(const Cams<TC>& cams, TC u1x, T
         TC C[6], x0[3];
         const TC det = sym3_cofactors(M, C);
         sym3_apply(C, v, fast_rcp(det), x0);
-        const TC nrm = TC(1) / tsqrt(tfma(x0[0], x0[0], tfma(x0[1], x0[1], tfma(x0[2], x0[2], TC(1)))));
+        const TC nrm = trsqrt(tfma(x0[0], x0[0], tfma(x0[1], x0[1], tfma(x0[2], x0[2], TC(1)))));
         X[0] = x0[0] * nrm; X[1] = x0[1] * nrm; X[2] = x0[2] * nrm; X[3] = nrm;
     }
     const TC tol = TC(4) * Num<TC>::eps() * tr;
@@ -290,7 +341,7 @@ __device__ __forceinline__ bool eigen_point_fast(const Cams<TC>& cams, TC u1x, T
         for (int k = 0; k < 10; ++k) S[k] = G[k];
         S[0] -= lam; S[4] -= lam; S[7] -= lam; S[9] -= lam;
         if (ldl4<TC, true>(S, X, y) < 0) return false;
-        const TC nrm = TC(1) / tsqrt(tfma(y[0], y[0], tfma(y[1], y[1], tfma(y[2], y[2], y[3] * y[3]))));
+        const TC nrm = trsqrt(tfma(y[0], y[0], tfma(y[1], y[1], tfma(y[2], y[2], y[3] * y[3]))));
 #pragma unroll
         for (int k = 0; k < 4; ++k) X[k] = y[k] * nrm;
     }
