@@ -380,12 +380,41 @@ __device__ __forceinline__ void solve_blocks(const Cams<T>& cams, T a, T b, T c,
     }
 }
 
-// linear_LS point: unweighted system.
+// Accumulate two more rows into the normal equations.
 template <typename T>
-__device__ __forceinline__ void ls_point(const Cams<T>& cams, T a, T b, T c, T d, T x[3]) {
-    T M1[6], v1[3], M2[6], v2[3];
-    point_blocks<T>(cams, a, b, c, d, M1, v1, M2, v2);
-    solve_blocks<T>(cams, a, b, c, d, M1, v1, M2, v2, T(1), T(1), x);
+__device__ __forceinline__ void normal_add2(const T r0[4], const T r1[4], T M[6], T v[3]) {
+    M[0] = tfma(r1[0], r1[0], tfma(r0[0], r0[0], M[0]));
+    M[1] = tfma(r1[0], r1[1], tfma(r0[0], r0[1], M[1]));
+    M[2] = tfma(r1[0], r1[2], tfma(r0[0], r0[2], M[2]));
+    M[3] = tfma(r1[1], r1[1], tfma(r0[1], r0[1], M[3]));
+    M[4] = tfma(r1[1], r1[2], tfma(r0[1], r0[2], M[4]));
+    M[5] = tfma(r1[2], r1[2], tfma(r0[2], r0[2], M[5]));
+    v[0] = tfma(-r1[0], r1[3], tfma(-r0[0], r0[3], v[0]));
+    v[1] = tfma(-r1[1], r1[3], tfma(-r0[1], r0[3], v[1]));
+    v[2] = tfma(-r1[2], r1[3], tfma(-r0[2], r0[3], v[2]));
+}
+
+// linear_LS point, straight-line part only (no calls, so the compiler can interleave several points of one thread).
+// Returns false when the point must be redone by solve_point_careful (FP64: anything but tier 1; FP32: beyond the
+// reach of the inline refinement step).
+template <typename T>
+__device__ __forceinline__ bool ls_point_fast(const Cams<T>& cams, T a, T b, T c, T d, T x[3]) {
+    T r0[4], r1[4], M[6], v[3], C[6];
+    dlt_rows<T>(cams.P1, a, b, r0, r1);
+    normal_acc2<T>(r0, r1, M, v);
+    dlt_rows<T>(cams.P2, c, d, r0, r1);
+    normal_add2<T>(r0, r1, M, v);
+    const T det = sym3_cofactors(M, C);
+    const T tr = M[0] + M[3] + M[5];
+    const T tr3 = tr * tr * tr;
+    const T inv = fast_rcp(det);
+    sym3_apply(C, v, inv, x);
+    if constexpr (sizeof(T) == 8) {
+        return tr3 < Tiers<T>::t1() * det;
+    } else {
+        refine_inline<T>(cams, a, b, c, d, T(1), T(1), C, inv, x);
+        return tr3 < Tiers<T>::t2() * det;
+    }
 }
 
 }  // namespace trgl

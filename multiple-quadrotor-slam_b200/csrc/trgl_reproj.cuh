@@ -63,7 +63,7 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __re
 
 template <typename TX, typename TP>
 __global__ void __launch_bounds__(kThreads)
-k_reproj_error(const TX* __restrict__ x, const TP* __restrict__ imgp, const ProjParams pp, TP* __restrict__ proj,
+k_reproj_error(const TX* __restrict__ x, const TP* __restrict__ imgp, const __grid_constant__ ProjParams pp, TP* __restrict__ proj,
                double* __restrict__ partials, const int64_t n) {
     double acc[5] = {0, 0, 0, 0, 0};          // sum dx^2, sum dy^2, finite count, sum |dx|, sum |dy|
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
@@ -95,7 +95,7 @@ k_reproj_error(const TX* __restrict__ x, const TP* __restrict__ imgp, const Proj
 
 template <typename TI, typename TO, typename TS>
 __global__ void __launch_bounds__(kThreads)
-k_pair_reproj(const TO* __restrict__ x, const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<double> cams,
+k_pair_reproj(const TO* __restrict__ x, const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<double> cams,
               const TS* __restrict__ status, const int min_status, const double max_sq_err, TO* __restrict__ err1,
               TO* __restrict__ err2, uint8_t* __restrict__ good, double* __restrict__ partials, const int64_t n) {
     double acc[4] = {0, 0, 0, 0};             // sum err1 (good), sum err2 (good), #good, #status > min_status
@@ -136,7 +136,7 @@ struct F8Params { double m1[2], m2[2], s1, s2; };
 
 template <typename TI, int STAGE>
 __global__ void __launch_bounds__(kThreads)
-k_f8_reduce(const TI* __restrict__ u1, const TI* __restrict__ u2, const F8Params fp, double* __restrict__ partials,
+k_f8_reduce(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ F8Params fp, double* __restrict__ partials,
             const int64_t n) {
     constexpr int NV = STAGE == 0 ? 4 : (STAGE == 1 ? 2 : 45);
     double acc[NV];

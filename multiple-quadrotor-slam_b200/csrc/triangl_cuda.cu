@@ -100,6 +100,14 @@ int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_
     return TRGL_OK;
 }
 
+template <typename TI, typename TC, typename TO>
+void launch_ls_direct(int ppt, const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n,
+                      cudaStream_t s) {
+    if (ppt == 1) k_linear_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n);
+    else if (ppt == 2) k_linear_ls<TI, TC, TO, 2><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n);
+    else k_linear_ls<TI, TC, TO, 4><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n);
+}
+
 int launch_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                      int64_t n, int mode, cudaStream_t s) {
     if (n == 0) return TRGL_OK;
@@ -107,7 +115,7 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
     int variant = g_variant.load();
     // auto: the persistent bulk-async pipeline pays off once its prologue/tail is amortised (measured cross-over
     // between 10 M and 100 M points on B200); smaller batches use per-thread vector loads with 4 points in flight.
-    if (variant < 0) variant = (n >= (int64_t(1) << 25)) ? 2 : 0;
+    if (variant < 0) variant = (n >= (int64_t(1) << 25)) ? 1 : 0;
     // cp.async.bulk needs 16-byte aligned global addresses; fall back to per-thread loads otherwise
     if ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & 15) variant = 0;
     MODE_SWITCH(mode, {
@@ -122,10 +130,7 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
             case 4: rc = launch_ls_tma<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s); break;
             case 5: rc = launch_ls_tma<TI, TC, TO, 4, 4, 1>(a, b, cams, xo, status, n, s); break;
             case 6: rc = launch_ls_tma<TI, TC, TO, 1, 8, 3>(a, b, cams, xo, status, n, s); break;
-            default:
-                if (ppt == 1) k_linear_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n);
-                else if (ppt == 2) k_linear_ls<TI, TC, TO, 2><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n);
-                else k_linear_ls<TI, TC, TO, 4><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n);
+            default: launch_ls_direct<TI, TC, TO>(ppt, a, b, cams, xo, status, n, s);
         }
         if (rc) return rc;
     })
