@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Turn the scratch output of tools/gpu_round.sh (gpurun_out/<tag>/) into the committed evidence under profiles/:
+     profiles/<tag>_launches.md     per-kernel share of the ncu launch list (cold-cache, serialised: compare shares)
+     profiles/<tag>_ncu_full.md     selected metrics of each `ncu --set full` capture (+ top stall reasons per source line)
+     profiles/<tag>_bench_*.json    the bench lines of the same call
+     profiles/traffic.json          DRAM bytes per point per solver (read by bench.py for roofline.traffic)
+   python tools/summarise_ncu.py <tag>"""
+import csv
+import glob
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+src = os.path.join(ROOT, "gpurun_out", tag)
+dst = os.path.join(ROOT, "profiles")
+os.makedirs(dst, exist_ok=True)
+
+METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+] + ["smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % k for k in (
+    "wait", "long_scoreboard", "short_scoreboard", "math_pipe_throttle", "barrier", "not_selected", "branch_resolving",
+    "lg_throttle", "mio_throttle", "dispatch_stall", "no_instruction", "drain")]
+
+
+def ncu_csv(rep, page):
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    lines = [ln for ln in out.splitlines() if ln.startswith('"')]
+    return list(csv.reader(io.StringIO("\n".join(lines))))
+
+
+def num(s):
+    try:
+        return float(s.replace(",", ""))
+    except ValueError:
+        return None
+
+
+# ---- launch list ------------------------------------------------------------------------------------------------
+ll = os.path.join(src, "launches.csv")
+if os.path.isfile(ll):
+    rows = [r for r in csv.reader(open(ll)) if len(r) > 10]
+    h = rows[0]
+    ki, vi, gi = h.index("Kernel Name"), h.index("Metric Value"), h.index("Grid Size")
+    agg = defaultdict(list)
+    for r in rows[1:]:
+        v = num(r[vi])
+        if v is not None:
+            agg[(r[ki].split("(")[0], r[gi])].append(v)
+    tot = sum(sum(v) for v in agg.values())
+    with open(os.path.join(dst, tag + "_launches.md"), "w") as f:
+        f.write("# ncu launch list, `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (%s)\n\n" % tag)
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` -- per-launch times are cold-cache and "
+                "serialised; compare SHARES with bench.py's per_solver.share_of_step, not absolutes.  Grids of 39063 / 9766 "
+                "blocks are the 10 M-point device-resident steps; the 8192 / 2048-block grids are the 2 Mi-point chunks of "
+                "the host-mode (e2e) pipeline.\n\n")
+        f.write("| kernel | grid | launches | mean us | share of all kernel time |\n|---|---|---|---|---|\n")
+        for (k, g), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write("| `%s` | %s | %d | %.1f | %.3f |\n" % (k.replace("void ", ""), g, len(v), sum(v) / len(v) / 1e3, sum(v) / tot))
+        # share within the device-resident step only (largest grid per kernel)
+        f.write("\nDevice-resident 10 M-point launches only (the timed `value` region):\n\n| kernel | mean us | share |\n|---|---|---|\n")
+        big = {}
+        for (k, g), v in agg.items():
+            blocks = int(g.strip("()").split(",")[0])
+            if k not in big or blocks > big[k][0]:
+                big[k] = (blocks, v)
+        nsolv = {k: (len(v[1])) for k, v in big.items()}
+        # pair_reproj runs once per solver per step -> weight by launches per step
+        per_step = {}
+        for k, (blocks, v) in big.items():
+            per_step[k] = sum(v) / len(v) * (4 if "pair_reproj" in k and len(big) < 7 else 1)
+        for k, (blocks, v) in sorted(big.items(), key=lambda kv: -sum(kv[1][1]) / len(kv[1][1])):
+            f.write("| `%s` | %.1f | %.3f |\n" % (k.replace("void ", ""), sum(v) / len(v) / 1e3,
+                                                   sum(v) / len(v) / sum(sum(x[1]) / len(x[1]) for x in big.values())))
+    print("wrote", tag + "_launches.md")
+
+# ---- full captures ------------------------------------------------------------------------------------------------
+traffic = {}
+with open(os.path.join(dst, tag + "_ncu_full.md"), "w") as f:
+    f.write("# `ncu --set full --clock-control none --import-source on` captures (%s)\n\n" % tag)
+    f.write("One launch per kernel after warm-up.  Times under the profiler are not bench values.\n")
+    for rep in sorted(glob.glob(os.path.join(src, "full_*.ncu-rep"))):
+        raw = ncu_csv(rep, "raw")
+        if len(raw) < 3:
+            continue
+        h, u, v = raw[0], raw[1], raw[2]
+        col = {n: i for i, n in enumerate(h)}
+        name = v[col["Kernel Name"]]
+        f.write("\n## %s\n\n`%s`\n\n| metric | value | unit |\n|---|---|---|\n" % (os.path.basename(rep), name))
+        for m in METRICS:
+            if m in col:
+                f.write("| %s | %s | %s |\n" % (m, v[col[m]], u[col[m]]))
+
+        def bytes_of(m):
+            x = num(v[col[m]]); unit = u[col[m]]
+            return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        grid = num(v[col["launch__grid_size"]])
+        tr = bytes_of("dram__bytes_read.sum") + bytes_of("dram__bytes_write.sum")
+        f.write("| **DRAM traffic per launch** | %.4g | byte |\n" % tr)
+        key = os.path.basename(rep)[len("full_k_"):-len(".ncu-rep")]
+        traffic[key] = tr
+        # source page: top lines by sampled stalls
+        srcp = ncu_csv(rep, "source")
+        while srcp and srcp[0][0] != "Address":
+            srcp.pop(0)
+        if srcp:
+            hh = srcp[0]
+            try:
+                si = hh.index("# Samples") if "# Samples" in hh else hh.index("Sampling Data (All)")
+            except ValueError:
+                si = None
+            s_src = hh.index("Source") if "Source" in hh else 1
+            if si is not None:
+                ranked = sorted((r for r in srcp[1:] if len(r) > si and num(r[si])), key=lambda r: -num(r[si]))[:12]
+                total = sum(num(r[si]) or 0 for r in srcp[1:] if len(r) > si)
+                f.write("\nTop SASS lines by warp-state samples (total %d):\n\n| samples | share | instruction |\n|---|---|---|\n" % total)
+                for r in ranked:
+                    f.write("| %s | %.3f | `%s` |\n" % (r[si], num(r[si]) / max(total, 1), r[s_src].strip()[:110]))
+print("wrote", tag + "_ncu_full.md")
+
+for fn in glob.glob(os.path.join(src, "bench_*.json")) + glob.glob(os.path.join(src, "sweep_*.jsonl")) + \
+        glob.glob(os.path.join(src, "*.log")):
+    if os.path.getsize(fn) and "full_" not in os.path.basename(fn) and "launches_bench" not in fn:
+        shutil.copy(fn, os.path.join(dst, tag + "_" + os.path.basename(fn)))
+print(json.dumps(traffic))
