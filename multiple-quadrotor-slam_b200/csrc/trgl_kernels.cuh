@@ -148,77 +148,108 @@ __device__ __forceinline__ int iter_ls_status(int it, double d1n, double d2n) { 
     return st;
 }
 
-// Two phases per block.  Phase 1: every thread runs the first kPhase1 iterations of its point (on translating rigs every
-// point converges at the second solve; on rotating rigs ~70 % do).  Points still running are compacted into shared
-// memory (their four input scalars and the loop state), and in phase 2 the block runs the remaining iterations on the
-// dense list, so warps stay full instead of idling on the ~30 % of lanes that need all 10 solves.
+// Persistent CTAs (one grid-stride loop over 256-point tiles, next tile's four input scalars prefetched into registers
+// while the current tile is solved) with a block-level work queue in shared memory for the divergent tail:
+//   phase 1: every thread runs the first kPhase1 iterations of its point (on translating rigs every point converges
+//            at the second solve; on rotating rigs ~70 % do).  Finished points leave through the coalesced store.
+//   queue  : points still running push their four input scalars and loop state (w1,w2,d1,d2) to the queue.
+//   phase 2: whenever the queue holds >= 256 entries the block runs the remaining iterations on a full batch, so
+//            every warp is dense instead of idling on the ~30 % of lanes that need all 10 solves; the remainder is
+//            flushed after the last tile.
 constexpr int kPhase1 = 2;
+constexpr int kQueueCap = 2 * kThreads;
 
-template <typename TI, typename TC, typename TO, int PPT>
-__global__ void __launch_bounds__(kThreads)
+// Shared memory of one k_iterative_ls CTA (dynamic: 49 KB in the all-double mode, just above the static limit).
+template <typename TI, typename TC, typename TO>
+struct IterSmem {
+    PairPrefetch<TI, kThreads> pre;          // cp.async landing zone of the next tile
+    TC q_state[8][kQueueCap];                // queue: a b c d w1 w2 d1 d2
+    int64_t q_idx[kQueueCap];                //        global point index
+    TO stage[kWarps][96];                    // coalesced (n,3) store staging
+    int q_count;
+};
+
+template <typename TC, typename TO>
+__device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*q_state)[kQueueCap], const int64_t* q_idx,
+                                               int slot, TO* __restrict__ x, int32_t* __restrict__ status,
+                                               TC tolerance, int py_semantics) {
+    const TC a = q_state[0][slot], b = q_state[1][slot], c = q_state[2][slot], d = q_state[3][slot];
+    TC w1 = q_state[4][slot], w2 = q_state[5][slot], d1 = q_state[6][slot], d2 = q_state[7][slot], d1n = d1, d2n = d2;
+    const int64_t dst = q_idx[slot];
+    TC M1[6], v1[3], M2[6], v2[3], xs[3];
+    point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
+    int it = py_semantics ? 9 : 10;                 // value of the loop variable after a loop that never breaks
+#pragma unroll 1
+    for (int k = kPhase1; k < 10; ++k)
+        if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
+            it = k; break;
+        }
+    x[3 * dst + 0] = static_cast<TO>(xs[0]);
+    x[3 * dst + 1] = static_cast<TO>(xs[1]);
+    x[3 * dst + 2] = static_cast<TO>(xs[2]);
+    status[dst] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+}
+
+template <typename TI, typename TC, typename TO>
+__global__ void __launch_bounds__(kThreads, 2)
 k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
                const TC tolerance, const int py_semantics) {
-    __shared__ TO stage[kWarps][96];
-    __shared__ TC s_state[8][kThreads];
-    __shared__ int s_src[kThreads];
-    __shared__ int s_count;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    IterSmem<TI, TC, TO>& sm = *reinterpret_cast<IterSmem<TI, TC, TO>*>(smem_raw);
+    auto& pre = sm.pre; auto& q_state = sm.q_state; auto& q_idx = sm.q_idx; auto& stage = sm.stage; int& q_count = sm.q_count;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * kThreads;
-    const int64_t i = block_base + threadIdx.x;
-    if (threadIdx.x == 0) s_count = 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+    if (threadIdx.x == 0) q_count = 0;
     __syncthreads();
-    TC a = 0, b = 0, c = 0, d = 0;
-    if (i < n) { load_uv<TC>(u1, i, a, b); load_uv<TC>(u2, i, c, d); }
-    const int it_never = py_semantics ? 9 : 10;     // value of the loop variable after a loop that never breaks
-    {
-        TC M1[6], v1[3], M2[6], v2[3], xs[3] = {0, 0, 0};
-        point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
-        TC w1 = 1, w2 = 1, d1 = 1, d2 = 1, d1n = 1, d2n = 1;
-        int it = -1;
+    int64_t tile = static_cast<int64_t>(blockIdx.x) * kThreads;
+    int count = 0;                                       // queue length, identical in every thread
+    pre.issue(u1, u2, tile + threadIdx.x, n);
+    for (; tile < n; tile += stride) {
+        const int64_t i = tile + threadIdx.x;
+        TC a, b, c, d;
+        pre.take(i, n, a, b, c, d);
+        pre.issue(u1, u2, i + stride, n);                // next tile of this CTA lands while this one is solved
+        {
+            TC M1[6], v1[3], M2[6], v2[3], xs[3] = {0, 0, 0};
+            point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
+            TC w1 = 1, w2 = 1, d1 = 1, d2 = 1, d1n = 1, d2n = 1;
+            int it = -1;
 #pragma unroll 1
-        for (int k = 0; k < kPhase1; ++k)
-            if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
-                it = k; break;
+            for (int k = 0; k < kPhase1; ++k)
+                if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
+                    it = k; break;
+                }
+            const bool pending = (it < 0) && (i < n);
+            const unsigned ball = __ballot_sync(0xffffffffu, pending);
+            if (ball) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&q_count, __popc(ball));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pending) {
+                    const int slot = base + __popc(ball & ((1u << lane) - 1u));
+                    q_state[0][slot] = a; q_state[1][slot] = b; q_state[2][slot] = c; q_state[3][slot] = d;
+                    q_state[4][slot] = w1; q_state[5][slot] = w2; q_state[6][slot] = d1; q_state[7][slot] = d2;
+                    q_idx[slot] = i;
+                }
             }
-        const bool pending = (it < 0) && (i < n);
-        const unsigned ball = __ballot_sync(0xffffffffu, pending);
-        if (ball) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_count, __popc(ball));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pending) {
-                const int slot = base + __popc(ball & ((1u << lane) - 1u));
-                s_state[0][slot] = a; s_state[1][slot] = b; s_state[2][slot] = c; s_state[3][slot] = d;
-                s_state[4][slot] = w1; s_state[5][slot] = w2; s_state[6][slot] = d1; s_state[7][slot] = d2;
-                s_src[slot] = threadIdx.x;
-            }
+            // finished points leave through the coalesced path (pending lanes write a placeholder that phase 2 overwrites)
+            store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+                             static_cast<TO>(xs[2]), stage[warp]);
+            if (i < n && !pending) status[i] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+            // every thread learns how many points this tile queued (the barrier also publishes the queue entries);
+            // the queue length lives in a register so the drain decision is uniform without re-reading q_count
+            count += __syncthreads_count(pending);
         }
-        // finished points leave through the coalesced path (pending lanes write a placeholder that phase 2 overwrites)
-        store_x_warp<TO>(x, block_base + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                         static_cast<TO>(xs[2]), stage[warp]);
-        if (i < n && !pending) status[i] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+        if (count >= kThreads) {                         // count < kQueueCap: <= kThreads-1 left over + kThreads pushed
+            count -= kThreads;
+            if (threadIdx.x == 0) q_count = count;       // nobody pushes before the barrier below
+            iter_ls_phase2<TC, TO>(cams, q_state, q_idx, count + threadIdx.x, x, status, tolerance, py_semantics);
+            __syncthreads();
+        }
     }
-    __syncthreads();
-    const int count = s_count;
-    if (static_cast<int>(threadIdx.x) < count) {
-        const int slot = threadIdx.x;
-        a = s_state[0][slot]; b = s_state[1][slot]; c = s_state[2][slot]; d = s_state[3][slot];
-        TC w1 = s_state[4][slot], w2 = s_state[5][slot], d1 = s_state[6][slot], d2 = s_state[7][slot], d1n = d1, d2n = d2;
-        const int64_t dst = block_base + s_src[slot];
-        TC M1[6], v1[3], M2[6], v2[3], xs[3];
-        point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
-        int it = it_never;
-#pragma unroll 1
-        for (int k = kPhase1; k < 10; ++k)
-            if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
-                it = k; break;
-            }
-        x[3 * dst + 0] = static_cast<TO>(xs[0]);
-        x[3 * dst + 1] = static_cast<TO>(xs[1]);
-        x[3 * dst + 2] = static_cast<TO>(xs[2]);
-        status[dst] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
-    }
+    if (static_cast<int>(threadIdx.x) < count)
+        iter_ls_phase2<TC, TO>(cams, q_state, q_idx, threadIdx.x, x, status, tolerance, py_semantics);
 }
 
 // ---- linear_eigen_triangulation (triangulation.py:6-25) --------------------------------------------------------
@@ -369,61 +400,76 @@ __device__ __forceinline__ void eigen_point(const Cams<TC>& cams, TC u1x, TC u1y
     good = (xs[0] == xs[0]) && (xs[1] == xs[1]) && (xs[2] == xs[2]) && (m <= max_coord);   // NaN -> False, :23
 }
 
+// Persistent CTAs: grid-stride loop over 256-point tiles, the next tile's inputs are prefetched into registers while the
+// current tile is solved (the solve is ~700 instructions per point, so one tile of lookahead hides the HBM latency).
 template <typename TI, typename TC, typename TO, int ROWS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord) {
     __shared__ TO stage[kWarps][96];
+    __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
     const int warp = threadIdx.x >> 5;
-    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * kThreads;
-    const int64_t i = block_base + threadIdx.x;
-    TC a = 0, b = 0, c = 0, d = 0;
-    if (i < n) { load_uv<TC>(u1, i, a, b); load_uv<TC>(u2, i, c, d); }
-    TC xs[3]; bool good;
-    eigen_point<TC, ROWS>(cams, a, b, c, d, max_coord, xs, good);
-    store_x_warp<TO>(x, block_base + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                     static_cast<TO>(xs[2]), stage[warp]);
-    if (i < n) status[i] = good ? 1 : 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+    int64_t tile = static_cast<int64_t>(blockIdx.x) * kThreads;
+    pre.issue(u1, u2, tile + threadIdx.x, n);
+    for (; tile < n; tile += stride) {
+        const int64_t i = tile + threadIdx.x;
+        TC a, b, c, d;
+        pre.take(i, n, a, b, c, d);
+        pre.issue(u1, u2, i + stride, n);
+        TC xs[3]; bool good;
+        eigen_point<TC, ROWS>(cams, a, b, c, d, max_coord, xs, good);
+        store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+                         static_cast<TO>(xs[2]), stage[warp]);
+        if (i < n) status[i] = good ? 1 : 0;
+    }
 }
 
 // ---- polynomial_triangulation (triangulation.py:198-232) -------------------------------------------------------
 // Hartley-Sturm correction of the match (cv2.correctMatches) followed by the linear-eigen solve, fused.
 template <typename TI, typename TC, typename TO, int ROWS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams, const __grid_constant__ HSParams hs,
              TO* __restrict__ x, uint8_t* __restrict__ status, TI* __restrict__ u1c, TI* __restrict__ u2c,
              unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord) {
     __shared__ TO stage[kWarps][96];
+    __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
     const int warp = threadIdx.x >> 5;
-    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * kThreads;
-    const int64_t i = block_base + threadIdx.x;
-    TC a = 0, b = 0, c = 0, d = 0;
-    if (i < n) { load_uv<TC>(u1, i, a, b); load_uv<TC>(u2, i, c, d); }
-    // The correction always runs in double: the degree-6 coefficients span many orders of magnitude.
-    double n1x, n1y, n2x, n2y;
-    hs_correct(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c), static_cast<double>(d),
-               n1x, n1y, n2x, n2y);
-    // cv2.correctMatches returns the dtype of its input, so the corrected points are rounded to TI
-    // before the triangulation (triangulation.py:224,232).
-    const TI r1x = static_cast<TI>(n1x), r1y = static_cast<TI>(n1y), r2x = static_cast<TI>(n2x), r2y = static_cast<TI>(n2y);
-    if (i < n) {
-        if (u1c) store_uv(u1c, i, r1x, r1y);
-        if (u2c) store_uv(u2c, i, r2x, r2y);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+    int64_t tile = static_cast<int64_t>(blockIdx.x) * kThreads;
+    bool any1 = false, any2 = false;           // "not all NaN" bookkeeping for the fallback test, per thread
+    pre.issue(u1, u2, tile + threadIdx.x, n);
+    for (; tile < n; tile += stride) {
+        const int64_t i = tile + threadIdx.x;
+        TC a, b, c, d;
+        pre.take(i, n, a, b, c, d);
+        pre.issue(u1, u2, i + stride, n);
+        // The correction always runs in double: the degree-6 coefficients span many orders of magnitude.
+        double n1x, n1y, n2x, n2y;
+        hs_correct(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c), static_cast<double>(d),
+                   n1x, n1y, n2x, n2y);
+        // cv2.correctMatches returns the dtype of its input, so the corrected points are rounded to TI
+        // before the triangulation (triangulation.py:224,232).
+        const TI r1x = static_cast<TI>(n1x), r1y = static_cast<TI>(n1y), r2x = static_cast<TI>(n2x), r2y = static_cast<TI>(n2y);
+        if (i < n) {
+            if (u1c) store_uv(u1c, i, r1x, r1y);
+            if (u2c) store_uv(u2c, i, r2x, r2y);
+            any1 = any1 || !(n1x != n1x) || !(n1y != n1y);
+            any2 = any2 || !(n2x != n2x) || !(n2y != n2y);
+        }
+        TC xs[3]; bool good;
+        eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
+                              static_cast<TC>(r2y), max_coord, xs, good);
+        store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+                         static_cast<TO>(xs[2]), stage[warp]);
+        if (i < n) status[i] = good ? 1 : 0;
     }
-    const bool finite1 = !(n1x != n1x) || !(n1y != n1y);     // "not all NaN" bookkeeping for the fallback test
-    const bool finite2 = !(n2x != n2x) || !(n2y != n2y);
-    const unsigned m1 = __ballot_sync(0xffffffffu, (i < n) && finite1);
-    const unsigned m2 = __ballot_sync(0xffffffffu, (i < n) && finite2);
-    if ((threadIdx.x & 31) == 0) {
-        if (m1) atomicOr(&not_nan_count[0], 1u);
-        if (m2) atomicOr(&not_nan_count[1], 1u);
+    // one flag update per CTA (two words shared by the whole grid: per-warp atomics would all hit the same L2 line)
+    const int f1 = __syncthreads_or(any1), f2 = __syncthreads_or(any2);
+    if (threadIdx.x == 0) {
+        if (f1) atomicOr(&not_nan_count[0], 1u);
+        if (f2) atomicOr(&not_nan_count[1], 1u);
     }
-    TC xs[3]; bool good;
-    eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
-                          static_cast<TC>(r2y), max_coord, xs, good);
-    store_x_warp<TO>(x, block_base + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                     static_cast<TO>(xs[2]), stage[warp]);
-    if (i < n) status[i] = good ? 1 : 0;
 }
 
 }  // namespace trgl

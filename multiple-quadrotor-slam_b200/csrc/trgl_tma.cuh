@@ -36,4 +36,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+// ---- per-thread asynchronous copies (cp.async, SASS LDGSTS): the register-free prefetch of the persistent solvers ----
+// Every thread copies its own (x,y) pair of the NEXT tile straight into shared memory while it solves the current one,
+// then reads its own slot back after cp.async.wait_all: no barrier is needed (a thread only reads what it copied) and
+// the lookahead costs no registers, which matters at 128 registers / thread.
+__device__ __forceinline__ void cp_async_pair(double* dst_smem, const double* src_gmem) {          // 16 bytes
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_pair(float* dst_smem, const float* src_gmem) {            // 8 bytes
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// Shared-memory landing zone of one CTA: slot t of view v holds the pair of thread t.
+template <typename TI, int THREADS>
+struct PairPrefetch {
+    TI buf[2][THREADS * 2];
+    __device__ __forceinline__ void issue(const TI* __restrict__ u1, const TI* __restrict__ u2, int64_t i, int64_t n) {
+        if (i < n) {
+            cp_async_pair(&buf[0][threadIdx.x * 2], u1 + 2 * i);
+            cp_async_pair(&buf[1][threadIdx.x * 2], u2 + 2 * i);
+        }
+    }
+    template <typename TC>
+    __device__ __forceinline__ void take(int64_t i, int64_t n, TC& a, TC& b, TC& c, TC& d) {
+        cp_async_wait_all();
+        if (i < n) {
+            a = static_cast<TC>(buf[0][threadIdx.x * 2]); b = static_cast<TC>(buf[0][threadIdx.x * 2 + 1]);
+            c = static_cast<TC>(buf[1][threadIdx.x * 2]); d = static_cast<TC>(buf[1][threadIdx.x * 2 + 1]);
+        } else {
+            a = b = c = d = TC(0);
+        }
+    }
+};
+
 }  // namespace trgl

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 
 using namespace trgl;
 
@@ -100,6 +101,26 @@ int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_
     return TRGL_OK;
 }
 
+// Persistent grid of the FP64-bound solvers: SMs x resident CTAs (occupancy API, cached per kernel), or fewer when
+// the batch has fewer 256-point tiles than that.
+template <typename K>
+unsigned persistent_grid(K kern, int64_t n, size_t dyn_smem = 0) {
+    static thread_local std::unordered_map<const void*, int> cache;     // keyed by the instantiation's address
+    if (g_sm_count == 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int& per_sm = cache[reinterpret_cast<const void*>(kern)];
+    if (per_sm == 0) {
+        if (dyn_smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const int64_t tiles = (n + kThreads - 1) / kThreads;
+    const int64_t full = static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148) * per_sm;
+    return static_cast<unsigned>(tiles < full ? tiles : full);
+}
+
 template <typename TI, typename TC, typename TO>
 void launch_ls_direct(int ppt, const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n,
                       cudaStream_t s) {
@@ -113,9 +134,10 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
     if (n == 0) return TRGL_OK;
     const int ppt = g_ppt.load();
     int variant = g_variant.load();
-    // auto: the persistent bulk-async pipeline pays off once its prologue/tail is amortised (measured cross-over
-    // between 10 M and 100 M points on B200); smaller batches use per-thread vector loads with 4 points in flight.
-    if (variant < 0) variant = (n >= (int64_t(1) << 25)) ? 1 : 0;
+    // auto: per-thread vector loads with 4 points in flight.  Measured on B200 (profiles/r01b_sweep_100M.jsonl): 0.84 of
+    // the measured copy peak at 100 M points vs 0.74 for the bulk-async pipeline (variants 1-6, kept selectable), and
+    // 0.82 at 10 M points.
+    if (variant < 0) variant = 0;
     // cp.async.bulk needs 16-byte aligned global addresses; fall back to per-thread loads otherwise
     if ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & 15) variant = 0;
     MODE_SWITCH(mode, {
@@ -145,7 +167,9 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
-        k_iterative_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(
+        auto kern = k_iterative_ls<TI, TC, TO>;
+        constexpr size_t smem = sizeof(IterSmem<TI, TC, TO>);
+        kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
             static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
             static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0);
     })
@@ -161,10 +185,13 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
-        if (rows == 4)
-            k_linear_eigen<TI, TC, TO, 4><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc));
-        else
-            k_linear_eigen<TI, TC, TO, 6><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc));
+        if (rows == 4) {
+            auto kern = k_linear_eigen<TI, TC, TO, 4>;
+            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc));
+        } else {
+            auto kern = k_linear_eigen<TI, TC, TO, 6>;
+            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc));
+        }
     })
     g_launches++;
     CK(cudaGetLastError());
@@ -179,10 +206,13 @@ int launch_polynomial(const void* u1, const void* u2, const double* P1, const do
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
-        if (rows == 4)
-            k_polynomial<TI, TC, TO, 4><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc));
-        else
-            k_polynomial<TI, TC, TO, 6><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc));
+        if (rows == 4) {
+            auto kern = k_polynomial<TI, TC, TO, 4>;
+            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc));
+        } else {
+            auto kern = k_polynomial<TI, TC, TO, 6>;
+            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc));
+        }
     })
     g_launches++;
     CK(cudaGetLastError());
@@ -290,6 +320,10 @@ int check_common(const void* u1, const void* u2, const double* P1, const double*
     if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
     if (!P1 || !P2) return fail(TRGL_E_BADARG, "camera matrix pointer is NULL");
     if (n > 0 && (!u1 || !u2 || !x || !status)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
+    // the kernels read one (x,y) pair per vector load / cp.async: device buffers must be aligned to a pair
+    if (mem == TRGL_MEM_DEVICE && n > 0 &&
+        ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & static_cast<uintptr_t>(2 * mi.in_bytes - 1)))
+        return fail(TRGL_E_BADARG, "device u1/u2 must be aligned to one (x,y) pair (16 bytes float64, 8 bytes float32)");
     if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
     return TRGL_OK;
 }
