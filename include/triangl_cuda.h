@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define TRGL_VERSION 100
+#define TRGL_VERSION 101
 
 enum { TRGL_F64 = 0, TRGL_F32IO = 1, TRGL_F32 = 2, TRGL_F64_OUT32 = 3, TRGL_F32_OUT64 = 4 };
 enum { TRGL_MEM_HOST = 0, TRGL_MEM_DEVICE = 1 };
@@ -117,6 +117,35 @@ int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const do
  * reductions of the moments and of the 9x9 normal matrix, tiny eigen-solve on the host.  F: 9 doubles out (host).
  * Only the element type of u is taken from `mode`.  Synchronises. */
 int trgl_fundamental_8point(const void* u1, const void* u2, int64_t n, int mode, int mem, double* F, void* stream);
+
+/* ---- input normalisation in front of the solvers ---- */
+
+/* cv2.undistortPoints(src, K, dist) with the default criteria (5 fixed-point iterations) and no R / P:
+ * call sites Work/SLAM/application/own/slam2.py:551-552, Work/triangulation_comparison/triangulation_comparison.py:164-173,
+ * Work/calibration/calibrate.py:252-253.  src, dst: (n,2) pixel / normalised coordinates, both float32 (in_is_f32 = 1)
+ * or both float64 -- cv2 returns its input dtype.  K: 9 doubles row-major (host); dist: (k1,k2,p1,p2,k3) (host) or NULL.
+ * Arithmetic is float64 in OpenCV's evaluation order without FMA contraction: results are bit-identical to cv2 4.13. */
+int trgl_undistort_points(const void* src, void* dst, const double* K, const double* dist, int64_t n, int in_is_f32,
+                          int mem, void* stream);
+
+/* The four solvers on PIXEL coordinates: px1, px2 are what the callers hand to cv2.undistortPoints, (K1,dist1) and
+ * (K2,dist2) the intrinsics of the two views (the reference uses one camera for both, slam2.py:551-552).  The
+ * undistortion runs in registers in front of the solve (one HBM round trip of u1,u2 less); the normalised pair is
+ * rounded to the dtype of px exactly as cv2.undistortPoints' output would be, so every *_px call returns bit for bit
+ * what trgl_undistort_points followed by the plain solver returns.  All other arguments as in the plain solvers. */
+int trgl_linear_ls_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
+                      const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status, int64_t n,
+                      int mode, int mem, void* stream);
+int trgl_iterative_ls_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
+                         const double* dist2, const double* P1, const double* P2, void* x, int32_t* status, int64_t n,
+                         double tolerance, int semantics, int mode, int mem, void* stream);
+int trgl_linear_eigen_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
+                         const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status, int64_t n,
+                         double max_coordinate_value, int rows, int mode, int mem, void* stream);
+int trgl_polynomial_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
+                       const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status,
+                       void* u1_corr, void* u2_corr, int* all_nan, int64_t n, double max_coordinate_value, int rows,
+                       int mode, int mem, void* stream);
 
 /* ---- fused reprojection error / good-point mask ---- */
 

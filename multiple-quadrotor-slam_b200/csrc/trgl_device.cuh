@@ -59,6 +59,65 @@ __device__ __forceinline__ void store_uv(float* __restrict__ u, int64_t i, float
     __stcs(reinterpret_cast<float2*>(u) + i, make_float2(x, y));
 }
 
+// ---- input normalisation fused in front of the solvers: cv2.undistortPoints(src, K, dist) -------------------------
+// Call sites slam2.py:551-552, triangulation_comparison.py:164-173, calibrate.py:252-253.  Restates OpenCV's
+// cvUndistortPointsInternal for the (k1,k2,p1,p2,k3) model with the default criteria (5 fixed-point iterations, no
+// epsilon test, no R / P): every operation is an explicitly rounded IEEE double operation in OpenCV's evaluation order
+// (no FMA contraction), so the result is BIT-IDENTICAL to cv2 4.13 -- checked in tests/ against committed cv2 output.
+struct Undist { double ifx, ify, cx, cy, k1, k2, p1, p2, k3; int has_dist; int tangential; };
+struct Undist2 { Undist cam[2]; };
+
+__device__ __forceinline__ void undistort_pair(const Undist& U, double u, double v, double& xo, double& yo) {
+    const double x0 = __dmul_rn(__dsub_rn(u, U.cx), U.ifx), y0 = __dmul_rn(__dsub_rn(v, U.cy), U.ify);
+    double x = x0, y = y0;
+    if (U.has_dist) {
+#pragma unroll 1
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+            const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(U.k3, r2), U.k2), r2), U.k1), r2));
+            const double icdist = __drcp_rn(den);            // == 1.0 / den, correctly rounded (numerator is exactly 1)
+            if (icdist < 0.0) { x = x0; y = y0; break; }
+            if (U.tangential) {
+                const double two_x = __dmul_rn(2.0, x), two_y = __dmul_rn(2.0, y);
+                // deltaX = 2*p1*x*y + p2*(r2 + 2*x*x);  deltaY = p1*(r2 + 2*y*y) + 2*p2*x*y   (left-to-right products)
+                const double dX = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, U.p1), x), y),
+                                            __dmul_rn(U.p2, __dadd_rn(r2, __dmul_rn(two_x, x))));
+                const double dY = __dadd_rn(__dmul_rn(U.p1, __dadd_rn(r2, __dmul_rn(two_y, y))),
+                                            __dmul_rn(__dmul_rn(__dmul_rn(2.0, U.p2), x), y));
+                x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+                y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+            } else {
+                // p1 = p2 = 0: deltaX = deltaY = +0 exactly for finite x,y, and x0 - 0 = x0.  (Non-finite x,y give NaN
+                // on both routes: 0*inf in the deltas there, inf*0 or NaN*icdist here.)
+                x = __dmul_rn(x0, icdist);
+                y = __dmul_rn(y0, icdist);
+            }
+        }
+    }
+    xo = x; yo = y;
+}
+
+// Pre-stage policies of the solver kernels: what happens to the four loaded scalars before the solve.
+struct PreNone {
+    static constexpr bool kActive = false;
+    template <typename TI, typename TC>
+    __device__ __forceinline__ void apply(TC&, TC&, TC&, TC&) const {}
+};
+// Pixel coordinates in, normalised coordinates out.  cv2.undistortPoints returns its input dtype, so the normalised pair
+// is rounded to TI before the solve: fused == (undistort kernel, then solver) bit for bit.
+struct PreUndistort {
+    static constexpr bool kActive = true;
+    Undist2 p;
+    template <typename TI, typename TC>
+    __device__ __forceinline__ void apply(TC& a, TC& b, TC& c, TC& d) const {
+        double x, y;
+        undistort_pair(p.cam[0], static_cast<double>(a), static_cast<double>(b), x, y);
+        a = static_cast<TC>(static_cast<TI>(x)); b = static_cast<TC>(static_cast<TI>(y));
+        undistort_pair(p.cam[1], static_cast<double>(c), static_cast<double>(d), x, y);
+        c = static_cast<TC>(static_cast<TI>(x)); d = static_cast<TC>(static_cast<TI>(y));
+    }
+};
+
 // ---- coalesced store of the (n,3) AoS result ---------------------------------------------------------------
 // Each warp owns 32 consecutive points starting at warp_base.  The 96 scalars are transposed through a per-warp
 // shared-memory row (stride-3 writes are bank-conflict free) and leave as three 32-wide contiguous stores.

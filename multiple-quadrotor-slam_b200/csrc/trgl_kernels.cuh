@@ -14,10 +14,10 @@ constexpr int kWarps = kThreads / 32;
 // Per point: straight-line fast solve, (rare) careful redo, immediate coalesced store.  Measured on B200: storing each
 // point as soon as it is solved beats "solve all PPT points, then store" by 0.81 vs 0.65 of the HBM peak, and keeping
 // the 4x4 row block alive for an inline refinement path costs 2x (0.39).
-template <typename TI, typename TC, typename TO, int PPT>
+template <typename TI, typename TC, typename TO, int PPT, class PRE = PreNone>
 __global__ void __launch_bounds__(kThreads)
 k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-            TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n) {
+            TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ PRE pre) {
     __shared__ TO stage[kWarps][96];
     const int warp = threadIdx.x >> 5;
     const int64_t block_base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT);
@@ -36,6 +36,7 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
     for (int p = 0; p < PPT; ++p) {
         const int64_t i = block_base + p * kThreads + threadIdx.x;
         TC xs[3];
+        if constexpr (PRE::kActive) pre.template apply<TI, TC>(in[p][0], in[p][1], in[p][2], in[p][3]);
         if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs))
             solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
         store_x_warp<TO>(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
@@ -190,11 +191,11 @@ __device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*
     status[dst] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
 }
 
-template <typename TI, typename TC, typename TO>
+template <typename TI, typename TC, typename TO, class PRE = PreNone>
 __global__ void __launch_bounds__(kThreads, 2)
 k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
-               const TC tolerance, const int py_semantics) {
+               const TC tolerance, const int py_semantics, const __grid_constant__ PRE pre_stage) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IterSmem<TI, TC, TO>& sm = *reinterpret_cast<IterSmem<TI, TC, TO>*>(smem_raw);
     auto& pre = sm.pre; auto& q_state = sm.q_state; auto& q_idx = sm.q_idx; auto& stage = sm.stage; int& q_count = sm.q_count;
@@ -210,6 +211,7 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         TC a, b, c, d;
         pre.take(i, n, a, b, c, d);
         pre.issue(u1, u2, i + stride, n);                // next tile of this CTA lands while this one is solved
+        if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
         {
             TC M1[6], v1[3], M2[6], v2[3], xs[3] = {0, 0, 0};
             point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
@@ -402,10 +404,11 @@ __device__ __forceinline__ void eigen_point(const Cams<TC>& cams, TC u1x, TC u1y
 
 // Persistent CTAs: grid-stride loop over 256-point tiles, the next tile's inputs are prefetched into registers while the
 // current tile is solved (the solve is ~700 instructions per point, so one tile of lookahead hides the HBM latency).
-template <typename TI, typename TC, typename TO, int ROWS>
+template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone>
 __global__ void __launch_bounds__(kThreads, 2)
 k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-               TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord) {
+               TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord,
+               const __grid_constant__ PRE pre_stage) {
     __shared__ TO stage[kWarps][96];
     __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
     const int warp = threadIdx.x >> 5;
@@ -417,6 +420,7 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         TC a, b, c, d;
         pre.take(i, n, a, b, c, d);
         pre.issue(u1, u2, i + stride, n);
+        if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
         TC xs[3]; bool good;
         eigen_point<TC, ROWS>(cams, a, b, c, d, max_coord, xs, good);
         store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
@@ -427,11 +431,12 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
 
 // ---- polynomial_triangulation (triangulation.py:198-232) -------------------------------------------------------
 // Hartley-Sturm correction of the match (cv2.correctMatches) followed by the linear-eigen solve, fused.
-template <typename TI, typename TC, typename TO, int ROWS>
+template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone>
 __global__ void __launch_bounds__(kThreads, 2)
 k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams, const __grid_constant__ HSParams hs,
              TO* __restrict__ x, uint8_t* __restrict__ status, TI* __restrict__ u1c, TI* __restrict__ u2c,
-             unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord) {
+             unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord,
+             const __grid_constant__ PRE pre_stage) {
     __shared__ TO stage[kWarps][96];
     __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
     const int warp = threadIdx.x >> 5;
@@ -444,6 +449,7 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
         TC a, b, c, d;
         pre.take(i, n, a, b, c, d);
         pre.issue(u1, u2, i + stride, n);
+        if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
         // The correction always runs in double: the degree-6 coefficients span many orders of magnitude.
         double n1x, n1y, n2x, n2y;
         hs_correct(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c), static_cast<double>(d),
@@ -469,6 +475,19 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
     if (threadIdx.x == 0) {
         if (f1) atomicOr(&not_nan_count[0], 1u);
         if (f2) atomicOr(&not_nan_count[1], 1u);
+    }
+}
+
+// ---- cv2.undistortPoints as a standalone kernel (slam2.py:551-552; output dtype = input dtype) ---------------------
+template <typename TI>
+__global__ void __launch_bounds__(kThreads)
+k_undistort_points(const TI* __restrict__ src, TI* __restrict__ dst, const __grid_constant__ Undist U, const int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        double u, v, x, y;
+        load_uv<double>(src, i, u, v);
+        undistort_pair(U, u, v, x, y);
+        store_uv(dst, i, x, y);
     }
 }
 

@@ -123,14 +123,20 @@ unsigned persistent_grid(K kern, int64_t n, size_t dyn_smem = 0) {
 
 template <typename TI, typename TC, typename TO>
 void launch_ls_direct(int ppt, const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n,
-                      cudaStream_t s) {
-    if (ppt == 1) k_linear_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n);
-    else if (ppt == 2) k_linear_ls<TI, TC, TO, 2><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n);
-    else k_linear_ls<TI, TC, TO, 4><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n);
+                      cudaStream_t s, const Undist2* pre) {
+    if (pre) {      // pixel inputs: the undistortion makes the kernel FP64-bound, one point per thread is enough
+        const PreUndistort pu{*pre};
+        k_linear_ls<TI, TC, TO, 1, PreUndistort><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, pu);
+        return;
+    }
+    const PreNone none{};
+    if (ppt == 1) k_linear_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, none);
+    else if (ppt == 2) k_linear_ls<TI, TC, TO, 2><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n, none);
+    else k_linear_ls<TI, TC, TO, 4><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, none);
 }
 
 int launch_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
-                     int64_t n, int mode, cudaStream_t s) {
+                     int64_t n, int mode, cudaStream_t s, const Undist2* pre = nullptr) {
     if (n == 0) return TRGL_OK;
     const int ppt = g_ppt.load();
     int variant = g_variant.load();
@@ -140,6 +146,7 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
     if (variant < 0) variant = 0;
     // cp.async.bulk needs 16-byte aligned global addresses; fall back to per-thread loads otherwise
     if ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & 15) variant = 0;
+    if (pre) variant = 0;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
@@ -152,7 +159,7 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
             case 4: rc = launch_ls_tma<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s); break;
             case 5: rc = launch_ls_tma<TI, TC, TO, 4, 4, 1>(a, b, cams, xo, status, n, s); break;
             case 6: rc = launch_ls_tma<TI, TC, TO, 1, 8, 3>(a, b, cams, xo, status, n, s); break;
-            default: launch_ls_direct<TI, TC, TO>(ppt, a, b, cams, xo, status, n, s);
+            default: launch_ls_direct<TI, TC, TO>(ppt, a, b, cams, xo, status, n, s, pre);
         }
         if (rc) return rc;
     })
@@ -162,36 +169,52 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
 }
 
 int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
-                        int64_t n, double tol, int semantics, int mode, cudaStream_t s) {
+                        int64_t n, double tol, int semantics, int mode, cudaStream_t s, const Undist2* pre = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
-        auto kern = k_iterative_ls<TI, TC, TO>;
         constexpr size_t smem = sizeof(IterSmem<TI, TC, TO>);
-        kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
-            static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
-            static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0);
+        if (pre) {
+            auto kern = k_iterative_ls<TI, TC, TO, PreUndistort>;
+            kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
+                static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
+                static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, PreUndistort{*pre});
+        } else {
+            auto kern = k_iterative_ls<TI, TC, TO, PreNone>;
+            kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
+                static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
+                static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, PreNone{});
+        }
     })
     g_launches++;
     CK(cudaGetLastError());
     return TRGL_OK;
 }
 
+#define EIGEN_LAUNCH(ROWS, PRE, prearg)                                                                        \
+    {                                                                                                          \
+        auto kern = k_linear_eigen<TI, TC, TO, ROWS, PRE>;                                                     \
+        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n,         \
+                                                           static_cast<TC>(maxc), prearg);                     \
+    }
+#define POLY_LAUNCH(ROWS, PRE, prearg)                                                                         \
+    {                                                                                                          \
+        auto kern = k_polynomial<TI, TC, TO, ROWS, PRE>;                                                       \
+        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status,        \
+                                                           static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, \
+                                                           static_cast<TC>(maxc), prearg);                     \
+    }
+
 int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
-                        int64_t n, double maxc, int rows, int mode, cudaStream_t s) {
+                        int64_t n, double maxc, int rows, int mode, cudaStream_t s, const Undist2* pre = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
-        if (rows == 4) {
-            auto kern = k_linear_eigen<TI, TC, TO, 4>;
-            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc));
-        } else {
-            auto kern = k_linear_eigen<TI, TC, TO, 6>;
-            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc));
-        }
+        if (pre) { if (rows == 4) EIGEN_LAUNCH(4, PreUndistort, PreUndistort{*pre}) else EIGEN_LAUNCH(6, PreUndistort, PreUndistort{*pre}) }
+        else { if (rows == 4) EIGEN_LAUNCH(4, PreNone, PreNone{}) else EIGEN_LAUNCH(6, PreNone, PreNone{}) }
     })
     g_launches++;
     CK(cudaGetLastError());
@@ -200,19 +223,14 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
 
 int launch_polynomial(const void* u1, const void* u2, const double* P1, const double* P2, const HSParams& hs, void* x,
                       uint8_t* status, void* u1c, void* u2c, unsigned int* flags, int64_t n, double maxc, int rows,
-                      int mode, cudaStream_t s) {
+                      int mode, cudaStream_t s, const Undist2* pre = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
-        if (rows == 4) {
-            auto kern = k_polynomial<TI, TC, TO, 4>;
-            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc));
-        } else {
-            auto kern = k_polynomial<TI, TC, TO, 6>;
-            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc));
-        }
+        if (pre) { if (rows == 4) POLY_LAUNCH(4, PreUndistort, PreUndistort{*pre}) else POLY_LAUNCH(6, PreUndistort, PreUndistort{*pre}) }
+        else { if (rows == 4) POLY_LAUNCH(4, PreNone, PreNone{}) else POLY_LAUNCH(6, PreNone, PreNone{}) }
     })
     g_launches++;
     CK(cudaGetLastError());
@@ -326,6 +344,21 @@ int check_common(const void* u1, const void* u2, const double* P1, const double*
         return fail(TRGL_E_BADARG, "device u1/u2 must be aligned to one (x,y) pair (16 bytes float64, 8 bytes float32)");
     if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
     return TRGL_OK;
+}
+
+// Parameters of cv2.undistortPoints: K (3x3 row-major) and (k1,k2,p1,p2,k3) or NULL.  OpenCV multiplies by 1/fx.
+bool make_undist(const double* K, const double* dist, Undist& U) {
+    if (!K || K[0] == 0.0 || K[4] == 0.0) return false;
+    U.ifx = 1.0 / K[0]; U.ify = 1.0 / K[4]; U.cx = K[2]; U.cy = K[5];
+    U.k1 = dist ? dist[0] : 0.0; U.k2 = dist ? dist[1] : 0.0; U.p1 = dist ? dist[2] : 0.0; U.p2 = dist ? dist[3] : 0.0;
+    U.k3 = dist ? dist[4] : 0.0;
+    // all-zero coefficients: the fixed-point loop is the identity (icdist = 1, delta = 0), skip it
+    U.has_dist = (U.k1 != 0.0 || U.k2 != 0.0 || U.p1 != 0.0 || U.p2 != 0.0 || U.k3 != 0.0) ? 1 : 0;
+    U.tangential = (U.p1 != 0.0 || U.p2 != 0.0) ? 1 : 0;
+    return true;
+}
+bool make_undist2(const double* K1, const double* d1, const double* K2, const double* d2, Undist2& p) {
+    return make_undist(K1, d1, p.cam[0]) && make_undist(K2, d2, p.cam[1]);
 }
 
 // Right and left epipoles of a rank-2 F as the largest cross product of two rows / columns.
@@ -502,54 +535,88 @@ int trgl_set_points_per_thread(int ppt) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int trgl_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
-                   int64_t n, int mode, int mem, void* stream) {
+static int impl_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                          int64_t n, int mode, int mem, void* stream, const Undist2* pre) {
     int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
     if (rc || n == 0) return rc;
-    if (mem == TRGL_MEM_DEVICE) return launch_linear_ls(u1, u2, P1, P2, x, status, n, mode, static_cast<cudaStream_t>(stream));
+    if (mem == TRGL_MEM_DEVICE) return launch_linear_ls(u1, u2, P1, P2, x, status, n, mode, static_cast<cudaStream_t>(stream), pre);
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
     return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
-        return launch_linear_ls(d[0], d[1], P1, P2, d[2], static_cast<uint8_t*>(d[3]), m, mode, s);
+        return launch_linear_ls(d[0], d[1], P1, P2, d[2], static_cast<uint8_t*>(d[3]), m, mode, s, pre);
     });
 }
+int trgl_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                   int64_t n, int mode, int mem, void* stream) {
+    return impl_linear_ls(u1, u2, P1, P2, x, status, n, mode, mem, stream, nullptr);
+}
+int trgl_linear_ls_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
+                      const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status, int64_t n,
+                      int mode, int mem, void* stream) {
+    Undist2 pre;
+    if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
+    return impl_linear_ls(px1, px2, P1, P2, x, status, n, mode, mem, stream, &pre);
+}
 
-int trgl_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
-                      int64_t n, double tolerance, int semantics, int mode, int mem, void* stream) {
+static int impl_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
+                             int64_t n, double tolerance, int semantics, int mode, int mem, void* stream, const Undist2* pre) {
     int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
     if (rc) return rc;
     if (semantics != TRGL_ITER_C && semantics != TRGL_ITER_PY) return fail(TRGL_E_BADARG, "unknown iterative semantics");
     if (n == 0) return TRGL_OK;
     if (mem == TRGL_MEM_DEVICE)
-        return launch_iterative_ls(u1, u2, P1, P2, x, status, n, tolerance, semantics, mode, static_cast<cudaStream_t>(stream));
+        return launch_iterative_ls(u1, u2, P1, P2, x, status, n, tolerance, semantics, mode, static_cast<cudaStream_t>(stream), pre);
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 4}};
     return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
-        return launch_iterative_ls(d[0], d[1], P1, P2, d[2], static_cast<int32_t*>(d[3]), m, tolerance, semantics, mode, s);
+        return launch_iterative_ls(d[0], d[1], P1, P2, d[2], static_cast<int32_t*>(d[3]), m, tolerance, semantics, mode, s, pre);
     });
 }
+int trgl_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
+                      int64_t n, double tolerance, int semantics, int mode, int mem, void* stream) {
+    return impl_iterative_ls(u1, u2, P1, P2, x, status, n, tolerance, semantics, mode, mem, stream, nullptr);
+}
+int trgl_iterative_ls_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
+                         const double* dist2, const double* P1, const double* P2, void* x, int32_t* status, int64_t n,
+                         double tolerance, int semantics, int mode, int mem, void* stream) {
+    Undist2 pre;
+    if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
+    return impl_iterative_ls(px1, px2, P1, P2, x, status, n, tolerance, semantics, mode, mem, stream, &pre);
+}
 
-int trgl_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
-                      int64_t n, double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+static int impl_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                             int64_t n, double max_coordinate_value, int rows, int mode, int mem, void* stream,
+                             const Undist2* pre) {
     int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
     if (rc) return rc;
     if (rows != 4 && rows != 6) return fail(TRGL_E_BADARG, "rows must be 4 or 6");
     if (n == 0) return TRGL_OK;
     if (mem == TRGL_MEM_DEVICE)
-        return launch_linear_eigen(u1, u2, P1, P2, x, status, n, max_coordinate_value, rows, mode, static_cast<cudaStream_t>(stream));
+        return launch_linear_eigen(u1, u2, P1, P2, x, status, n, max_coordinate_value, rows, mode, static_cast<cudaStream_t>(stream), pre);
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
     return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
-        return launch_linear_eigen(d[0], d[1], P1, P2, d[2], static_cast<uint8_t*>(d[3]), m, max_coordinate_value, rows, mode, s);
+        return launch_linear_eigen(d[0], d[1], P1, P2, d[2], static_cast<uint8_t*>(d[3]), m, max_coordinate_value, rows, mode, s, pre);
     });
 }
+int trgl_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
+                      int64_t n, double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+    return impl_linear_eigen(u1, u2, P1, P2, x, status, n, max_coordinate_value, rows, mode, mem, stream, nullptr);
+}
+int trgl_linear_eigen_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
+                         const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status, int64_t n,
+                         double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+    Undist2 pre;
+    if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
+    return impl_linear_eigen(px1, px2, P1, P2, x, status, n, max_coordinate_value, rows, mode, mem, stream, &pre);
+}
 
-int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const double* P2, const double* F, void* x,
-                      uint8_t* status, void* u1_corr, void* u2_corr, int* all_nan, int64_t n,
-                      double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, const double* P2, const double* F, void* x,
+                             uint8_t* status, void* u1_corr, void* u2_corr, int* all_nan, int64_t n,
+                             double max_coordinate_value, int rows, int mode, int mem, void* stream, const Undist2* pre) {
     int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
     if (rc) return rc;
     if (!F) return fail(TRGL_E_BADARG, "F is NULL");
@@ -568,7 +635,7 @@ int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const do
         }
         unsigned int* fl = g_flags + 2 * kSlots;
         CK(cudaMemsetAsync(fl, 0, 2 * sizeof(unsigned int), s));
-        rc = launch_polynomial(u1, u2, P1, P2, hs, x, status, u1_corr, u2_corr, fl, n, max_coordinate_value, rows, mode, s);
+        rc = launch_polynomial(u1, u2, P1, P2, hs, x, status, u1_corr, u2_corr, fl, n, max_coordinate_value, rows, mode, s, pre);
         if (rc) return rc;
         if (all_nan) {
             CK(cudaMemcpyAsync(hflags, fl, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -588,7 +655,7 @@ int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const do
                         {nullptr, u1_corr, size_t(2 * mi.in_bytes)}, {nullptr, u2_corr, size_t(2 * mi.in_bytes)}};
     rc = host_pipeline(arr, 6, n, [&](void** d, int64_t m, cudaStream_t s, int slot) {
         return launch_polynomial(d[0], d[1], P1, P2, hs, d[2], static_cast<uint8_t*>(d[3]), u1_corr ? d[4] : nullptr,
-                                 u2_corr ? d[5] : nullptr, g_flags + 2 * slot, m, max_coordinate_value, rows, mode, s);
+                                 u2_corr ? d[5] : nullptr, g_flags + 2 * slot, m, max_coordinate_value, rows, mode, s, pre);
     });
     if (rc) return rc;
     if (all_nan) {
@@ -600,6 +667,13 @@ int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const do
     return TRGL_OK;
 }
 
+int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const double* P2, const double* F, void* x,
+                      uint8_t* status, void* u1_corr, void* u2_corr, int* all_nan, int64_t n,
+                      double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+    return impl_polynomial_F(u1, u2, P1, P2, F, x, status, u1_corr, u2_corr, all_nan, n, max_coordinate_value, rows, mode,
+                             mem, stream, nullptr);
+}
+
 int trgl_polynomial(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                     void* u1_corr, void* u2_corr, int* all_nan, int64_t n, double max_coordinate_value, int rows,
                     int mode, int mem, void* stream) {
@@ -608,6 +682,48 @@ int trgl_polynomial(const void* u1, const void* u2, const double* P1, const doub
     fundamental_from_P(P1, P2, F);
     return trgl_polynomial_F(u1, u2, P1, P2, F, x, status, u1_corr, u2_corr, all_nan, n, max_coordinate_value, rows,
                              mode, mem, stream);
+}
+
+int trgl_polynomial_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
+                       const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status,
+                       void* u1_corr, void* u2_corr, int* all_nan, int64_t n, double max_coordinate_value, int rows,
+                       int mode, int mem, void* stream) {
+    if (!P1 || !P2) return fail(TRGL_E_BADARG, "camera matrix pointer is NULL");
+    Undist2 pre;
+    if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
+    double F[9];
+    fundamental_from_P(P1, P2, F);
+    return impl_polynomial_F(px1, px2, P1, P2, F, x, status, u1_corr, u2_corr, all_nan, n, max_coordinate_value, rows,
+                             mode, mem, stream, &pre);
+}
+
+// cv2.undistortPoints(src, K, dist) -> normalised coordinates in the dtype of src (slam2.py:551-552)
+int trgl_undistort_points(const void* src, void* dst, const double* K, const double* dist, int64_t n, int in_is_f32,
+                          int mem, void* stream) {
+    if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (n > 0 && (!src || !dst)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
+    Undist U;
+    if (!make_undist(K, dist, U)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    if (n == 0) return TRGL_OK;
+    const size_t pb = in_is_f32 ? 8 : 16;
+    auto run = [&](const void* s_, void* d_, int64_t m, cudaStream_t st) -> int {
+        const int64_t tiles = (m + kThreads - 1) / kThreads;
+        const unsigned grid = static_cast<unsigned>(tiles < 148 * 16 ? tiles : 148 * 16);
+        if (in_is_f32) k_undistort_points<float><<<grid, kThreads, 0, st>>>(static_cast<const float*>(s_), static_cast<float*>(d_), U, m);
+        else k_undistort_points<double><<<grid, kThreads, 0, st>>>(static_cast<const double*>(s_), static_cast<double*>(d_), U, m);
+        g_launches++;
+        CK(cudaGetLastError());
+        return TRGL_OK;
+    };
+    if (mem == TRGL_MEM_DEVICE) {
+        if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & (pb - 1))
+            return fail(TRGL_E_BADARG, "device src/dst must be aligned to one (x,y) pair");
+        return run(src, dst, n, static_cast<cudaStream_t>(stream));
+    }
+    HostArray arr[2] = {{src, nullptr, pb}, {nullptr, dst, pb}};
+    return host_pipeline(arr, 2, n, [&](void** d, int64_t m, cudaStream_t st, int) { return run(d[0], d[1], m, st); });
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ EXPORTS = [
     "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
     "trgl_set_points_per_thread", "trgl_set_stream_variant",
+    "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
 
@@ -79,6 +80,12 @@ def lib():
     L.trgl_fundamental_8point.argtypes = [vp, vp, i64, cint, cint, dp, vp]
     L.trgl_reproj_error.argtypes = [vp, vp, dp, dp, dp, dp, vp, dp, dp, i64, cint, cint, cint, vp]
     L.trgl_pair_reproj.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, dp, i64, cint, cint, vp]
+    L.trgl_undistort_points.argtypes = [vp, vp, dp, dp, i64, cint, cint, vp]
+    L.trgl_linear_ls_px.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, vp, vp, i64, cint, cint, vp]
+    L.trgl_iterative_ls_px.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
+    L.trgl_linear_eigen_px.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
+    L.trgl_polynomial_px.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, vp, vp, vp, vp, ctypes.POINTER(cint), i64, dbl, cint,
+                                     cint, cint, vp]
     _lib = L
     return L
 
@@ -278,37 +285,104 @@ def _out(dev, n, cols, dtype, given):
     return np.empty(shape, dtype=dtype)
 
 
-def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=None, status=None, stream=None):
+class Intrinsics:
+    """(K1, dist1, K2, dist2) of the two views for the pixel-input (`*_px`) entry points; dist may be None, 4 or 5
+    coefficients (k1,k2,p1,p2[,k3]).  One camera for both views: Intrinsics(K, dist)."""
+
+    def __init__(self, K1, dist1=None, K2=None, dist2=None):
+        self.K1 = _K9(K1); self.d1 = _dist5(dist1)
+        self.K2 = self.K1 if K2 is None else _K9(K2)
+        self.d2 = self.d1 if K2 is None and dist2 is None else _dist5(dist2)
+
+    def args(self):
+        return (_dp(self.K1), None if self.d1 is None else _dp(self.d1),
+                _dp(self.K2), None if self.d2 is None else _dp(self.d2))
+
+
+def _K9(K):
+    K = np.ascontiguousarray(K, dtype=np.float64)
+    if K.shape != (3, 3):
+        raise ValueError("camera matrix K must be 3x3, got %r" % (K.shape,))
+    return K
+
+
+def _dist5(dist):
+    if dist is None:
+        return None
+    dd = np.asarray(dist, dtype=np.float64).ravel()
+    if len(dd) not in (4, 5):
+        raise ValueError("distortion model must be (k1,k2,p1,p2[,k3]); got %d coefficients" % len(dd))
+    d = np.zeros(5)
+    d[:len(dd)] = dd
+    return d
+
+
+def undistort_points(src, K, dist=None, dst=None, stream=None):
+    """cv2.undistortPoints(src, K, dist) -> (N,2) normalised coordinates in the dtype of src (float32 / float64);
+    any (…,2) input shape is accepted (the reference passes (1,N,2), slam2.py:551-552)."""
+    dev = _is_device(src)
+    if not dev:
+        src = np.asarray(src)
+        if src.dtype != np.float32:
+            src = src.astype(np.float64, copy=False)
+        src = np.ascontiguousarray(src.reshape(-1, 2))
+    n = len(src)
+    dt = np.dtype(str(src.dtype).replace("torch.", ""))
+    K = _K9(K); d = _dist5(dist)
+    dst = _out(dev, n, 2, dt, dst)
+    check(lib().trgl_undistort_points(_ptr(src), _ptr(dst), _dp(K), None if d is None else _dp(d), n,
+                                      int(dt == np.float32), MEM_DEVICE if dev else MEM_HOST, stream))
+    return dst
+
+
+def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=None, status=None, stream=None,
+              pixel=None):
+    """pixel: an Intrinsics -> u1,u2 are pixel coordinates, undistorted in registers in front of the solve."""
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
-    check(lib().trgl_linear_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, mode,
-                               MEM_DEVICE if dev else MEM_HOST, stream))
+    mem = MEM_DEVICE if dev else MEM_HOST
+    if pixel is None:
+        check(lib().trgl_linear_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, mode, mem, stream))
+    else:
+        check(lib().trgl_linear_ls_px(_ptr(u1), _ptr(u2), *pixel.args(), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
+                                      mode, mem, stream))
     return x, status
 
 
 def iterative_ls(u1, P1, u2, P2, tolerance=3.e-5, semantics=ITER_C, out_dtype=np.float64, compute_dtype=np.float64,
-                 x=None, status=None, stream=None):
+                 x=None, status=None, stream=None, pixel=None):
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.int32, status)
-    check(lib().trgl_iterative_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, float(tolerance),
-                                  semantics, mode, MEM_DEVICE if dev else MEM_HOST, stream))
+    mem = MEM_DEVICE if dev else MEM_HOST
+    if pixel is None:
+        check(lib().trgl_iterative_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, float(tolerance),
+                                      semantics, mode, mem, stream))
+    else:
+        check(lib().trgl_iterative_ls_px(_ptr(u1), _ptr(u2), *pixel.args(), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
+                                         float(tolerance), semantics, mode, mem, stream))
     return x, status
 
 
 def linear_eigen(u1, P1, u2, P2, max_coordinate_value=1.e16, rows=4, out_dtype=np.float64, compute_dtype=np.float64,
-                 x=None, status=None, stream=None):
+                 x=None, status=None, stream=None, pixel=None):
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
-    check(lib().trgl_linear_eigen(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
-                                  float(max_coordinate_value), rows, mode, MEM_DEVICE if dev else MEM_HOST, stream))
+    mem = MEM_DEVICE if dev else MEM_HOST
+    if pixel is None:
+        check(lib().trgl_linear_eigen(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
+                                      float(max_coordinate_value), rows, mode, mem, stream))
+    else:
+        check(lib().trgl_linear_eigen_px(_ptr(u1), _ptr(u2), *pixel.args(), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
+                                         float(max_coordinate_value), rows, mode, mem, stream))
     return x, status
 
 
 def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_dtype=np.float64,
-               compute_dtype=np.float64, x=None, status=None, want_corrected=False, check_all_nan=True, stream=None):
+               compute_dtype=np.float64, x=None, status=None, want_corrected=False, check_all_nan=True, stream=None,
+               pixel=None):
     """Returns x, status, all_nan[, u1_corr, u2_corr]."""
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
     P1 = _P12(P1); P2 = _P12(P2)
@@ -319,7 +393,13 @@ def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_d
     flag = ctypes.c_int(0)
     flag_p = ctypes.byref(flag) if check_all_nan else None
     mem = MEM_DEVICE if dev else MEM_HOST
-    if F is None:
+    if pixel is not None:
+        if F is not None:
+            raise ValueError("pixel inputs and an explicit F cannot be combined")
+        check(lib().trgl_polynomial_px(_ptr(u1), _ptr(u2), *pixel.args(), _dp(P1), _dp(P2), _ptr(x), _ptr(status),
+                                       _ptr(c1), _ptr(c2), flag_p, n, float(max_coordinate_value), rows, mode, mem,
+                                       stream))
+    elif F is None:
         check(lib().trgl_polynomial(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), _ptr(c1), _ptr(c2),
                                     flag_p, n, float(max_coordinate_value), rows, mode, mem, stream))
     else:

@@ -19,7 +19,14 @@ Beyond the reference (all optional, defaults reproduce the reference):
   * set_triangl_semantics(iterative='c'|'py', eigen_rows=4|6) selects the iterative_LS control flow
     (C extension vs pure-Python fallback, SURVEY.md F2) and the OpenCV-4 / OpenCV-2.4 DLT system (F4);
   * device-resident inputs (triangl_cuda.DeviceArray or CUDA torch tensors) are accepted and give
-    device-resident outputs.
+    device-resident outputs;
+  * undistort_points(imgp, cameraMatrix, distCoeffs) is cv2.undistortPoints on the GPU (bit-identical to cv2 4.13), and
+    every solver has a `*_px` twin taking PIXEL coordinates plus the intrinsics, i.e. the three reference lines
+        imgpnrm0 = cv2.undistortPoints(np.array([imgp0]), cameraMatrix, distCoeffs)[0]          (slam2.py:551)
+        imgpnrm1 = cv2.undistortPoints(np.array([imgp1]), cameraMatrix, distCoeffs)[0]          (slam2.py:552)
+        objp, status = iterative_LS_triangulation(imgpnrm0, P0, imgpnrm1, P1)                   (slam2.py:553-555)
+    become   objp, status = iterative_LS_triangulation_px(imgp0, P0, imgp1, P1, cameraMatrix, distCoeffs)
+    with the undistortion done in registers in front of the solve (same bits as the three-line version).
 There is no CPU fallback: without the built library or a GPU every call raises.
 """
 import numpy as np
@@ -126,6 +133,77 @@ def polynomial_triangulation(u1, P1, u2, P2):
         F = _tc.fundamental_8point(u1, u2)
         x, status, _ = _tc.polynomial(u1, P1, u2, P2, F, 1.e16, eigen_rows, _kernel_out_dtype(), compute_dtype,
                                       check_all_nan=False)
+    return _finish(x, status)
+
+
+def P_from_R_and_t(R, t):
+    """4x4 P = [R | t; 0 0 0 1]  (the reference's transforms.P_from_R_and_t, transforms.py:156-168)."""
+    P = np.eye(4)
+    P[0:3, 0:3] = R
+    P[0:3, 3:4] = np.asarray(t, dtype=np.float64).reshape(3, 1)
+    return P
+
+
+def P_from_rvec_and_tvec(rvec, tvec):
+    """4x4 camera matrix from OpenCV's (rvec, tvec) (transforms.py:249 = P_from_R_and_t(cv2.Rodrigues(rvec)[0], tvec)),
+    the form in which slam2.py:554-555 hands the two poses to the solvers.  Rodrigues' formula on the host."""
+    r = np.asarray(rvec, dtype=np.float64).reshape(3)
+    th = float(np.sqrt(r.dot(r)))
+    if th < np.finfo(np.float64).eps:
+        R = np.eye(3)
+    else:
+        k = r / th
+        Kx = np.array([[0., -k[2], k[1]], [k[2], 0., -k[0]], [-k[1], k[0], 0.]])
+        R = np.cos(th) * np.eye(3) + (1. - np.cos(th)) * np.outer(k, k) + np.sin(th) * Kx
+    return P_from_R_and_t(R, tvec)
+
+
+def undistort_points(imgp, cameraMatrix, distCoeffs=None):
+    """cv2.undistortPoints(imgp, cameraMatrix, distCoeffs) without R / P: (N,2) normalised image coordinates in the
+    dtype of `imgp` (any (...,2) shape is accepted, so the cv2-4.x (N,1,2) vs cv2-2.x (1,N,2) pitfall of the
+    reference idiom `cv2.undistortPoints(np.array([imgp]), K, d)[0]` -- SURVEY.md F7 -- does not arise)."""
+    return _tc.undistort_points(imgp, cameraMatrix, distCoeffs)
+
+
+def _intr(cameraMatrix, distCoeffs, cameraMatrix2, distCoeffs2):
+    return _tc.Intrinsics(cameraMatrix, distCoeffs, cameraMatrix2, distCoeffs2)
+
+
+def linear_eigen_triangulation_px(imgp1, P1, imgp2, P2, cameraMatrix, distCoeffs=None, max_coordinate_value=1.e16,
+                                  cameraMatrix2=None, distCoeffs2=None):
+    """linear_eigen_triangulation on pixel coordinates (undistortion fused in front of the solve)."""
+    x, status = _tc.linear_eigen(imgp1, P1, imgp2, P2, max_coordinate_value, eigen_rows, _kernel_out_dtype(),
+                                 compute_dtype, pixel=_intr(cameraMatrix, distCoeffs, cameraMatrix2, distCoeffs2))
+    return _finish(x, status)
+
+
+def linear_LS_triangulation_px(imgp1, P1, imgp2, P2, cameraMatrix, distCoeffs=None, cameraMatrix2=None,
+                               distCoeffs2=None):
+    """linear_LS_triangulation on pixel coordinates (undistortion fused in front of the solve)."""
+    x, status = _tc.linear_ls(imgp1, P1, imgp2, P2, _kernel_out_dtype(), compute_dtype,
+                              pixel=_intr(cameraMatrix, distCoeffs, cameraMatrix2, distCoeffs2))
+    return _finish(x, status)
+
+
+def iterative_LS_triangulation_px(imgp1, P1, imgp2, P2, cameraMatrix, distCoeffs=None, tolerance=3.e-5,
+                                  cameraMatrix2=None, distCoeffs2=None):
+    """iterative_LS_triangulation on pixel coordinates: the SLAM keyframe call pattern slam2.py:551-555 in one call."""
+    sem = _tc.ITER_PY if iterative_semantics == 'py' else _tc.ITER_C
+    x, status = _tc.iterative_ls(imgp1, P1, imgp2, P2, tolerance, sem, _kernel_out_dtype(), compute_dtype,
+                                 pixel=_intr(cameraMatrix, distCoeffs, cameraMatrix2, distCoeffs2))
+    return _finish(x, status, np.int64 if iterative_semantics == 'py' else None)
+
+
+def polynomial_triangulation_px(imgp1, P1, imgp2, P2, cameraMatrix, distCoeffs=None, cameraMatrix2=None,
+                                distCoeffs2=None):
+    """polynomial_triangulation on pixel coordinates (undistortion fused in front of the Hartley-Sturm correction)."""
+    intr = _intr(cameraMatrix, distCoeffs, cameraMatrix2, distCoeffs2)
+    x, status, all_nan = _tc.polynomial(imgp1, P1, imgp2, P2, None, 1.e16, eigen_rows, _kernel_out_dtype(),
+                                        compute_dtype, pixel=intr)
+    if all_nan and len(status) >= 8:
+        # the rare 8-point fallback needs the normalised points as arrays: undistort, then the plain path
+        u1 = _tc.undistort_points(imgp1, intr.K1, intr.d1); u2 = _tc.undistort_points(imgp2, intr.K2, intr.d2)
+        return polynomial_triangulation(u1, P1, u2, P2)
     return _finish(x, status)
 
 

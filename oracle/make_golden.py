@@ -8,6 +8,7 @@ Generate the committed parity fixtures under tests/golden/ (run in the build con
 2. golden_cells.json : sampled cells of the reference's golden result files
    Work/triangulation_comparison/{test_1and2,test_3}.mat and figures_scene/test_1and2.mat (numbers
    only), with the trajectory tables needed to replay them.
+3. cv2_undistort.npz : cv2.undistortPoints outputs (cv2 4.13) pinning the input-normalisation stage.
 """
 import json
 import os
@@ -103,6 +104,28 @@ def golden_cells():
     print("wrote golden_cells.json")
 
 
+def cv2_undistort_fixture():
+    """3. cv2_undistort.npz : cv2.undistortPoints (OpenCV 4.13, the executable third-party statement of the call at
+    slam2.py:551-552) on seeded pixel points, float64 and float32, for several distortion models."""
+    import cv2
+    rng = np.random.RandomState(rig.RSEED + 500)
+    K = np.array([[480., 0, 320], [0, 470., 240], [0, 0, 1]])
+    px = rng.uniform([-200, -200], [840, 680], (2000, 2))
+    dists = np.array([[0.3, -0.1, 0.001, 0.002, 0.05], [-0.6, 0.1, 0, 0, 0], [0.3, 0, 0, 0, 0], [0, 0, 0, 0, 0],
+                      [-0.28, 0.07, 2e-4, -1e-4, 0.0]])
+    out = {"K": K, "px": px, "dists": dists, "cv2_version": np.array(cv2.__version__)}
+    for k, d in enumerate(dists):
+        out["n64_%d" % k] = cv2.undistortPoints(px.reshape(1, -1, 2), K, d).reshape(-1, 2)
+        out["n32_%d" % k] = cv2.undistortPoints(px.astype(np.float32).reshape(1, -1, 2), K, d).reshape(-1, 2)
+    out["n64_none"] = cv2.undistortPoints(px.reshape(1, -1, 2), K, None).reshape(-1, 2)
+    np.savez_compressed(os.path.join(GOLDEN, "cv2_undistort.npz"), **out)
+    print("wrote cv2_undistort.npz (cv2 %s)" % cv2.__version__)
+
+
 if __name__ == "__main__":
-    per_point_fixtures()
-    golden_cells()
+    if len(sys.argv) > 1 and sys.argv[1] == "undistort":
+        cv2_undistort_fixture()
+    else:
+        per_point_fixtures()
+        golden_cells()
+        cv2_undistort_fixture()

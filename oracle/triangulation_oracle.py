@@ -24,6 +24,9 @@ Reference statements followed (paths relative to /root/reference):
   linear_eigen_triangulation triangulation.py:6-25 (cv2.triangulatePoints; rows=4 is OpenCV 4, rows=6 OpenCV 2.4)
   polynomial_triangulation  triangulation.py:198-232 (cv2.correctMatches = Hartley-Sturm, H&Z alg. 12.1)
   reprojection_error        Work/python_libs/calibration_tools.py:116-124 (cv2.projectPoints)
+  undistort_points          cv2.undistortPoints call sites Work/SLAM/application/own/slam2.py:551-552,
+                            Work/triangulation_comparison/triangulation_comparison.py:164-173 (third-party: OpenCV;
+                            pinned bit-exactly to cv2 4.13 output, tests/golden/cv2_undistort.npz)
 """
 import numpy as np
 
@@ -357,6 +360,38 @@ def reprojection_error_ext(objp, imgp, cameraMatrix, distCoeffs, rvecs, tvecs):
         mean_error += np.abs(error).sum(axis=0) / len(imgp[i])
         square_error += (error ** 2).sum(axis=0) / len(imgp[i])
     return np.linalg.norm(mean_error / n_images), np.sqrt(square_error.sum() / n_images)
+
+
+def undistort_points(src, cameraMatrix, distCoeffs=None, iters=5):
+    """
+    cv2.undistortPoints(src, K, dist) for the (k1,k2,p1,p2[,k3]) model with the default criteria (5 fixed-point
+    iterations, no R / P), restating OpenCV's cvUndistortPointsInternal operation by operation: float64 arithmetic in
+    the same evaluation order (x0 = (u-cx)*(1/fx); icdist = 1/(1+((k3 r2+k2) r2+k1) r2); a negative icdist restores the
+    undistorted start value and stops).  Output (N,2) in the dtype of src (float32 stays float32), bit-identical to
+    cv2 4.13 on the committed fixture.
+    """
+    src = np.asarray(src)
+    out_dtype = np.float32 if src.dtype == np.float32 else np.float64
+    p = src.reshape(-1, 2).astype(np.float64)
+    K = np.asarray(cameraMatrix, dtype=np.float64)
+    ifx, ify, cx, cy = 1.0 / K[0, 0], 1.0 / K[1, 1], K[0, 2], K[1, 2]
+    x0 = (p[:, 0] - cx) * ifx; y0 = (p[:, 1] - cy) * ify
+    x = x0.copy(); y = y0.copy()
+    if distCoeffs is not None:
+        dd = np.zeros(5); d_in = np.asarray(distCoeffs, dtype=np.float64).ravel(); dd[:min(5, len(d_in))] = d_in[:5]
+        k1, k2, p1, p2, k3 = dd
+        done = np.zeros(len(x), dtype=bool)
+        with np.errstate(all='ignore'):
+            for _ in range(iters):
+                r2 = x * x + y * y
+                icdist = 1.0 / (1 + ((k3 * r2 + k2) * r2 + k1) * r2)
+                neg = (icdist < 0) & ~done
+                dX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+                dY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+                xn = np.where(neg, x0, (x0 - dX) * icdist); yn = np.where(neg, y0, (y0 - dY) * icdist)
+                x = np.where(done, x, xn); y = np.where(done, y, yn)
+                done |= neg
+    return np.stack([x, y], axis=1).astype(out_dtype)
 
 
 SOLVERS = {

@@ -56,6 +56,11 @@ def eigen_well_posed(u1, P1, u2, P2, rows=4, tol=1e-9):
     return amp * 2.2e-16 * 50 < tol
 
 
+def iterative_margin(u1, P1, u2, P2, semantics='c'):
+    """Distance of the deciding convergence test |d_new - d| <= tol from its threshold (knife-edge points < 1e-9)."""
+    return orc.iterative_LS_core(np.asarray(u1, dtype=np.float64), P1, np.asarray(u2, dtype=np.float64), P2, 3e-5, semantics)[3]
+
+
 def ls_well_posed(u1, P1, u2, P2, tol=1e-9):
     A, _ = orc.build_Ab(u1, P1, u2, P2)
     s = np.linalg.svd(A, compute_uv=False)
@@ -382,3 +387,70 @@ def test_full_size_properties(tri):
         lo = int(rng.randint(0, n - 70000)); hi = lo + 65537
         xs, ss = getattr(tri, name + "_triangulation")(u1[lo:hi], P1, u2[lo:hi], P2)
         assert np.array_equal(xs, x[lo:hi]) and np.array_equal(ss, st[lo:hi]), name
+
+
+# ---- input normalisation fused in front of the solvers -----------------------------------------
+def _pixel_batch(n, rig_name="rotating", dtype=np.float64, seed=5):
+    """Pixel observations of the synthetic rig with a distorting camera: normalised noisy points pushed through the
+    forward distortion model + K (what a real detector would hand to cv2.undistortPoints)."""
+    u1, P1, u2, P2, X = rig.make_correspondences(n, rig_name, sigma=0.8, seed=rig.RSEED + seed)
+    K = np.array([[480., 0, 320], [0, 480., 240], [0, 0, 1]])
+    dist = np.array([-0.28, 0.07, 2e-4, -1e-4, 0.01])
+
+    def to_px(u):
+        z = np.zeros(3)
+        return orc.project_points(np.column_stack([u, np.ones(len(u))]), z, z, K, dist)
+    return to_px(u1).astype(dtype), P1, to_px(u2).astype(dtype), P2, K, dist
+
+
+def test_undistort_kernel_bit_identical_to_cv2_fixture(tri, golden_dir):
+    g = np.load(os.path.join(golden_dir, "cv2_undistort.npz"))
+    px, K = g["px"], g["K"]
+    for k, d in enumerate(g["dists"]):
+        out = tri.undistort_points(px, K, d)
+        assert out.dtype == np.float64 and np.array_equal(out, g["n64_%d" % k]), "float64 model %d" % k
+        out32 = tri.undistort_points(px.astype(np.float32), K, d)
+        assert out32.dtype == np.float32 and np.array_equal(out32, g["n32_%d" % k]), "float32 model %d" % k
+    assert np.array_equal(tri.undistort_points(px, K, None), g["n64_none"])
+    assert np.array_equal(tri.undistort_points(px.reshape(1, -1, 2), K, g["dists"][0]), g["n64_0"])   # cv2-style shape
+    assert tri.undistort_points(np.zeros((0, 2)), K, None).shape == (0, 2)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["linear_eigen", "linear_LS", "iterative_LS", "polynomial"])
+def test_pixel_input_solvers_equal_undistort_then_solve(tri, name, dtype):
+    """*_px == undistort kernel followed by the plain solver, bit for bit (x and status), and both agree with the
+    oracle chain cv2.undistortPoints-restatement -> solver restatement within the FP64 bar."""
+    px1, P1, px2, P2, K, dist = _pixel_batch(20011, dtype=dtype)
+    tri.set_triangl_output_dtype(dtype)
+    try:
+        xf, sf = getattr(tri, name + "_triangulation_px")(px1, P1, px2, P2, K, dist)
+        u1 = tri.undistort_points(px1, K, dist); u2 = tri.undistort_points(px2, K, dist)
+        xs, ss = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)
+    finally:
+        tri.set_triangl_output_dtype(float)
+    assert xf.dtype == dtype
+    assert np.array_equal(np.asarray(sf), np.asarray(ss))
+    assert np.array_equal(xf, xs, equal_nan=True)
+    o1 = orc.undistort_points(px1, K, dist); o2 = orc.undistort_points(px2, K, dist)
+    assert np.array_equal(u1, o1) and np.array_equal(u2, o2)
+    xo, so = orc.SOLVERS[name](o1, P1, o2, P2)
+    ok = eigen_well_posed(o1.astype(np.float64), P1, o2.astype(np.float64), P2) if name in ("linear_eigen", "polynomial") \
+        else np.ones(len(xo), bool)
+    if name == "iterative_LS":
+        ok &= iterative_margin(o1, P1, o2, P2) > 1e-9
+    assert np.array_equal(np.asarray(sf)[ok], np.asarray(so)[ok])
+    tol = TOL64 if dtype == np.float64 else 1e-6          # float32 storage of x: 6e-8 rounding
+    assert rel_err(xf, xo)[ok].max() < tol
+
+
+def test_pixel_input_two_cameras_and_no_distortion(tri):
+    px1, P1, px2, P2, K, dist = _pixel_batch(4099)
+    K2 = K.copy(); K2[0, 0] = 500.; K2[0, 2] = 300.
+    x, st = tri.iterative_LS_triangulation_px(px1, P1, px2, P2, K, dist, cameraMatrix2=K2, distCoeffs2=None)
+    xo, so = orc.iterative_LS_triangulation(orc.undistort_points(px1, K, dist), P1, orc.undistort_points(px2, K2, None), P2)
+    ok = iterative_margin(orc.undistort_points(px1, K, dist), P1, orc.undistort_points(px2, K2, None), P2) > 1e-9
+    assert np.array_equal(st[ok], so[ok]) and rel_err(x, xo)[ok].max() < TOL64
+    # no distortion at all: (p - c) / f shortcut of the harness (triangulation_comparison.py:168-172) up to 1 ulp
+    u = tri.undistort_points(px1, K, None)
+    assert np.allclose(u, (px1 - K[0:2, 2]) / 480., rtol=0, atol=1e-15)

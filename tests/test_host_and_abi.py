@@ -33,7 +33,8 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(L, name), "libtriangl_cuda.so does not export %s" % name
     assert sorted(tc.EXPORTS) == declared
-    assert L.trgl_version() == 100
+    m = re.search(r"#define TRGL_VERSION (\d+)", header)
+    assert L.trgl_version() == int(m.group(1))
 
 
 def test_kernels_are_sm100a_native():
@@ -220,3 +221,37 @@ def test_sharded_path_world_size_2_gloo(tmp_path):
         d = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
         assert np.array_equal(d["st"], so) and np.allclose(d["x"], xo, rtol=1e-12, atol=1e-12)
         assert d["xp"].shape == (999, 3) and np.allclose(d["xp"], xp, rtol=1e-12, atol=1e-12) and d["sp"].all()
+
+
+# ---- input normalisation: oracle pinned to cv2 ------------------------------------------------
+def test_oracle_undistort_bit_identical_to_cv2_fixture():
+    """tests/golden/cv2_undistort.npz holds cv2 4.13 `undistortPoints` output (oracle/make_golden.py): the NumPy
+    restatement must reproduce every bit, float64 and float32, for all distortion models incl. the icdist < 0 branch."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cv2_undistort.npz"))
+    px, K = g["px"], g["K"]
+    for k, d in enumerate(g["dists"]):
+        assert np.array_equal(orc.undistort_points(px, K, d), g["n64_%d" % k])
+        out32 = orc.undistort_points(px.astype(np.float32), K, d)
+        assert out32.dtype == np.float32 and np.array_equal(out32, g["n32_%d" % k])
+    assert np.array_equal(orc.undistort_points(px, K, None), g["n64_none"])
+
+
+def test_oracle_undistort_matches_installed_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(3)
+    K = np.array([[525., 0, 319.5], [0, 525., 239.5], [0, 0, 1]])
+    px = rng.uniform(0, 640, (5000, 2))
+    for d in ([0.2, -0.3, 1e-3, -2e-3, 0.1], [0.1, 0.01, 0, 0]):
+        ref = cv2.undistortPoints(px.reshape(-1, 1, 2), K, np.array(d)).reshape(-1, 2)
+        assert np.array_equal(orc.undistort_points(px, K, d), ref)
+
+
+def test_P_from_rvec_and_tvec_matches_cv2_rodrigues():
+    cv2 = pytest.importorskip("cv2")
+    import triangulation
+    rng = np.random.RandomState(11)
+    for rvec in list(rng.normal(0, 1.5, (20, 3))) + [np.zeros(3), np.array([1e-20, 0, 0])]:
+        tvec = rng.normal(0, 3, (3, 1))
+        P = triangulation.P_from_rvec_and_tvec(rvec, tvec)
+        assert P.shape == (4, 4) and np.array_equal(P[3], [0, 0, 0, 1])
+        assert np.allclose(P[0:3, 0:3], cv2.Rodrigues(rvec)[0], atol=1e-14) and np.array_equal(P[0:3, 3:4], tvec)
