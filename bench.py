@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="N > 1: all-gather x over NCCL inside the timed step")
+    ap.add_argument("--workload", default="solvers", choices=["solvers", "slam"],
+                    help="solvers: the four solvers at --points per GPU (default, BASELINE configs[1]); "
+                         "slam: keyframe map-extension latency at SLAM-sized batches (BASELINE configs[4])")
     return ap.parse_args()
 
 
@@ -338,8 +341,101 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---- SLAM keyframe map-extension replay: latency at SLAM-sized batches (BASELINE.json configs[4]) ----------------
+def run_slam(args):
+    """
+    One keyframe = the triangulation work of slam2.py:541-600 on B new correspondences: float32 pixel points, 4x4 P from
+    (rvec, tvec), output dtype float32 (slam2.py:19):
+        undistortPoints x2 -> iterative_LS -> keep status == 1 -> (solvePnP, not on this path) -> iterative_LS again on the
+        inliers -> keep status >= 0.
+    Timed end to end through the Python API with pageable host arrays (what SLAM holds), wall clock, median of K keyframes:
+      dropin : undistort_points x2 + iterative_LS_triangulation x2   (the reference's call sequence, 4 library calls)
+      fused  : iterative_LS_triangulation_px x2                      (undistortion in registers, 2 library calls)
+      cpu    : cv2.undistortPoints x2 + the C oracle port of triangulation.c, 1 thread (the reference's shipped build
+               has OpenMP disabled, triangulation_c/setup.py:12-13)
+    """
+    import triangl_cuda as tc
+    import triangulation as tri
+    tc.require_device()
+    K = np.array([[525., 0, 319.5], [0, 525., 239.5], [0, 0, 1]])
+    dist = np.array([-0.28, 0.07, 2e-4, -1e-4, 0.01])
+    out = {"metric": "slam_keyframe_triangulation_latency", "unit": "us per keyframe (median)", "higher_is_better": False,
+           "n_gpus": 1, "dtype": "f64 arithmetic, f32 storage", "data": "synthetic",
+           "config": {"workload": "SLAM keyframe map-extension replay (BASELINE.json configs[4]): float32 pixels, 4x4 P, "
+                                  "output float32, undistort x2 + iterative_LS x2 + status masks per keyframe",
+                      "keyframes_per_size": args.steps, "warmup": args.warmup}, "sizes": {}}
+    tri.set_triangl_output_dtype(np.float32)
+    try:
+        for B in (1000, 3000, 10000, 30000, 100000):
+            u1, P1, u2, P2, _ = rig.make_correspondences(B, args.rig, sigma=0.8, seed=rig.RSEED + B)
+
+            def to_px(u):
+                x, y = u[:, 0], u[:, 1]
+                r2 = x * x + y * y
+                k1, k2, p1, p2, k3 = dist
+                rad = 1 + k1 * r2 + k2 * r2 * r2 + k3 * r2 ** 3
+                return np.stack([K[0, 0] * (x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)) + K[0, 2],
+                                 K[1, 1] * (y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y) + K[1, 2]], 1).astype(np.float32)
+            px1, px2 = to_px(u1), to_px(u2)
+            P1f = np.eye(4); P1f[0:3] = P1
+            P2f = np.eye(4); P2f[0:3] = P2
+
+            def dropin():
+                n1 = tri.undistort_points(px1, K, dist); n2 = tri.undistort_points(px2, K, dist)
+                x, st = tri.iterative_LS_triangulation(n1, P1f, n2, P2f)
+                inl = np.where(st == 1)[0]
+                n1 = n1[inl]; n2 = n2[inl]
+                x, st = tri.iterative_LS_triangulation(n1, P1f, n2, P2f)
+                return x[np.where(st >= 0)[0]]
+
+            def fused():
+                x, st = tri.iterative_LS_triangulation_px(px1, P1f, px2, P2f, K, dist)
+                inl = np.where(st == 1)[0]
+                x, st = tri.iterative_LS_triangulation_px(px1[inl], P1f, px2[inl], P2f, K, dist)
+                return x[np.where(st >= 0)[0]]
+
+            def timed(fn, reps):
+                for _ in range(args.warmup):
+                    fn()
+                ts = []
+                for _ in range(reps):
+                    t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+                return 1e6 * float(np.median(ts)), 1e6 * float(np.percentile(ts, 95))
+            l0 = tc.launch_count()
+            d_med, d_p95 = timed(dropin, args.steps)
+            f_med, f_p95 = timed(fused, args.steps)
+            launches = tc.launch_count() - l0
+            assert np.array_equal(dropin(), fused())
+            row = {"dropin_us": d_med, "dropin_p95_us": d_p95, "fused_us": f_med, "fused_p95_us": f_p95,
+                   "fused_points_per_sec": 2 * B / (f_med * 1e-6), "gpu_launches": launches}
+            if not args.no_cpu_baseline:
+                from oracle import oracle_c
+                try:
+                    import cv2
+                    und = lambda p: cv2.undistortPoints(p.reshape(-1, 1, 2), K, dist).reshape(-1, 2)      # noqa: E731
+                except ImportError:
+                    from oracle import triangulation_oracle as orc
+                    und = lambda p: orc.undistort_points(p, K, dist)                                       # noqa: E731
+                oracle_c.set_num_threads(1)
+
+                def cpu():
+                    n1 = und(px1); n2 = und(px2)
+                    x, st = oracle_c.iterative_LS_triangulation(n1, P1f[0:3], n2, P2f[0:3])
+                    inl = np.where(st == 1)[0]
+                    x, st = oracle_c.iterative_LS_triangulation(n1[inl], P1f[0:3], n2[inl], P2f[0:3])
+                    return x[np.where(st >= 0)[0]].astype(np.float32)
+                c_med, c_p95 = timed(cpu, max(3, min(args.steps, 2_000_000 // B)))
+                row.update({"cpu_us": c_med, "cpu_threads": oracle_c.num_threads(), "speedup_fused_vs_cpu": c_med / f_med})
+            out["sizes"][str(B)] = row
+    finally:
+        tri.set_triangl_output_dtype(float)
+    print(json.dumps(out))
+
+
 def main():
     args = parse()
+    if args.workload == "slam":
+        return run_slam(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -297,10 +297,51 @@ inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255);
 
 struct HostArray { const void* in; void* out; size_t bytes_per_point; };
 
+// Small batches (the SLAM keyframe sizes, slam2.py:1080-1082: a few hundred points): latency is all API calls, so the
+// kernel works straight on page-locked, device-mapped host memory (UVA: the cudaHostAlloc pointer is valid on the
+// device).  Inputs are memcpy'd into the staging block by the CPU, ONE kernel reads them over PCIe and writes x / status
+// back into the same block, one stream synchronise, CPU memcpy out: 1 launch + 1 sync instead of 4 copies + launch + sync.
+constexpr int64_t kZeroCopyMax = 16384;
+char* g_zc_buf = nullptr;
+size_t g_zc_cap = 0;
+
+int ensure_zero_copy(size_t bytes) {
+    if (g_zc_cap >= bytes) return TRGL_OK;
+    if (g_zc_buf) { cudaFreeHost(g_zc_buf); g_zc_buf = nullptr; g_zc_cap = 0; }
+    const size_t want = bytes < (size_t(1) << 20) ? (size_t(1) << 20) : bytes + bytes / 4;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_zc_buf), want, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(TRGL_E_NOMEM, "cudaHostAlloc of the zero-copy staging block failed");
+    }
+    g_zc_cap = want;
+    return TRGL_OK;
+}
+
 // launcher(dev pointers in the order of `arrays`, chunk point count, stream)
 template <typename Launch>
 int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
     std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    if (n <= kZeroCopyMax) {
+        size_t total = 0;
+        for (int a = 0; a < narrays; ++a) total += align256(arrays[a].bytes_per_point * n);
+        int rc = ensure_zero_copy(total);
+        if (rc) return rc;
+        rc = ensure_slot(g_slots[0], 0);
+        if (rc) return rc;
+        void* dptr[8];
+        size_t pos = 0;
+        for (int a = 0; a < narrays; ++a) {
+            dptr[a] = g_zc_buf + pos;
+            pos += align256(arrays[a].bytes_per_point * n);
+            if (arrays[a].in) std::memcpy(dptr[a], arrays[a].in, arrays[a].bytes_per_point * n);
+        }
+        rc = launch(dptr, n, g_slots[0].stream, 0);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(g_slots[0].stream));
+        for (int a = 0; a < narrays; ++a)
+            if (arrays[a].out) std::memcpy(arrays[a].out, dptr[a], arrays[a].bytes_per_point * n);
+        return TRGL_OK;
+    }
     const int64_t chunk = n < kChunk ? n : kChunk;
     size_t per_chunk = 0;
     for (int a = 0; a < narrays; ++a) per_chunk += align256(arrays[a].bytes_per_point * chunk);

@@ -243,6 +243,7 @@ def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
 
+_FLOAT_DTYPES = (np.dtype(np.float32), np.dtype(np.float64))
 _MODE = {(8, 8, 8): F64, (4, 8, 4): F32IO, (4, 4, 4): F32, (8, 8, 4): F64_OUT32, (4, 8, 8): F32_OUT64}
 
 
@@ -256,6 +257,14 @@ def mode_for(in_dtype, compute_dtype, out_dtype):
 def _prep(u1, u2, compute_dtype, out_dtype):
     """Input coercion of the reference wrapper (triangulation_c/__init__.py:32-39), without the forced up-cast:
     float32 inputs stay float32 in HBM and are widened in registers."""
+    if type(u1) is np.ndarray and type(u2) is np.ndarray and u1.dtype == u2.dtype and u1.ndim == 2 and u2.ndim == 2 \
+            and u1.shape[1] == 2 and u1.shape == u2.shape and u1.flags.c_contiguous and u2.flags.c_contiguous \
+            and u1.dtype in _FLOAT_DTYPES:
+        # fast path of the small-batch (SLAM keyframe) calls: nothing to coerce
+        in_dtype = u1.dtype
+        if np.dtype(compute_dtype) == np.float32 and (in_dtype != np.float32 or np.dtype(out_dtype) != np.float32):
+            compute_dtype = np.float64
+        return u1, u2, False, len(u1), mode_for(in_dtype, compute_dtype, out_dtype)
     dev = _is_device(u1)
     if dev != _is_device(u2):
         raise ValueError("u1 and u2 must both be host arrays or both be device buffers")

@@ -40,6 +40,10 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))
+
+
 def linear_LS_triangulation(u1, P1, u2, P2):
     u1, P1, u2, P2, n = _prep(u1, P1, u2, P2)
     x = np.empty((n, 3)); st = np.empty(n, dtype=np.uint8)
