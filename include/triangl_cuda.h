@@ -170,6 +170,27 @@ int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double
                      void* err1, void* err2, uint8_t* good, double* sums,
                      int64_t n, int mode, int mem, void* stream);
 
+/* ---- harness statistics on the device ---- */
+
+/* error_vectors_3D + error_rms + robustness_stat of the comparison harness
+ * (Work/triangulation_comparison/triangulation_comparison.py:179-188, 205-217, 242-260):
+ * errors[i] = |x[i] - exact[i, 0:3]|^2 (n doubles, may be NULL; same memory space as x), exact: (n, exact_stride) doubles
+ * (stride 4 for the harness' homogeneous cloud).  status (uint8 / int32, may be NULL) feeds robustness_stat with the
+ * thresholds robustness_thresh_max / _min (:372-373).  stats (host, 4 doubles): sum of errors, number of NaN errors,
+ * number of false positives (error > thresh_max and status > 0), number of false negatives (error <= thresh_min and
+ * not status > 0); divide by n for the reference's ratios.  Synchronises the stream. */
+int trgl_eval_errors_3d(const void* x, const double* exact, int exact_stride, const void* status, int status_is_i32,
+                        double thresh_max, double thresh_min, double* errors, double* stats, int64_t n, int x_is_f32,
+                        int mem, void* stream);
+/* error_rms on 2-D residuals: errors[i] = |proj[i] - exact[i]|^2 with proj from trgl_reproj_error (pixels) and the exact
+ * pixel positions (error_vectors_2D, :190-203).  stats (host, 4 doubles): sum of errors, number of NaN errors, 0, 0. */
+int trgl_eval_errors_2d(const void* proj, const double* exact, double* errors, double* stats, int64_t n, int proj_is_f32,
+                        int mem, void* stream);
+/* np.median of n non-negative doubles (the squared errors above), exact: most-significant-digit radix selection on the
+ * IEEE bit patterns (8 histogram passes), mean of the two middle elements for even n, NaN if any element is NaN or
+ * n == 0.  median: host double.  Synchronises the stream. */
+int trgl_median(const double* values, int64_t n, int mem, double* median, void* stream);
+
 /* ---- bench / diagnostics ---- */
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t trgl_launch_count(void);

@@ -129,6 +129,92 @@ k_pair_reproj(const TO* __restrict__ x, const TI* __restrict__ u1, const TI* __r
     block_reduce_store<4>(acc, partials);
 }
 
+// ---- harness statistics on the device (triangulation_comparison.py:179-188, 205-217, 242-260) ---------------------
+// Squared 3-D error per point against the exact cloud, with the reductions error_rms and robustness_stat need:
+// partials per block = sum of errors, #NaN errors, #false positives (error > thresh_max and status > 0),
+// #false negatives (error <= thresh_min and not status > 0).
+template <typename TO, typename TS>
+__global__ void __launch_bounds__(kThreads)
+k_sq_errors_3d(const TO* __restrict__ x, const double* __restrict__ exact, const int exact_stride,
+               const TS* __restrict__ status, const double thresh_max, const double thresh_min,
+               double* __restrict__ errors, double* __restrict__ partials, const int64_t n) {
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        // error_vectors_3D: points_3D_calc - points_3D_exact[:, 0:3]; error_rms: sum(v**2, axis=1) = (dx^2 + dy^2) + dz^2
+        const double dx = static_cast<double>(x[3 * i + 0]) - exact[exact_stride * i + 0];
+        const double dy = static_cast<double>(x[3 * i + 1]) - exact[exact_stride * i + 1];
+        const double dz = static_cast<double>(x[3 * i + 2]) - exact[exact_stride * i + 2];
+        const double e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (errors) errors[i] = e;
+        acc[0] += e;
+        if (e != e) acc[1] += 1.0;
+        if (status) {
+            const bool est = static_cast<int>(status[i]) > 0;
+            if (!(e <= thresh_max) && est) acc[2] += 1.0;          // (errors <= max) == False  and  positives_est
+            if ((e <= thresh_min) && !est) acc[3] += 1.0;
+        }
+    }
+    block_reduce_store<4>(acc, partials);
+}
+
+// Squared norm of (n,2) residual vectors proj - exact (error_rms on error_vectors_2D), same partials[0..1].
+template <typename TP>
+__global__ void __launch_bounds__(kThreads)
+k_sq_errors_2d(const TP* __restrict__ proj, const double* __restrict__ exact, double* __restrict__ errors,
+               double* __restrict__ partials, const int64_t n) {
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const double dx = static_cast<double>(proj[2 * i + 0]) - exact[2 * i + 0];
+        const double dy = static_cast<double>(proj[2 * i + 1]) - exact[2 * i + 1];
+        const double e = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (errors) errors[i] = e;
+        acc[0] += e;
+        if (e != e) acc[1] += 1.0;
+    }
+    block_reduce_store<4>(acc, partials);
+}
+
+// Exact order statistics of non-negative doubles (np.median semantics) by most-significant-digit radix selection: the
+// IEEE-754 bit pattern of a non-negative double is monotone as an unsigned integer.  One pass histograms the 8-bit digit
+// at `shift` of every key whose higher digits equal `prefix` (shared-memory privatised, one global atomic per bin/block).
+__global__ void __launch_bounds__(kThreads)
+k_radix_hist(const double* __restrict__ v, const int64_t n, const unsigned long long prefix, const unsigned long long mask,
+             const int shift, unsigned long long* __restrict__ hist /* 256 bins + [256] = NaN count (first pass) */) {
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0;                       // kThreads == 256
+    __syncthreads();
+    unsigned int nans = 0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const double val = v[i];
+        const unsigned long long key = static_cast<unsigned long long>(__double_as_longlong(val));
+        if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & 255ull], 1u);
+        if (val != val) ++nans;
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], static_cast<unsigned long long>(h[threadIdx.x]));
+    if (mask == 0ull && nans) atomicAdd(&hist[256], static_cast<unsigned long long>(nans));
+}
+
+// Smallest key strictly greater than `key0` (for the upper middle element of an even-sized sample).
+__global__ void __launch_bounds__(kThreads)
+k_min_above(const double* __restrict__ v, const int64_t n, const unsigned long long key0, unsigned long long* __restrict__ out) {
+    unsigned long long best = ~0ull;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const unsigned long long key = static_cast<unsigned long long>(__double_as_longlong(v[i]));
+        if (key > key0 && key < best) best = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(out, best);
+}
+
 // ---- whole-batch reductions for the normalised 8-point fundamental matrix (triangulation.py:228) ---------------
 // stage 0: sum x1,y1,x2,y2   stage 1: sum |p1-m1|, |p2-m2|   stage 2: the 45 unique entries of A^T A, where the row of
 // A for one match is (x2x1, x2y1, x2, y2x1, y2y1, y2, x1, y1, 1) in normalised coordinates.

@@ -989,4 +989,137 @@ int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double
     return TRGL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Harness statistics on the device (triangulation_comparison.py:179-260): per-point squared errors, their sum, the
+// false-positive / false-negative counts of robustness_stat, and the exact median (radix selection).
+static int eval_errors_common(bool three_d, const void* a, const double* exact, int exact_stride, const void* status,
+                              int status_is_i32, double thresh_max, double thresh_min, double* errors, double* stats,
+                              int64_t n, int a_is_f32, int mem, void* stream) {
+    if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (!stats) return fail(TRGL_E_BADARG, "stats is NULL");
+    if (n > 0 && (!a || !exact)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
+    if (three_d && exact_stride < 3) return fail(TRGL_E_BADARG, "exact_stride must be >= 3");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    stats[0] = stats[1] = stats[2] = stats[3] = 0.0;
+    if (n == 0) return TRGL_OK;
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    int rc = ensure_scratch(kReduceBlocks * 8);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t ab = (a_is_f32 ? 4 : 8) * (three_d ? 3 : 2), eb = 8 * (three_d ? exact_stride : 2), sb = status_is_i32 ? 4 : 1;
+    const void* da = a; const double* de = exact; const void* dst = status; double* derr = errors;
+    if (mem == TRGL_MEM_HOST) {
+        const size_t oa = 0, oe = align256(ab * n), os = oe + align256(eb * n), oerr = os + align256(sb * n);
+        rc = ensure_slot(g_slots[0], oerr + align256(8 * n));
+        if (rc) return rc;
+        Slot& sl = g_slots[0];
+        s = sl.stream;
+        CK(cudaMemcpyAsync(sl.buf + oa, a, ab * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(sl.buf + oe, exact, eb * n, cudaMemcpyHostToDevice, s));
+        if (status) CK(cudaMemcpyAsync(sl.buf + os, status, sb * n, cudaMemcpyHostToDevice, s));
+        da = sl.buf + oa; de = reinterpret_cast<const double*>(sl.buf + oe); dst = status ? sl.buf + os : nullptr;
+        derr = errors ? reinterpret_cast<double*>(sl.buf + oerr) : nullptr;
+    }
+    const int blocks = kReduceBlocks;
+    if (three_d) {
+#define E3(TO, TS) k_sq_errors_3d<TO, TS><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(da), de, exact_stride, static_cast<const TS*>(dst), thresh_max, thresh_min, derr, g_partials, n)
+        if (a_is_f32) { if (status_is_i32) E3(float, int32_t); else E3(float, uint8_t); }
+        else { if (status_is_i32) E3(double, int32_t); else E3(double, uint8_t); }
+#undef E3
+    } else {
+        if (a_is_f32) k_sq_errors_2d<float><<<blocks, kThreads, 0, s>>>(static_cast<const float*>(da), de, derr, g_partials, n);
+        else k_sq_errors_2d<double><<<blocks, kThreads, 0, s>>>(static_cast<const double*>(da), de, derr, g_partials, n);
+    }
+    g_launches++;
+    CK(cudaGetLastError());
+    static thread_local double hpart[kReduceBlocks * 4];
+    CK(cudaMemcpyAsync(hpart, g_partials, sizeof(double) * blocks * 4, cudaMemcpyDeviceToHost, s));
+    if (mem == TRGL_MEM_HOST && errors) CK(cudaMemcpyAsync(errors, derr, 8 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int b = 0; b < blocks; ++b)
+        for (int k = 0; k < 4; ++k) stats[k] += hpart[b * 4 + k];
+    return TRGL_OK;
+}
+
+int trgl_eval_errors_3d(const void* x, const double* exact, int exact_stride, const void* status, int status_is_i32,
+                        double thresh_max, double thresh_min, double* errors, double* stats, int64_t n, int x_is_f32,
+                        int mem, void* stream) {
+    return eval_errors_common(true, x, exact, exact_stride, status, status_is_i32, thresh_max, thresh_min, errors, stats, n,
+                              x_is_f32, mem, stream);
+}
+
+int trgl_eval_errors_2d(const void* proj, const double* exact, double* errors, double* stats, int64_t n, int proj_is_f32,
+                        int mem, void* stream) {
+    return eval_errors_common(false, proj, exact, 2, nullptr, 0, 0.0, 0.0, errors, stats, n, proj_is_f32, mem, stream);
+}
+
+int trgl_median(const double* values, int64_t n, int mem, double* median, void* stream) {
+    if (n < 0) return fail(TRGL_E_BADARG, "negative count");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (!median || (n > 0 && !values)) return fail(TRGL_E_BADARG, "NULL pointer");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    *median = std::nan("");
+    if (n == 0) return TRGL_OK;                       // np.median of an empty array is NaN
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    int rc = ensure_scratch(kReduceBlocks * 8);       // g_partials doubles as the 256-bin histogram (2048 bytes)
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const double* dv = values;
+    if (mem == TRGL_MEM_HOST) {
+        rc = ensure_slot(g_slots[0], 8 * n);
+        if (rc) return rc;
+        s = g_slots[0].stream;
+        CK(cudaMemcpyAsync(g_slots[0].buf, values, 8 * n, cudaMemcpyHostToDevice, s));
+        dv = reinterpret_cast<const double*>(g_slots[0].buf);
+    }
+    unsigned long long* dh = reinterpret_cast<unsigned long long*>(g_partials);
+    const int64_t tiles = (n + kThreads - 1) / kThreads;
+    const unsigned blocks = static_cast<unsigned>(tiles < kReduceBlocks ? tiles : kReduceBlocks);
+    unsigned long long hist[257];
+    // rank of the lower middle element (0-based); keys: non-negative doubles sort like their bit patterns, NaNs
+    // (0x7ff8...) sort above +inf, negative values are not supported (the inputs are squared errors)
+    int64_t rank = (n - 1) / 2;
+    unsigned long long prefix = 0, mask = 0;
+    int64_t below = 0, eq = 0;
+    for (int pass = 7; pass >= 0; --pass) {
+        const int shift = 8 * pass;
+        CK(cudaMemsetAsync(dh, 0, sizeof(hist), s));
+        k_radix_hist<<<blocks, kThreads, 0, s>>>(dv, n, prefix, mask, shift, dh);
+        g_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hist, dh, sizeof(hist), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (pass == 7) {
+            if (hist[256]) return TRGL_OK;            // np.median: any NaN in the sample gives NaN
+            for (int b2 = 128; b2 < 256; ++b2)
+                if (hist[b2]) return fail(TRGL_E_BADARG, "median: negative values are not supported (inputs are squared errors)");
+        }
+        int64_t cum = 0;
+        int b = 0;
+        for (; b < 256; ++b) {
+            if (cum + static_cast<int64_t>(hist[b]) > rank) break;
+            cum += static_cast<int64_t>(hist[b]);
+        }
+        if (b == 256) return fail(TRGL_E_BADARG, "median: inconsistent histogram (negative values?)");
+        rank -= cum; below += cum; eq = static_cast<int64_t>(hist[b]);
+        prefix |= static_cast<unsigned long long>(b) << shift;
+        mask |= 255ull << shift;
+    }
+    unsigned long long key_lo = prefix, key_hi = prefix;
+    if (n % 2 == 0 && below + eq <= n / 2) {          // the upper middle element is the next larger key
+        unsigned long long init = ~0ull;
+        CK(cudaMemcpyAsync(dh, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+        k_min_above<<<blocks, kThreads, 0, s>>>(dv, n, prefix, dh);
+        g_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&key_hi, dh, sizeof(key_hi), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    double lo, hi;
+    std::memcpy(&lo, &key_lo, 8); std::memcpy(&hi, &key_hi, 8);
+    *median = (n % 2) ? lo : 0.5 * (lo + hi);
+    return TRGL_OK;
+}
+
 }  // extern "C"

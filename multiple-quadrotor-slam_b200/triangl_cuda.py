@@ -31,6 +31,7 @@ EXPORTS = [
     "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
     "trgl_set_points_per_thread", "trgl_set_stream_variant",
+    "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -80,6 +81,9 @@ def lib():
     L.trgl_fundamental_8point.argtypes = [vp, vp, i64, cint, cint, dp, vp]
     L.trgl_reproj_error.argtypes = [vp, vp, dp, dp, dp, dp, vp, dp, dp, i64, cint, cint, cint, vp]
     L.trgl_pair_reproj.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, dp, i64, cint, cint, vp]
+    L.trgl_eval_errors_3d.argtypes = [vp, vp, cint, vp, cint, dbl, dbl, vp, dp, i64, cint, cint, vp]
+    L.trgl_eval_errors_2d.argtypes = [vp, vp, vp, dp, i64, cint, cint, vp]
+    L.trgl_median.argtypes = [vp, i64, cint, dp, vp]
     L.trgl_undistort_points.argtypes = [vp, vp, dp, dp, i64, cint, cint, vp]
     L.trgl_linear_ls_px.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, vp, vp, i64, cint, cint, vp]
     L.trgl_iterative_ls_px.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
@@ -136,11 +140,23 @@ class DeviceArray:
         check(lib().trgl_stream_synchronize(stream))
         return out
 
+    def view(self, offset, shape):
+        """Non-owning view of `shape` starting `offset` elements into this buffer (keeps the parent alive)."""
+        v = DeviceArray.__new__(DeviceArray)
+        v.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        v.dtype = self.dtype
+        v.nbytes = int(np.prod(v.shape, dtype=np.int64)) * self.dtype.itemsize
+        if offset < 0 or offset * self.dtype.itemsize + v.nbytes > self.nbytes:
+            raise ValueError("view outside the buffer")
+        v.ptr = self.ptr + int(offset) * self.dtype.itemsize
+        v._parent = self
+        return v
+
     def __del__(self):
         try:
-            if getattr(self, "ptr", 0):
+            if getattr(self, "ptr", 0) and getattr(self, "_parent", None) is None:
                 _lib.trgl_device_free(self.ptr)
-                self.ptr = 0
+            self.ptr = 0
         except Exception:
             pass
 
@@ -485,6 +501,60 @@ def pair_reproj(x, u1, P1, u2, P2, status, min_status=0, max_sq_err=np.inf, want
                                  int(min_status), float(max_sq_err), _ptr(e1), _ptr(e2), _ptr(good), _dp(sums), n,
                                  mode, MEM_DEVICE if dev else MEM_HOST, stream))
     return e1, e2, good, sums
+
+
+def eval_errors_3d(x, exact, status=None, thresh_max=1.0, thresh_min=1.0, want_errors=True, stream=None):
+    """Squared 3-D errors against the exact cloud + the sums error_rms / robustness_stat need.
+    Returns errors (or None), stats = (sum, #NaN, #false positives, #false negatives)."""
+    dev = _is_device(x)
+    if not dev:
+        x = np.asarray(x)
+        if x.dtype != np.float32:
+            x = x.astype(np.float64, copy=False)
+        x = np.ascontiguousarray(x.reshape(-1, 3))
+        exact = np.ascontiguousarray(exact, dtype=np.float64)
+        if status is not None:
+            status = np.asarray(status)
+            status = np.ascontiguousarray(status).view(np.uint8) if status.dtype == np.bool_ else \
+                np.ascontiguousarray(status, dtype=np.uint8 if status.dtype == np.uint8 else np.int32)
+    n = len(x)
+    stride = int(exact.shape[1])
+    x32 = int(np.dtype(str(x.dtype).replace("torch.", "")) == np.float32)
+    s_i32 = int(status is not None and np.dtype(str(status.dtype).replace("torch.", "")).itemsize == 4)
+    errors = _out(dev, n, 0, np.float64, None) if want_errors else None
+    stats = np.zeros(4)
+    check(lib().trgl_eval_errors_3d(_ptr(x), _ptr(exact), stride, _ptr(status), s_i32, float(thresh_max), float(thresh_min),
+                                    _ptr(errors), _dp(stats), n, x32, MEM_DEVICE if dev else MEM_HOST, stream))
+    return errors, stats
+
+
+def eval_errors_2d(proj, exact, want_errors=True, stream=None):
+    """Squared 2-D errors |proj - exact|^2 and their sum.  Returns errors (or None), stats = (sum, #NaN, 0, 0)."""
+    dev = _is_device(proj)
+    if not dev:
+        proj = np.asarray(proj)
+        if proj.dtype != np.float32:
+            proj = proj.astype(np.float64, copy=False)
+        proj = np.ascontiguousarray(proj.reshape(-1, 2))
+        exact = np.ascontiguousarray(np.asarray(exact, dtype=np.float64).reshape(-1, 2))
+    n = len(proj)
+    p32 = int(np.dtype(str(proj.dtype).replace("torch.", "")) == np.float32)
+    errors = _out(dev, n, 0, np.float64, None) if want_errors else None
+    stats = np.zeros(4)
+    check(lib().trgl_eval_errors_2d(_ptr(proj), _ptr(exact), _ptr(errors), _dp(stats), n, p32,
+                                    MEM_DEVICE if dev else MEM_HOST, stream))
+    return errors, stats
+
+
+def median(values, stream=None):
+    """np.median of non-negative float64 values (host array or device buffer), exact."""
+    dev = _is_device(values)
+    if not dev:
+        values = np.ascontiguousarray(values, dtype=np.float64).ravel()
+    n = int(np.prod(values.shape))
+    out = np.zeros(1)
+    check(lib().trgl_median(_ptr(values), n, MEM_DEVICE if dev else MEM_HOST, _dp(out), stream))
+    return float(out[0])
 
 
 def launch_count():

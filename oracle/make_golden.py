@@ -9,6 +9,8 @@ Generate the committed parity fixtures under tests/golden/ (run in the build con
    Work/triangulation_comparison/{test_1and2,test_3}.mat and figures_scene/test_1and2.mat (numbers
    only), with the trajectory tables needed to replay them.
 3. cv2_undistort.npz : cv2.undistortPoints outputs (cv2 4.13) pinning the input-normalisation stage.
+4. slam_replay_svo.npz : per-keyframe batches of the recorded slam2 run on the reference's SVO dataset + the reference's
+   own results on them.
 """
 import json
 import os
@@ -122,10 +124,46 @@ def cv2_undistort_fixture():
     print("wrote cv2_undistort.npz (cv2 %s)" % cv2.__version__)
 
 
+def slam_replay_fixture():
+    """4. slam_replay_svo.npz : the recorded slam2 run on the SVO dataset shipped with the reference
+    (Work/SLAM/datasets/SVO/sin2_tex2_h1_v8_d: BA_info.* + traj_out.cam0-slam2.txt), turned into per-keyframe
+    triangulation batches by multiple-quadrotor-slam_b200/slam_replay.py, plus what the REFERENCE computes on them:
+    cv2.undistortPoints and the reference's own iterative_LS_triangulation (exec'd, float32 points, float32 output,
+    the convention of slam2.py:19,551-555), first pass and the re-triangulation of the status == 1 inliers."""
+    import cv2
+    import slam_replay
+    ref = load_reference_triangulation()
+    ds = slam_replay.load_dataset(os.path.join(REFERENCE_ROOT, "Work/SLAM/datasets/SVO/sin2_tex2_h1_v8_d"))
+    K, dist = ds["K"], ds["dist"]
+    off = [0]; px0 = []; px1 = []; P0 = []; P1 = []; steps = []; x1 = []; s1 = []; off2 = [0]; x2 = []; s2 = []
+    ref.set_triangl_output_dtype(np.float32)
+    for kf in ds["keyframes"]:
+        a = kf["px0"].astype(np.float32); b = kf["px1"].astype(np.float32)
+        n0 = cv2.undistortPoints(a.reshape(-1, 1, 2), K, dist).reshape(-1, 2)
+        n1 = cv2.undistortPoints(b.reshape(-1, 1, 2), K, dist).reshape(-1, 2)
+        Pa, Pb = ds["poses"][kf["frame0"]], ds["poses"][kf["frame1"]]
+        x, st = ref.iterative_LS_triangulation(n0, Pa, n1, Pb)
+        inl = np.where(st == 1)[0]
+        xr, sr = ref.iterative_LS_triangulation(n0[inl], Pa, n1[inl], Pb) if len(inl) else (np.zeros((0, 3), np.float32), np.zeros(0, int))
+        px0.append(a); px1.append(b); P0.append(Pa); P1.append(Pb); steps.append(kf["step"])
+        x1.append(x); s1.append(st); x2.append(xr); s2.append(sr)
+        off.append(off[-1] + len(a)); off2.append(off2[-1] + len(inl))
+    ref.set_triangl_output_dtype(float)
+    np.savez_compressed(os.path.join(GOLDEN, "slam_replay_svo.npz"), K=K, dist=dist, steps=np.array(steps),
+                        offsets=np.array(off), px0=np.concatenate(px0), px1=np.concatenate(px1), P0=np.array(P0),
+                        P1=np.array(P1), x_first=np.concatenate(x1), status_first=np.concatenate(s1),
+                        offsets_second=np.array(off2), x_second=np.concatenate(x2), status_second=np.concatenate(s2))
+    print("wrote slam_replay_svo.npz: %d keyframes, %d correspondences (batch sizes %d..%d, median %d)" % (
+        len(steps), off[-1], min(np.diff(off)), max(np.diff(off)), int(np.median(np.diff(off)))))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "undistort":
         cv2_undistort_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "slam":
+        slam_replay_fixture()
     else:
         per_point_fixtures()
         golden_cells()
         cv2_undistort_fixture()
+        slam_replay_fixture()

@@ -454,3 +454,83 @@ def test_pixel_input_two_cameras_and_no_distortion(tri):
     # no distortion at all: (p - c) / f shortcut of the harness (triangulation_comparison.py:168-172) up to 1 ulp
     u = tri.undistort_points(px1, K, None)
     assert np.allclose(u, (px1 - K[0:2, 2]) / 480., rtol=0, atol=1e-15)
+
+
+# ---- device-side harness statistics -------------------------------------------------------------
+def test_device_median_is_np_median(tri):
+    import triangl_cuda as tc
+    rng = np.random.RandomState(9)
+    cases = [rng.rand(1), rng.rand(2), rng.rand(1001) ** 4, rng.rand(1000) * 1e-12, np.repeat(rng.rand(7), 150),
+             np.r_[rng.rand(500), np.inf, np.inf], np.zeros(64), rng.rand(300000), np.r_[rng.rand(10), np.nan]]
+    for v in cases:
+        want = np.median(v)
+        for arr in (v, tc.to_device(v)):
+            got = tc.median(arr)
+            assert (np.isnan(want) and np.isnan(got)) or got == want, (len(v), got, want)
+    assert np.isnan(tc.median(np.zeros(0)))
+    with pytest.raises(tc.TrianglCudaError):
+        tc.median(np.array([1.0, -2.0, 3.0]))
+
+
+def test_device_error_statistics_match_numpy(tri):
+    import harness_stats as hs
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(50021, "rotating", sigma=4.0)
+    x, st = tri.iterative_LS_triangulation(u1, P1, u2, P2)
+    errors = np.sum((x - X[:, 0:3]) ** 2, axis=1)
+    rms, rmed, e_dev = hs.error_rms_3D(X, x)
+    assert np.array_equal(e_dev, errors)                                       # same operation order as numpy
+    assert rmed == np.sqrt(np.median(errors)) and rms == pytest.approx(np.sqrt(np.mean(errors)), rel=1e-12)
+    hs.robustness_thresh_max = hs.robustness_thresh_min = float(np.percentile(errors, 80))
+    try:
+        fp, fn = hs.robustness_stat_3D(X, x, st)
+        est = st > 0
+        assert fp == np.mean(~(errors <= hs.robustness_thresh_max) & est) and fn == np.mean((errors <= hs.robustness_thresh_min) & ~est)
+        assert fp > 0 and fn > 0
+        # device-resident route gives the same numbers
+        dx, dst = tc.iterative_ls(tc.to_device(u1), P1, tc.to_device(u2), P2)
+        fp2, fn2 = hs.robustness_stat_3D(tc.to_device(X), dx, dst)
+        assert (fp2, fn2) == (fp, fn)
+    finally:
+        hs.robustness_thresh_max = hs.robustness_thresh_min = 1.0
+
+
+def test_golden_cells_device_resident(tri, golden_dir):
+    """Cells of the reference's golden test_1and2.mat with everything after the RNG on the GPU: cv2.undistortPoints
+    (k1 = 0.3), the three solvers, the 3-D / 2-D error evaluation, medians and robustness ratios."""
+    import harness_stats as hs
+    import triangl_cuda as tc
+    with open(os.path.join(golden_dir, "golden_cells.json")) as f:
+        g = json.load(f)["test_1and2"]
+    points_3D = rig.finite_3D_points(4)
+    for cell in g["cells"]:
+        if cell["traj"] == 1 or cell["pose"] not in (20, 39):
+            continue
+        tr = g["trajectories"][cell["traj"]]
+        pose = (tr["sideways_values"][cell["pose"]], tr["towards_values"][cell["pose"]], tr["angle_values"][cell["pose"]])
+        cam1, cam2 = rig.Camera(), rig.Camera()
+        cam1.camera_pose(40.); cam2.camera_pose(40., *pose)
+        cams = []
+        for cam, ang, side, tow in ((cam1, 0., 0., 0.), (cam2, pose[2], pose[0], pose[1])):
+            cam.camera_intrinsics((640, 480), 0.3)
+            cam.project_points(points_3D)
+            cams.append(dict(K=cam.K, dist=cam.dist_coeffs, rvec=np.array([0., ang, 0.]), tvec=cam.P[:, 3].copy(),
+                             points_2D_exact=cam.points_2D_exact))
+        solvers = [lambda a, b: tc.linear_eigen(a, cam1.P, b, cam2.P, rows=6), lambda a, b: tc.linear_ls(a, cam1.P, b, cam2.P),
+                   lambda a, b: tc.iterative_ls(a, cam1.P, b, cam2.P)]
+        acc = [hs.CellStatistics(points_3D, cams, g["num_trials"]) for _ in solvers]
+        np.random.seed(g["rseed"])
+        for _ in range(g["num_trials"]):
+            cam1.apply_noise(0.8, True); cam2.apply_noise(0.8, True)
+            d1 = tc.undistort_points(tc.to_device(cam1.points_2D), cam1.K, cam1.dist_coeffs)
+            d2 = tc.undistort_points(tc.to_device(cam2.points_2D), cam2.K, cam2.dist_coeffs)
+            for a, solve in zip(acc, solvers):
+                x, st = solve(d1, d2)
+                a.add_trial(x, st)
+        keys = ("err3D_mean_summary", "err3D_median_summary", "err2D_mean_summary", "err2D_median_summary",
+                "false_pos_summary", "false_neg_summary")
+        for ti, a in enumerate(acc):
+            for k, got in zip(keys, a.summary()):
+                want = cell[k][ti]
+                if want is not None:
+                    assert got == pytest.approx(want, rel=2e-8, abs=1e-12), (cell["traj"], cell["pose"], k, ti)
