@@ -55,9 +55,11 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="N > 1: all-gather x over NCCL inside the timed step")
-    ap.add_argument("--workload", default="solvers", choices=["solvers", "slam"],
+    ap.add_argument("--workload", default="solvers", choices=["solvers", "slam", "scene"],
                     help="solvers: the four solvers at --points per GPU (default, BASELINE configs[1]); "
-                         "slam: keyframe map-extension latency at SLAM-sized batches (BASELINE configs[4])")
+                         "slam: keyframe map-extension latency at SLAM-sized batches (BASELINE configs[4]); "
+                         "scene: 8 cameras pairwise (28 pairs), --points correspondences per GPU sharded by range over "
+                         "the ranks, optional NCCL gather of x (BASELINE configs[3])")
     return ap.parse_args()
 
 
@@ -432,10 +434,128 @@ def run_slam(args):
     print(json.dumps(out))
 
 
+# ---- multi-quadrotor scene: 8 cameras pairwise, correspondences sharded over the ranks (BASELINE.json configs[3]) ---
+def run_scene(args, rank, world, local_rank):
+    """
+    8 poses on the trajectory-4/5 circle, all 28 camera pairs, an equal share of the correspondences per pair
+    (sharding.pair_segments).  The concatenated correspondence array is sharded by contiguous range: rank r owns
+    [r*P, (r+1)*P) of the world*P points and launches one solver call per pair segment that intersects its range, with
+    that pair's camera matrices (every rank holds all 8 matrices, broadcast from rank 0).  With --gather every rank
+    all-gathers x over NCCL/NVLink inside the timed step.  One step = the four solvers over the rank's range.
+    """
+    import sharding
+    import triangl_cuda as tc
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    tc.require_device()
+    tc.check(tc.lib().trgl_set_device(local_rank))
+    n = args.points
+    total = n * world
+    cams = sharding.broadcast_cameras(np.stack(rig.circle_cameras(8)), 0, "cuda" if world > 1 else None)
+    segs = sharding.pair_segments(8, total)
+    lo, hi = sharding.shard_range(total, rank, world)
+    mine = sharding.intersect_segments(segs, lo, hi)
+    # observations: one seeded cloud per pair, projected into both cameras of the pair (+ 0.8 px noise), tiled
+    u1 = np.empty((n, 2)); u2 = np.empty((n, 2))
+    for (i, j, off, cnt) in mine:
+        base = min(cnt, 500_000)
+        rng = np.random.RandomState(rig.RSEED + 100 * i + j)
+        X = rig.ball_3D_points(base, 4., rng)
+        obs = []
+        for P in (cams[i], cams[j]):
+            Xc = X.dot(P.T)
+            obs.append(Xc[:, 0:2] / Xc[:, 2:3] + rng.normal(0, 0.8 / 480., (base, 2)))
+        reps = -(-cnt // base)
+        u1[off - lo:off - lo + cnt] = np.tile(obs[0], (reps, 1))[:cnt]
+        u2[off - lo:off - lo + cnt] = np.tile(obs[1], (reps, 1))[:cnt]
+    d_u1, d_u2 = tc.to_device(u1), tc.to_device(u2)
+    del u1, u2
+    gather_buf = None
+    if world > 1 and args.gather:
+        import torch
+        d_x = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+        gather_buf = torch.empty((world * n, 3), dtype=torch.float64, device="cuda")
+    else:
+        d_x = tc.DeviceArray((n, 3), np.float64)
+    d_sb = tc.DeviceArray((n,), np.uint8); d_si = tc.DeviceArray((n,), np.int32)
+
+    def rows(buf, a, cnt, cols):        # device sub-range handed to the C ABI
+        if isinstance(buf, tc.DeviceArray):
+            return buf.view(a * max(cols, 1), (cnt, cols) if cols else (cnt,))
+        return buf[a:a + cnt]            # torch tensor
+
+    def step():
+        for name in SOLVERS:
+            for (i, j, off, cnt) in mine:
+                a = off - lo
+                s1 = rows(d_u1, a, cnt, 2); s2 = rows(d_u2, a, cnt, 2); xs = rows(d_x, a, cnt, 3)
+                if name == "linear_eigen":
+                    tc.linear_eigen(s1, cams[i], s2, cams[j], x=xs, status=rows(d_sb, a, cnt, 0))
+                elif name == "linear_LS":
+                    tc.linear_ls(s1, cams[i], s2, cams[j], x=xs, status=rows(d_sb, a, cnt, 0))
+                elif name == "iterative_LS":
+                    tc.iterative_ls(s1, cams[i], s2, cams[j], x=xs, status=rows(d_si, a, cnt, 0))
+                else:
+                    tc.polynomial(s1, cams[i], s2, cams[j], x=xs, status=rows(d_sb, a, cnt, 0), check_all_nan=False)
+            if gather_buf is not None:
+                dist.all_gather_into_tensor(gather_buf, d_x)
+        tc.synchronize()
+
+    def barrier():
+        tc.synchronize()
+        if dist is not None:
+            dist.barrier()
+        tc.synchronize()
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = tc.launch_count()
+    barrier()
+    e0, e1 = tc.Event(), tc.Event()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_ms(e1)
+    launches = tc.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": 4.0 * total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "multi-quadrotor scene: 8 cameras pairwise (28 pairs), %d correspondences per GPU "
+                                   "(%d total) sharded by contiguous range, all four solvers FP64%s (BASELINE.json configs[3])"
+                                   % (n, total, ", NCCL all-gather of x after each solver" if args.gather else ""),
+                       "points_per_gpu": n, "pairs": 28, "segments_on_rank0": len(mine),
+                       "gather_bytes_per_step": (4 * 24 * total) if args.gather else 0},
+            "gpu_launches": launches, "clocks": clocks}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.workload == "slam":
         return run_slam(args)
+    if args.workload == "scene":
+        return run_scene(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+                         int(os.environ.get("LOCAL_RANK", "0")))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
