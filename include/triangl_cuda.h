@@ -194,9 +194,10 @@ int trgl_median(const double* values, int64_t n, int mem, double* median, void* 
 /* ---- bench / diagnostics ---- */
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t trgl_launch_count(void);
-/* Tuning knob: input path of linear_LS.  -1 = auto (default), 0 = per-thread vector loads; 1..6 = cp.async.bulk (TMA
- * engine) shared-memory ring with (points per thread, stages) = (2,4) (4,3) (1,6) (2,6) (4,4) (1,8).  Returns the
- * previous value. */
+/* Tuning knob: input path of linear_LS.  -1 = auto (default: 0 for float64 arithmetic, 8 for TRGL_F32), 0 = per-thread
+ * vector loads; 1..6 = cp.async.bulk (TMA engine) shared-memory ring with (points per thread, stages) = (2,4) (4,3) (1,6)
+ * (2,6) (4,4) (1,8); 7..12 = per-thread cp.async (LDGSTS) ring with (points per thread, stages, min CTAs/SM) = (1,8,2)
+ * (2,4,2) (4,2,2) (4,3,2) (2,4,3) (2,6,2).  Measured on B200 in profiles/.  Returns the previous value. */
 int trgl_set_stream_variant(int variant);
 /* Tuning knob: points per thread of the per-thread-load linear_LS kernel (1, 2 or 4, default 4); returns the previous value. */
 int trgl_set_points_per_thread(int ppt);

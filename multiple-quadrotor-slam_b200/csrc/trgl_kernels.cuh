@@ -45,6 +45,69 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
     }
 }
 
+// ---- linear_LS, per-thread cp.async ring ---------------------------------------------------------------------------
+// Persistent CTAs; every thread keeps DEPTH of its own future (x,y) pairs in flight with cp.async (LDGSTS) into its
+// private shared-memory slots, one commit group per tile.  No block barrier anywhere (a thread only reads what it
+// copied), no registers spent on lookahead, and the bytes in flight per SM are DEPTH x 8 KB x resident CTAs regardless
+// of where the warps are in their solve.
+template <typename TI, typename TC, typename TO, int PPT, int DEPTH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_linear_ls_ring(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
+                 TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n) {
+    constexpr int TILE = kThreads * PPT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TI* ring = reinterpret_cast<TI*>(smem_raw);                                   // [DEPTH][2 views][TILE*2]
+    TO* stage = reinterpret_cast<TO*>(smem_raw + static_cast<size_t>(DEPTH) * 2 * TILE * 2 * sizeof(TI));
+    const int warp = threadIdx.x >> 5;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * TILE;
+    int64_t tile = static_cast<int64_t>(blockIdx.x) * TILE;
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const int j = p * kThreads + threadIdx.x;
+            const int64_t i = tile + d * stride + j;
+            if (i < n) {
+                cp_async_pair(ring + ((d * 2 + 0) * TILE + j) * 2, u1 + 2 * i);
+                cp_async_pair(ring + ((d * 2 + 1) * TILE + j) * 2, u2 + 2 * i);
+            }
+        }
+        cp_async_commit();
+    }
+    int slot = 0;
+    for (; tile < n; tile += stride) {
+        cp_async_wait_group<DEPTH - 1>();                                        // the oldest group has landed
+        TC in[PPT][4];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const int j = p * kThreads + threadIdx.x;
+            const int64_t i = tile + j;
+            TI* s1 = ring + ((slot * 2 + 0) * TILE + j) * 2;
+            TI* s2 = ring + ((slot * 2 + 1) * TILE + j) * 2;
+            in[p][0] = in[p][1] = in[p][2] = in[p][3] = TC(0);
+            if (i < n) {
+                in[p][0] = static_cast<TC>(s1[0]); in[p][1] = static_cast<TC>(s1[1]);
+                in[p][2] = static_cast<TC>(s2[0]); in[p][3] = static_cast<TC>(s2[1]);
+            }
+            const int64_t inext = i + DEPTH * stride;                            // refill the slot just consumed
+            if (inext < n) { cp_async_pair(s1, u1 + 2 * inext); cp_async_pair(s2, u2 + 2 * inext); }
+        }
+        cp_async_commit();
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const int64_t i = tile + p * kThreads + threadIdx.x;
+            TC xs[3];
+            if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs))
+                solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
+            store_x_warp<TO>(x, tile + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+                             static_cast<TO>(xs[2]), stage + warp * 96);
+            if (i < n) status[i] = 1;
+        }
+        if (++slot == DEPTH) slot = 0;
+    }
+    cp_async_wait_all();
+}
+
 // ---- linear_LS, bulk-async pipelined variant ------------------------------------------------------------------------
 // Persistent CTAs; tile = kThreads*PPT correspondences; ring of STAGES shared-memory stages filled by cp.async.bulk.
 // Dynamic shared memory layout: [STAGES][2][TILE*2] TI  |  kWarps*96 TO (store staging)  |  STAGES mbarriers.

@@ -121,6 +121,23 @@ unsigned persistent_grid(K kern, int64_t n, size_t dyn_smem = 0) {
     return static_cast<unsigned>(tiles < full ? tiles : full);
 }
 
+template <typename TI, typename TC, typename TO, int PPT, int DEPTH, int MINB>
+int launch_ls_ring(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n, cudaStream_t s) {
+    const size_t smem = size_t(DEPTH) * 2 * kThreads * PPT * 2 * sizeof(TI) + kWarps * 96 * sizeof(TO);
+    auto kern = k_linear_ls_ring<TI, TC, TO, PPT, DEPTH, MINB>;
+    static thread_local std::unordered_map<const void*, int> per_sm_cache;
+    int& per_sm = per_sm_cache[reinterpret_cast<const void*>(kern)];
+    if (per_sm == 0) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (g_sm_count == 0) { int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)); }
+    }
+    const int64_t tiles = (n + kThreads * PPT - 1) / (kThreads * PPT);
+    const int64_t full = static_cast<int64_t>(g_sm_count) * per_sm;
+    kern<<<static_cast<unsigned>(tiles < full ? tiles : full), kThreads, smem, s>>>(a, b, cams, xo, status, n);
+    return TRGL_OK;
+}
+
 template <typename TI, typename TC, typename TO>
 void launch_ls_direct(int ppt, const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n,
                       cudaStream_t s, const Undist2* pre) {
@@ -143,10 +160,13 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
     // auto: per-thread vector loads with 4 points in flight.  Measured on B200 (profiles/r01b_sweep_100M.jsonl): 0.84 of
     // the measured copy peak at 100 M points vs 0.74 for the bulk-async pipeline (variants 1-6, kept selectable), and
     // 0.82 at 10 M points.
-    if (variant < 0) variant = 0;
+    // FP32 arithmetic mode: the per-thread cp.async ring (2 points/thread, 4 stages) is 1.18x faster (0.63 vs 0.54 of the
+    // copy peak at 29 B/point; the kernel is FP32-issue bound there and the ring frees the load registers).
+    if (variant < 0) variant = (mode == TRGL_F32) ? 8 : 0;
     // cp.async.bulk needs 16-byte aligned global addresses; fall back to per-thread loads otherwise
     if ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & 15) variant = 0;
     if (pre) variant = 0;
+    if (variant >= 7 && ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & 7)) variant = 0;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
@@ -159,6 +179,12 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
             case 4: rc = launch_ls_tma<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s); break;
             case 5: rc = launch_ls_tma<TI, TC, TO, 4, 4, 1>(a, b, cams, xo, status, n, s); break;
             case 6: rc = launch_ls_tma<TI, TC, TO, 1, 8, 3>(a, b, cams, xo, status, n, s); break;
+            case 7: rc = launch_ls_ring<TI, TC, TO, 1, 8, 2>(a, b, cams, xo, status, n, s); break;
+            case 8: rc = launch_ls_ring<TI, TC, TO, 2, 4, 2>(a, b, cams, xo, status, n, s); break;
+            case 9: rc = launch_ls_ring<TI, TC, TO, 4, 2, 2>(a, b, cams, xo, status, n, s); break;
+            case 10: rc = launch_ls_ring<TI, TC, TO, 4, 3, 2>(a, b, cams, xo, status, n, s); break;
+            case 11: rc = launch_ls_ring<TI, TC, TO, 2, 4, 3>(a, b, cams, xo, status, n, s); break;
+            case 12: rc = launch_ls_ring<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s); break;
             default: launch_ls_direct<TI, TC, TO>(ppt, a, b, cams, xo, status, n, s, pre);
         }
         if (rc) return rc;
@@ -567,7 +593,7 @@ int trgl_event_elapsed_ms(void* start, void* stop, float* ms) {
 int64_t trgl_launch_count(void) { return g_launches.load(); }
 int trgl_set_stream_variant(int variant) {
     const int old = g_variant.load();
-    if (variant >= -1 && variant <= 6) g_variant.store(variant);
+    if (variant >= -1 && variant <= 12) g_variant.store(variant);
     return old;
 }
 int trgl_set_points_per_thread(int ppt) {

@@ -57,6 +57,12 @@ for mode in args.modes.split(","):
             for _ in range(3):
                 launch()
             tc.synchronize()
+            if solver == "linear_LS":       # every input path must give the same bits as the per-thread-load kernel
+                chk = x.to_host()[:: max(1, n // 200000)]
+                if (variant, ppt) == cfgs[0]:
+                    ref_bits = chk
+                else:
+                    assert np.array_equal(chk, ref_bits, equal_nan=True), "variant %d ppt %d differs from variant 0" % (variant, ppt)
             e = [tc.Event() for _ in range(args.iters + 1)]
             for i in range(args.iters):
                 e[i].record(); launch()
