@@ -37,7 +37,12 @@ METRICS = [
 
 
 def ncu_csv(rep, page):
-    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    """Page of a capture: the CSV exported on the GPU box (<name>.<page>.csv) or, if the report came back, ncu -i."""
+    pre = rep[:-len(".ncu-rep")] + "." + page + ".csv"
+    if os.path.isfile(pre):
+        out = open(pre).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
     lines = [ln for ln in out.splitlines() if ln.startswith('"')]
     return list(csv.reader(io.StringIO("\n".join(lines))))
 
@@ -70,21 +75,20 @@ if os.path.isfile(ll):
         f.write("| kernel | grid | launches | mean us | share of all kernel time |\n|---|---|---|---|---|\n")
         for (k, g), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write("| `%s` | %s | %d | %.1f | %.3f |\n" % (k.replace("void ", ""), g, len(v), sum(v) / len(v) / 1e3, sum(v) / tot))
-        # share within the device-resident step only (largest grid per kernel)
-        f.write("\nDevice-resident 10 M-point launches only (the timed `value` region):\n\n| kernel | mean us | share |\n|---|---|---|\n")
-        big = {}
-        for (k, g), v in agg.items():
-            blocks = int(g.strip("()").split(",")[0])
-            if k not in big or blocks > big[k][0]:
-                big[k] = (blocks, v)
-        nsolv = {k: (len(v[1])) for k, v in big.items()}
-        # pair_reproj runs once per solver per step -> weight by launches per step
-        per_step = {}
-        for k, (blocks, v) in big.items():
-            per_step[k] = sum(v) / len(v) * (4 if "pair_reproj" in k and len(big) < 7 else 1)
-        for k, (blocks, v) in sorted(big.items(), key=lambda kv: -sum(kv[1][1]) / len(kv[1][1])):
-            f.write("| `%s` | %.1f | %.3f |\n" % (k.replace("void ", ""), sum(v) / len(v) / 1e3,
-                                                   sum(v) / len(v) / sum(sum(x[1]) / len(x[1]) for x in big.values())))
+        # share within the device-resident steps only: bench.py runs (warmup + steps) device-resident steps of
+        # 4 solver + 4 reprojection kernels first, the host-mode (e2e) chunks follow
+        n_dev = 8 * 3
+        dev = defaultdict(list)
+        for r in rows[1:1 + n_dev]:
+            v = num(r[vi])
+            if v is not None:
+                dev[r[ki].split("(")[0]].append(v)
+        per_step = {k: sum(v) / 3.0 for k, v in dev.items()}          # time per step (pair_reproj runs 4x per step)
+        tot_step = sum(per_step.values())
+        f.write("\nDevice-resident 10 M-point steps only (the timed `value` region; first %d launches = 3 steps), "
+                "kernel time per step:\n\n| kernel | launches/step | us per step | share of step kernel time |\n|---|---|---|---|\n" % n_dev)
+        for k, v in sorted(per_step.items(), key=lambda kv: -kv[1]):
+            f.write("| `%s` | %.0f | %.1f | %.3f |\n" % (k.replace("void ", ""), len(dev[k]) / 3.0, v / 1e3, v / tot_step))
     print("wrote", tag + "_launches.md")
 
 # ---- full captures ------------------------------------------------------------------------------------------------
@@ -92,7 +96,9 @@ traffic = {}
 with open(os.path.join(dst, tag + "_ncu_full.md"), "w") as f:
     f.write("# `ncu --set full --clock-control none --import-source on` captures (%s)\n\n" % tag)
     f.write("One launch per kernel after warm-up.  Times under the profiler are not bench values.\n")
-    for rep in sorted(glob.glob(os.path.join(src, "full_*.ncu-rep"))):
+    reps = set(glob.glob(os.path.join(src, "full_*.ncu-rep"))) | \
+        {f[:-len(".raw.csv")] + ".ncu-rep" for f in glob.glob(os.path.join(src, "full_*.raw.csv"))}
+    for rep in sorted(reps):
         raw = ncu_csv(rep, "raw")
         if len(raw) < 3:
             continue
