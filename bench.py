@@ -209,6 +209,7 @@ def run_ours(args, rank, world, local_rank):
         gather_buf = torch.empty((world * n, 3), dtype=torch.float64, device="cuda")
 
     ev = [tc.Event() for _ in range(9)]
+    d_sums = tc.DeviceArray((4, 4), np.float64)      # per-solver reprojection sums, finished on the device
 
     def device_step(timed):
         k = 0
@@ -224,14 +225,14 @@ def run_ours(args, rank, world, local_rank):
             else:
                 tc.polynomial(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name], check_all_nan=False)
             ev[k].record(); k += 1
-        for name in SOLVERS:
-            _, _, _, sums = tc.pair_reproj(d_x[name], d_u1, P1, d_u2, P2, d_st[name], 0, np.inf, want_errors=False,
-                                           want_good=False)
-            sums_total += sums[0] + sums[1]
+        for si, name in enumerate(SOLVERS):
+            # asynchronous variant: the grid-level sums are finished inside the kernel, nothing to wait for per solver
+            tc.pair_reproj(d_x[name], d_u1, P1, d_u2, P2, d_st[name], 0, np.inf, want_errors=False, want_good=False,
+                           sums_device=d_sums.view(4 * si, (4,)))
             if gather_buf is not None:
                 dist.all_gather_into_tensor(gather_buf, d_x[name])
         ev[8].record()
-        tc.synchronize()
+        sums_total = float(d_sums.to_host()[:, 0:2].sum())      # the step's result comes back to the host (synchronises)
         if timed is not None:
             for i, name in enumerate(SOLVERS):
                 timed[name].append(ev[2 * i].elapsed_ms(ev[2 * i + 1]))

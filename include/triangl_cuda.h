@@ -25,6 +25,9 @@
  *     (H2D + kernel + D2H, chunked and overlapped; pinned buffers from trgl_host_alloc go at full PCIe speed);
  *     mem = TRGL_MEM_DEVICE: they are device pointers on the current device, the kernel is enqueued on
  *     `stream` (a cudaStream_t, NULL = default stream) and the call returns without synchronising.
+ *   - Re-entrancy: device-mode calls keep no shared mutable state (reduction scratch is owned per device and stream), so
+ *     different host threads may drive different streams concurrently, like the stack-local reference code
+ *     (triangulation.c:67,106); host-mode calls share the staging pipeline and are serialised by an internal mutex.
  *   - There is NO CPU fallback: without a CUDA device every compute entry point returns an error.
  *
  * Precision modes (`mode`):
@@ -47,7 +50,7 @@
 extern "C" {
 #endif
 
-#define TRGL_VERSION 101
+#define TRGL_VERSION 102
 
 enum { TRGL_F64 = 0, TRGL_F32IO = 1, TRGL_F32 = 2, TRGL_F64_OUT32 = 3, TRGL_F32_OUT64 = 4 };
 enum { TRGL_MEM_HOST = 0, TRGL_MEM_DEVICE = 1 };
@@ -117,6 +120,15 @@ int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const do
  * reductions of the moments and of the 9x9 normal matrix, tiny eigen-solve on the host.  F: 9 doubles out (host).
  * Only the element type of u is taken from `mode`.  Synchronises. */
 int trgl_fundamental_8point(const void* u1, const void* u2, int64_t n, int mode, int mem, double* F, void* stream);
+
+/* Asynchronous variant for device-resident pipelines: same kernel, but the grid-level sum is finished inside the kernel
+ * (last-block reduction in block order, so the four sums are bit-identical to the synchronous variant) and written to
+ * sums_device (4 doubles in DEVICE memory).  Nothing is copied back and the stream is not synchronised: the call only
+ * enqueues, and the result is owned by whatever the caller enqueues next on `stream`.  Device buffers only. */
+int trgl_pair_reproj_async(const void* x, const void* u1, const void* u2, const double* P1, const double* P2,
+                           const void* status, int status_is_i32, int min_status, double max_sq_err,
+                           void* err1, void* err2, uint8_t* good, double* sums_device,
+                           int64_t n, int mode, void* stream);
 
 /* ---- input normalisation in front of the solvers ---- */
 

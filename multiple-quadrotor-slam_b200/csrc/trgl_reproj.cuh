@@ -61,6 +61,29 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __re
     }
 }
 
+// Same, followed by the grid-level sum inside the kernel when `final_out` is given: the last CTA to arrive (ticket on
+// `counter`, which it resets for the next launch) adds the per-block partials in block order -- the order the host uses --
+// and writes NV doubles to device memory, so the caller needs no synchronisation to own the result in stream order.
+template <int NV>
+__device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], double* __restrict__ partials,
+                                                      unsigned int* __restrict__ counter, double* __restrict__ final_out) {
+    block_reduce_store<NV>(v, partials);
+    if (final_out == nullptr) return;
+    __shared__ bool is_last;
+    __threadfence();                                   // the partials of this CTA are visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);     // ... before its ticket is
+    __syncthreads();
+    if (is_last) {
+        if (threadIdx.x < NV) {
+            double s = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[b * NV + threadIdx.x]);
+            final_out[threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
 template <typename TX, typename TP>
 __global__ void __launch_bounds__(kThreads)
 k_reproj_error(const TX* __restrict__ x, const TP* __restrict__ imgp, const __grid_constant__ ProjParams pp, TP* __restrict__ proj,
@@ -97,7 +120,8 @@ template <typename TI, typename TO, typename TS>
 __global__ void __launch_bounds__(kThreads)
 k_pair_reproj(const TO* __restrict__ x, const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<double> cams,
               const TS* __restrict__ status, const int min_status, const double max_sq_err, TO* __restrict__ err1,
-              TO* __restrict__ err2, uint8_t* __restrict__ good, double* __restrict__ partials, const int64_t n) {
+              TO* __restrict__ err2, uint8_t* __restrict__ good, double* __restrict__ partials, const int64_t n,
+              unsigned int* __restrict__ counter, double* __restrict__ final_out) {
     double acc[4] = {0, 0, 0, 0};             // sum err1 (good), sum err2 (good), #good, #status > min_status
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * kThreads) {
@@ -126,7 +150,7 @@ k_pair_reproj(const TO* __restrict__ x, const TI* __restrict__ u1, const TI* __r
         if (g) { acc[0] += e[0]; acc[1] += e[1]; acc[2] += 1.0; }
         if (st_ok) acc[3] += 1.0;
     }
-    block_reduce_store<4>(acc, partials);
+    block_reduce_finalize<4>(acc, partials, counter, final_out);
 }
 
 // ---- harness statistics on the device (triangulation_comparison.py:179-188, 205-217, 242-260) ---------------------

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -280,10 +281,41 @@ struct Slot {
 };
 std::mutex g_pipe_mutex;
 Slot g_slots[kSlots];
-unsigned int* g_flags = nullptr;      // 2 words per slot for the polynomial all-NaN test
-double* g_partials = nullptr;         // reduction scratch
-size_t g_partials_cap = 0;
-int g_scratch_device = -1;
+std::mutex g_host_mutex;              // host-mode calls that keep state across host_pipeline (polynomial flags)
+
+// Reduction scratch (per-block partial sums, the polynomial NaN flags, the last-block ticket) is owned per
+// (device, stream): calls enqueued on one stream reuse it in stream order, calls on different streams never share it,
+// so the entry points are re-entrant per stream like the reference's stack-local C code (triangulation.c:67,106).
+struct Scratch {
+    double* partials = nullptr;       // kPartialDoubles
+    unsigned int* flags = nullptr;    // 2 words per pipeline slot + 2 for device-mode calls (polynomial all-NaN test)
+    unsigned int* counter = nullptr;  // ticket of the in-kernel final reduction (self-resetting)
+};
+constexpr size_t kPartialDoubles = static_cast<size_t>(kReduceBlocks) * 48;
+constexpr int kFlagWords = 2 * (kSlots + 1);
+std::mutex g_scratch_mutex;
+std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
+
+int scratch_for(cudaStream_t s, Scratch& out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    Scratch& sc = g_scratch[std::make_pair(dev, s)];
+    if (!sc.partials) {
+        if (cudaMalloc(&sc.partials, kPartialDoubles * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TRGL_E_NOMEM, "cudaMalloc of reduction scratch failed");
+        }
+        if (cudaMalloc(&sc.flags, sizeof(unsigned int) * (kFlagWords + 2)) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(sc.partials); sc.partials = nullptr;
+            return fail(TRGL_E_NOMEM, "cudaMalloc of reduction scratch failed");
+        }
+        CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * (kFlagWords + 2)));
+        sc.counter = sc.flags + kFlagWords;
+    }
+    out = sc;
+    return TRGL_OK;
+}
 
 int ensure_slot(Slot& sl, size_t bytes) {
     int dev = 0;
@@ -299,23 +331,6 @@ int ensure_slot(Slot& sl, size_t bytes) {
         size_t want = bytes + bytes / 8 + 4096;
         if (cudaMalloc(&sl.buf, want) != cudaSuccess) return fail(TRGL_E_NOMEM, "cudaMalloc of pipeline scratch failed");
         sl.cap = want;
-    }
-    return TRGL_OK;
-}
-
-int ensure_scratch(size_t partial_doubles) {
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    if (g_scratch_device != dev) {
-        if (g_flags) cudaFree(g_flags);
-        if (g_partials) cudaFree(g_partials);
-        g_flags = nullptr; g_partials = nullptr; g_partials_cap = 0; g_scratch_device = dev;
-    }
-    if (!g_flags) CK(cudaMalloc(&g_flags, sizeof(unsigned int) * 2 * (kSlots + 1)));
-    if (g_partials_cap < partial_doubles) {
-        if (g_partials) CK(cudaFree(g_partials));
-        CK(cudaMalloc(&g_partials, partial_doubles * sizeof(double)));
-        g_partials_cap = partial_doubles;
     }
     return TRGL_OK;
 }
@@ -696,12 +711,10 @@ static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, c
     unsigned int hflags[2 * (kSlots + 1)] = {0};
     if (mem == TRGL_MEM_DEVICE) {
         cudaStream_t s = static_cast<cudaStream_t>(stream);
-        {
-            std::lock_guard<std::mutex> lock(g_pipe_mutex);
-            rc = ensure_scratch(0);
-            if (rc) return rc;
-        }
-        unsigned int* fl = g_flags + 2 * kSlots;
+        Scratch sc;
+        rc = scratch_for(s, sc);
+        if (rc) return rc;
+        unsigned int* fl = sc.flags + 2 * kSlots;
         CK(cudaMemsetAsync(fl, 0, 2 * sizeof(unsigned int), s));
         rc = launch_polynomial(u1, u2, P1, P2, hs, x, status, u1_corr, u2_corr, fl, n, max_coordinate_value, rows, mode, s, pre);
         if (rc) return rc;
@@ -712,22 +725,21 @@ static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, c
         }
         return TRGL_OK;
     }
-    {
-        std::lock_guard<std::mutex> lock(g_pipe_mutex);
-        rc = ensure_scratch(0);
-        if (rc) return rc;
-        CK(cudaMemset(g_flags, 0, sizeof(unsigned int) * 2 * (kSlots + 1)));
-    }
+    std::lock_guard<std::mutex> host_lock(g_host_mutex);          // the slot flags live across host_pipeline
+    Scratch sc;
+    rc = scratch_for(nullptr, sc);
+    if (rc) return rc;
+    CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * 2 * kSlots));
     HostArray arr[6] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1},
                         {nullptr, u1_corr, size_t(2 * mi.in_bytes)}, {nullptr, u2_corr, size_t(2 * mi.in_bytes)}};
     rc = host_pipeline(arr, 6, n, [&](void** d, int64_t m, cudaStream_t s, int slot) {
         return launch_polynomial(d[0], d[1], P1, P2, hs, d[2], static_cast<uint8_t*>(d[3]), u1_corr ? d[4] : nullptr,
-                                 u2_corr ? d[5] : nullptr, g_flags + 2 * slot, m, max_coordinate_value, rows, mode, s, pre);
+                                 u2_corr ? d[5] : nullptr, sc.flags + 2 * slot, m, max_coordinate_value, rows, mode, s, pre);
     });
     if (rc) return rc;
     if (all_nan) {
-        CK(cudaMemcpy(hflags, g_flags, sizeof(unsigned int) * 2 * kSlots, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hflags, sc.flags, sizeof(unsigned int) * 2 * kSlots, cudaMemcpyDeviceToHost));
         unsigned a = 0, b = 0;
         for (int s = 0; s < kSlots; ++s) { a |= hflags[2 * s]; b |= hflags[2 * s + 1]; }
         *all_nan = (a == 0 || b == 0) ? 1 : 0;
@@ -801,9 +813,9 @@ int trgl_fundamental_8point(const void* u1, const void* u2, int64_t n, int mode,
     if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
     if (!F || n < 8 || !u1 || !u2) return fail(TRGL_E_BADARG, "need F and at least 8 matches");
     if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
-    std::lock_guard<std::mutex> lock(g_pipe_mutex);
-    int rc = ensure_scratch(kReduceBlocks * 48);
-    if (rc) return rc;
+    std::unique_lock<std::mutex> lock(g_pipe_mutex, std::defer_lock);
+    if (mem == TRGL_MEM_HOST) lock.lock();                  // the pipeline slots are shared by host-mode calls
+    int rc;
     const size_t ub = 2 * mi.in_bytes;
     const int64_t chunk = (mem == TRGL_MEM_HOST) ? (n < kChunk ? n : kChunk) : n;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -813,6 +825,9 @@ int trgl_fundamental_8point(const void* u1, const void* u2, int64_t n, int mode,
         if (rc) return rc;
         s = g_slots[0].stream; d1 = g_slots[0].buf; d2 = d1 + align256(ub * chunk);
     }
+    Scratch sc;
+    rc = scratch_for(s, sc);
+    if (rc) return rc;
     static thread_local double hpart[kReduceBlocks * 45];
     F8Params fp = {{0, 0}, {0, 0}, 1, 1};
     double acc[45];
@@ -827,13 +842,13 @@ int trgl_fundamental_8point(const void* u1, const void* u2, int64_t n, int mode,
                 CK(cudaMemcpyAsync(d2, b, ub * m, cudaMemcpyHostToDevice, s));
                 a = d1; b = d2;
             }
-#define F8_LAUNCH(TI, ST) k_f8_reduce<TI, ST><<<kReduceBlocks, kThreads, 0, s>>>(static_cast<const TI*>(a), static_cast<const TI*>(b), fp, g_partials, m)
+#define F8_LAUNCH(TI, ST) k_f8_reduce<TI, ST><<<kReduceBlocks, kThreads, 0, s>>>(static_cast<const TI*>(a), static_cast<const TI*>(b), fp, sc.partials, m)
             if (mi.in_bytes == 8) { if (stage == 0) F8_LAUNCH(double, 0); else if (stage == 1) F8_LAUNCH(double, 1); else F8_LAUNCH(double, 2); }
             else { if (stage == 0) F8_LAUNCH(float, 0); else if (stage == 1) F8_LAUNCH(float, 1); else F8_LAUNCH(float, 2); }
 #undef F8_LAUNCH
             g_launches++;
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(hpart, g_partials, sizeof(double) * kReduceBlocks * nv, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(hpart, sc.partials, sizeof(double) * kReduceBlocks * nv, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             for (int b2 = 0; b2 < kReduceBlocks; ++b2)
                 for (int k = 0; k < nv; ++k) acc[k] += hpart[b2 * nv + k];
@@ -890,7 +905,10 @@ int trgl_reproj_error(const void* x, const void* imgp, const double* K, const do
     const size_t xb = x_is_f32 ? 4 : 8, ib = img_is_f32 ? 4 : 8;
     double acc[5] = {0, 0, 0, 0, 0};
     auto run = [&](const void* dx, const void* di, void* dp, int64_t m, cudaStream_t s) -> int {
-        double* part = g_partials;
+        Scratch sc;
+        int rcs = scratch_for(s, sc);
+        if (rcs) return rcs;
+        double* part = sc.partials;
         const int blocks = kReduceBlocks;
         if (x_is_f32) {
             if (img_is_f32) k_reproj_error<float, float><<<blocks, kThreads, 0, s>>>(static_cast<const float*>(dx), static_cast<const float*>(di), pp, static_cast<float*>(dp), part, m);
@@ -909,11 +927,6 @@ int trgl_reproj_error(const void* x, const void* imgp, const double* K, const do
         return TRGL_OK;
     };
     int rc;
-    {
-        std::lock_guard<std::mutex> lock(g_pipe_mutex);
-        rc = ensure_scratch(kReduceBlocks * 8);
-        if (rc) return rc;
-    }
     if (mem == TRGL_MEM_DEVICE) {
         rc = run(x, imgp, proj, n, static_cast<cudaStream_t>(stream));
         if (rc) return rc;
@@ -942,28 +955,35 @@ int trgl_reproj_error(const void* x, const void* imgp, const double* K, const do
     return TRGL_OK;
 }
 
-int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double* P1, const double* P2,
-                     const void* status, int status_is_i32, int min_status, double max_sq_err, void* err1, void* err2,
-                     uint8_t* good, double* sums, int64_t n, int mode, int mem, void* stream) {
+static int impl_pair_reproj(const void* x, const void* u1, const void* u2, const double* P1, const double* P2,
+                            const void* status, int status_is_i32, int min_status, double max_sq_err, void* err1, void* err2,
+                            uint8_t* good, double* sums, double* sums_dev, int64_t n, int mode, int mem, void* stream) {
     ModeInfo mi;
     if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
     if (!mode_info(mode, mi)) return fail(TRGL_E_BADARG, "unknown precision mode");
     if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
-    if (!P1 || !P2 || !sums) return fail(TRGL_E_BADARG, "NULL parameter pointer");
+    if (!P1 || !P2 || (!sums && !sums_dev)) return fail(TRGL_E_BADARG, "NULL parameter pointer");
+    if (sums_dev && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "the asynchronous variant needs device buffers");
     if (n > 0 && (!x || !u1 || !u2 || !status)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
     if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
-    sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
-    if (n == 0) return TRGL_OK;
+    if (sums) sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+    if (n == 0) {
+        if (sums_dev) CK(cudaMemsetAsync(sums_dev, 0, 4 * sizeof(double), static_cast<cudaStream_t>(stream)));
+        return TRGL_OK;
+    }
     double acc[4] = {0, 0, 0, 0};
     const Cams<double> cams = make_cams<double>(P1, P2);
     auto run = [&](const void* dx, const void* d1, const void* d2, const void* dst, void* de1, void* de2, uint8_t* dg,
                    int64_t m, cudaStream_t s) -> int {
         const int blocks = kReduceBlocks;
+        Scratch sc;
+        int rcs = scratch_for(s, sc);
+        if (rcs) return rcs;
 #define PAIR_LAUNCH(TI, TO)                                                                                      \
         if (status_is_i32)                                                                                       \
-            k_pair_reproj<TI, TO, int32_t><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(dx), static_cast<const TI*>(d1), static_cast<const TI*>(d2), cams, static_cast<const int32_t*>(dst), min_status, max_sq_err, static_cast<TO*>(de1), static_cast<TO*>(de2), dg, g_partials, m); \
+            k_pair_reproj<TI, TO, int32_t><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(dx), static_cast<const TI*>(d1), static_cast<const TI*>(d2), cams, static_cast<const int32_t*>(dst), min_status, max_sq_err, static_cast<TO*>(de1), static_cast<TO*>(de2), dg, sc.partials, m, sc.counter, sums_dev); \
         else                                                                                                     \
-            k_pair_reproj<TI, TO, uint8_t><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(dx), static_cast<const TI*>(d1), static_cast<const TI*>(d2), cams, static_cast<const uint8_t*>(dst), min_status, max_sq_err, static_cast<TO*>(de1), static_cast<TO*>(de2), dg, g_partials, m);
+            k_pair_reproj<TI, TO, uint8_t><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(dx), static_cast<const TI*>(d1), static_cast<const TI*>(d2), cams, static_cast<const uint8_t*>(dst), min_status, max_sq_err, static_cast<TO*>(de1), static_cast<TO*>(de2), dg, sc.partials, m, sc.counter, sums_dev);
         if (mi.in_bytes == 8 && mi.out_bytes == 8) { PAIR_LAUNCH(double, double) }
         else if (mi.in_bytes == 4 && mi.out_bytes == 4) { PAIR_LAUNCH(float, float) }
         else if (mi.in_bytes == 8 && mi.out_bytes == 4) { PAIR_LAUNCH(double, float) }
@@ -971,19 +991,15 @@ int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double
 #undef PAIR_LAUNCH
         g_launches++;
         CK(cudaGetLastError());
+        if (sums_dev) return TRGL_OK;                  // asynchronous variant: the result stays on the device
         static thread_local double hpart[kReduceBlocks * 4];
-        CK(cudaMemcpyAsync(hpart, g_partials, sizeof(double) * blocks * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hpart, sc.partials, sizeof(double) * blocks * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         for (int b = 0; b < blocks; ++b)
             for (int k = 0; k < 4; ++k) acc[k] += hpart[b * 4 + k];
         return TRGL_OK;
     };
     int rc;
-    {
-        std::lock_guard<std::mutex> lock(g_pipe_mutex);
-        rc = ensure_scratch(kReduceBlocks * 8);
-        if (rc) return rc;
-    }
     if (mem == TRGL_MEM_DEVICE) {
         rc = run(x, u1, u2, status, err1, err2, good, n, static_cast<cudaStream_t>(stream));
         if (rc) return rc;
@@ -1012,8 +1028,25 @@ int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double
         }
         CK(cudaStreamSynchronize(sl.stream));
     }
-    for (int k = 0; k < 4; ++k) sums[k] = acc[k];
+    if (sums)
+        for (int k = 0; k < 4; ++k) sums[k] = acc[k];
     return TRGL_OK;
+}
+
+int trgl_pair_reproj(const void* x, const void* u1, const void* u2, const double* P1, const double* P2,
+                     const void* status, int status_is_i32, int min_status, double max_sq_err, void* err1, void* err2,
+                     uint8_t* good, double* sums, int64_t n, int mode, int mem, void* stream) {
+    if (!sums) return fail(TRGL_E_BADARG, "NULL parameter pointer");
+    return impl_pair_reproj(x, u1, u2, P1, P2, status, status_is_i32, min_status, max_sq_err, err1, err2, good, sums, nullptr,
+                            n, mode, mem, stream);
+}
+
+int trgl_pair_reproj_async(const void* x, const void* u1, const void* u2, const double* P1, const double* P2,
+                           const void* status, int status_is_i32, int min_status, double max_sq_err, void* err1, void* err2,
+                           uint8_t* good, double* sums_device, int64_t n, int mode, void* stream) {
+    if (!sums_device) return fail(TRGL_E_BADARG, "NULL parameter pointer");
+    return impl_pair_reproj(x, u1, u2, P1, P2, status, status_is_i32, min_status, max_sq_err, err1, err2, good, nullptr,
+                            sums_device, n, mode, TRGL_MEM_DEVICE, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1030,9 +1063,9 @@ static int eval_errors_common(bool three_d, const void* a, const double* exact, 
     if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
     stats[0] = stats[1] = stats[2] = stats[3] = 0.0;
     if (n == 0) return TRGL_OK;
-    std::lock_guard<std::mutex> lock(g_pipe_mutex);
-    int rc = ensure_scratch(kReduceBlocks * 8);
-    if (rc) return rc;
+    std::unique_lock<std::mutex> lock(g_pipe_mutex, std::defer_lock);
+    if (mem == TRGL_MEM_HOST) lock.lock();
+    int rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t ab = (a_is_f32 ? 4 : 8) * (three_d ? 3 : 2), eb = 8 * (three_d ? exact_stride : 2), sb = status_is_i32 ? 4 : 1;
     const void* da = a; const double* de = exact; const void* dst = status; double* derr = errors;
@@ -1048,20 +1081,23 @@ static int eval_errors_common(bool three_d, const void* a, const double* exact, 
         da = sl.buf + oa; de = reinterpret_cast<const double*>(sl.buf + oe); dst = status ? sl.buf + os : nullptr;
         derr = errors ? reinterpret_cast<double*>(sl.buf + oerr) : nullptr;
     }
+    Scratch sc;
+    rc = scratch_for(s, sc);
+    if (rc) return rc;
     const int blocks = kReduceBlocks;
     if (three_d) {
-#define E3(TO, TS) k_sq_errors_3d<TO, TS><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(da), de, exact_stride, static_cast<const TS*>(dst), thresh_max, thresh_min, derr, g_partials, n)
+#define E3(TO, TS) k_sq_errors_3d<TO, TS><<<blocks, kThreads, 0, s>>>(static_cast<const TO*>(da), de, exact_stride, static_cast<const TS*>(dst), thresh_max, thresh_min, derr, sc.partials, n)
         if (a_is_f32) { if (status_is_i32) E3(float, int32_t); else E3(float, uint8_t); }
         else { if (status_is_i32) E3(double, int32_t); else E3(double, uint8_t); }
 #undef E3
     } else {
-        if (a_is_f32) k_sq_errors_2d<float><<<blocks, kThreads, 0, s>>>(static_cast<const float*>(da), de, derr, g_partials, n);
-        else k_sq_errors_2d<double><<<blocks, kThreads, 0, s>>>(static_cast<const double*>(da), de, derr, g_partials, n);
+        if (a_is_f32) k_sq_errors_2d<float><<<blocks, kThreads, 0, s>>>(static_cast<const float*>(da), de, derr, sc.partials, n);
+        else k_sq_errors_2d<double><<<blocks, kThreads, 0, s>>>(static_cast<const double*>(da), de, derr, sc.partials, n);
     }
     g_launches++;
     CK(cudaGetLastError());
     static thread_local double hpart[kReduceBlocks * 4];
-    CK(cudaMemcpyAsync(hpart, g_partials, sizeof(double) * blocks * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hpart, sc.partials, sizeof(double) * blocks * 4, cudaMemcpyDeviceToHost, s));
     if (mem == TRGL_MEM_HOST && errors) CK(cudaMemcpyAsync(errors, derr, 8 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (int b = 0; b < blocks; ++b)
@@ -1088,9 +1124,9 @@ int trgl_median(const double* values, int64_t n, int mem, double* median, void* 
     if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
     *median = std::nan("");
     if (n == 0) return TRGL_OK;                       // np.median of an empty array is NaN
-    std::lock_guard<std::mutex> lock(g_pipe_mutex);
-    int rc = ensure_scratch(kReduceBlocks * 8);       // g_partials doubles as the 256-bin histogram (2048 bytes)
-    if (rc) return rc;
+    std::unique_lock<std::mutex> lock(g_pipe_mutex, std::defer_lock);
+    if (mem == TRGL_MEM_HOST) lock.lock();
+    int rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const double* dv = values;
     if (mem == TRGL_MEM_HOST) {
@@ -1100,7 +1136,10 @@ int trgl_median(const double* values, int64_t n, int mem, double* median, void* 
         CK(cudaMemcpyAsync(g_slots[0].buf, values, 8 * n, cudaMemcpyHostToDevice, s));
         dv = reinterpret_cast<const double*>(g_slots[0].buf);
     }
-    unsigned long long* dh = reinterpret_cast<unsigned long long*>(g_partials);
+    Scratch sc;
+    rc = scratch_for(s, sc);
+    if (rc) return rc;
+    unsigned long long* dh = reinterpret_cast<unsigned long long*>(sc.partials);   // the partials block doubles as the histogram
     const int64_t tiles = (n + kThreads - 1) / kThreads;
     const unsigned blocks = static_cast<unsigned>(tiles < kReduceBlocks ? tiles : kReduceBlocks);
     unsigned long long hist[257];

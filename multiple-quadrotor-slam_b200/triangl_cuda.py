@@ -31,7 +31,7 @@ EXPORTS = [
     "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
     "trgl_set_points_per_thread", "trgl_set_stream_variant",
-    "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median",
+    "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -81,6 +81,7 @@ def lib():
     L.trgl_fundamental_8point.argtypes = [vp, vp, i64, cint, cint, dp, vp]
     L.trgl_reproj_error.argtypes = [vp, vp, dp, dp, dp, dp, vp, dp, dp, i64, cint, cint, cint, vp]
     L.trgl_pair_reproj.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, dp, i64, cint, cint, vp]
+    L.trgl_pair_reproj_async.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, vp, i64, cint, vp]
     L.trgl_eval_errors_3d.argtypes = [vp, vp, cint, vp, cint, dbl, dbl, vp, dp, i64, cint, cint, vp]
     L.trgl_eval_errors_2d.argtypes = [vp, vp, vp, dp, i64, cint, cint, vp]
     L.trgl_median.argtypes = [vp, i64, cint, dp, vp]
@@ -473,8 +474,10 @@ def reproj_error(x, imgp, K, dist, rvec, tvec, want_proj=True, stream=None):
 
 
 def pair_reproj(x, u1, P1, u2, P2, status, min_status=0, max_sq_err=np.inf, want_errors=True, want_good=True,
-                stream=None):
-    """Two-view reprojection errors + good mask right after a solver call. Returns err1, err2, good, sums(4)."""
+                stream=None, sums_device=None):
+    """Two-view reprojection errors + good mask right after a solver call. Returns err1, err2, good, sums(4).
+    sums_device (a 4-double device buffer, device inputs only): asynchronous variant -- the sums are finished inside
+    the kernel and stay on the device, the call does not synchronise and returns sums_device in place of the host sums."""
     dev = _is_device(x)
     if not dev:
         x = np.asarray(x); u1 = np.asarray(u1); u2 = np.asarray(u2); status = np.asarray(status)
@@ -496,6 +499,13 @@ def pair_reproj(x, u1, P1, u2, P2, status, min_status=0, max_sq_err=np.inf, want
     e1 = _out(dev, n, 0, xdt, None) if want_errors else None
     e2 = _out(dev, n, 0, xdt, None) if want_errors else None
     good = _out(dev, n, 0, np.bool_, None) if want_good else None
+    if sums_device is not None:
+        if not dev:
+            raise ValueError("the asynchronous variant needs device buffers")
+        check(lib().trgl_pair_reproj_async(_ptr(x), _ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(status),
+                                           int(sdt.itemsize == 4), int(min_status), float(max_sq_err), _ptr(e1), _ptr(e2),
+                                           _ptr(good), _ptr(sums_device), n, mode, stream))
+        return e1, e2, good, sums_device
     sums = np.zeros(4)
     check(lib().trgl_pair_reproj(_ptr(x), _ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(status), int(sdt.itemsize == 4),
                                  int(min_status), float(max_sq_err), _ptr(e1), _ptr(e2), _ptr(good), _dp(sums), n,

@@ -534,3 +534,60 @@ def test_golden_cells_device_resident(tri, golden_dir):
                 want = cell[k][ti]
                 if want is not None:
                     assert got == pytest.approx(want, rel=2e-8, abs=1e-12), (cell["traj"], cell["pose"], k, ti)
+
+
+def test_async_pair_reprojection_matches_synchronous(tri):
+    """trgl_pair_reproj_async finishes the sums inside the kernel (last-block reduction in block order): same bits as the
+    host-summed synchronous variant, launch after launch (the ticket counter resets itself)."""
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(123457, "rotating", sigma=0.8)
+    d1, d2 = tc.to_device(u1), tc.to_device(u2)
+    x, st = tc.iterative_ls(d1, P1, d2, P2)
+    _, _, good_s, sums = tc.pair_reproj(x, d1, P1, d2, P2, st, 0, (2.0 / 480) ** 2)
+    dsum = tc.DeviceArray((4,), np.float64)
+    for _ in range(3):
+        _, _, good_a, out = tc.pair_reproj(x, d1, P1, d2, P2, st, 0, (2.0 / 480) ** 2, sums_device=dsum)
+        tc.synchronize()
+        assert np.array_equal(out.to_host(), sums)
+        assert np.array_equal(good_a.to_host(), good_s.to_host())
+    assert sums[2] > 1000
+
+
+def test_device_mode_is_reentrant_per_stream(tri):
+    """Four host threads, each on its own stream, hammer the entry points that use reduction scratch (polynomial NaN
+    flags, pair_reproj sums, median): scratch is per (device, stream), so every thread must get the single-thread answer."""
+    import ctypes
+    import threading
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(200003, "general", sigma=0.8)
+    d1, d2 = tc.to_device(u1), tc.to_device(u2)
+    x0, st0, nan0 = tc.polynomial(d1, P1, d2, P2)
+    tc.synchronize()
+    _, _, _, sums0 = tc.pair_reproj(x0, d1, P1, d2, P2, st0, 0, 1e-5, want_errors=False, want_good=False)
+    e0, _ = tc.eval_errors_3d(x0, tc.to_device(X))
+    med0 = tc.median(e0)
+    x0h = x0.to_host()
+    errors = []
+
+    def worker(k):
+        try:
+            s = ctypes.c_void_p()
+            tc.check(tc.lib().trgl_stream_create(ctypes.byref(s)))
+            dX = tc.to_device(X)
+            for _ in range(15):
+                x, st, nan = tc.polynomial(d1, P1, d2, P2, stream=s)
+                _, _, _, sums = tc.pair_reproj(x, d1, P1, d2, P2, st, 0, 1e-5, want_errors=False, want_good=False, stream=s)
+                e, _ = tc.eval_errors_3d(x, dX, stream=s)
+                med = tc.median(e, stream=s)
+                assert nan == nan0 and np.array_equal(sums, sums0) and med == med0
+            tc.check(tc.lib().trgl_stream_synchronize(s))
+            assert np.array_equal(x.to_host(), x0h, equal_nan=True)
+            tc.check(tc.lib().trgl_stream_destroy(s))
+        except Exception as exc:        # noqa: BLE001
+            errors.append((k, repr(exc)))
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
