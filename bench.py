@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="N > 1: all-gather x over NCCL inside the timed step")
+    ap.add_argument("--p2p-gather", action="store_true",
+                    help="N > 1: gather x/status by storing into every peer's buffer from inside the solver kernels "
+                         "(CUDA IPC + NVLink, sharding.PeerGather) instead of a separate NCCL all-gather")
     ap.add_argument("--workload", default="solvers", choices=["solvers", "slam", "scene"],
                     help="solvers: the four solvers at --points per GPU (default, BASELINE configs[1]); "
                          "slam: keyframe map-extension latency at SLAM-sized batches (BASELINE configs[4]); "
@@ -202,11 +205,18 @@ def run_ours(args, rank, world, local_rank):
     d_x = {s: tc.DeviceArray((n, 3), np.float64) for s in SOLVERS}
     d_st = {s: tc.DeviceArray((n,), np.int32 if s == "iterative_LS" else np.uint8) for s in SOLVERS}
     gather_buf = None
+    peer = None
     if world > 1 and args.gather:
         import torch
         # x lives in torch tensors so NCCL can all-gather it; kernels and NCCL share the legacy default stream
         d_x = {s: torch.empty((n, 3), dtype=torch.float64, device="cuda") for s in SOLVERS}
         gather_buf = torch.empty((world * n, 3), dtype=torch.float64, device="cuda")
+    elif world > 1 and args.p2p_gather:
+        import sharding
+        # every rank owns the full-size result of each solver; the solver kernels store into all of them over NVLink
+        peer = {s: sharding.PeerGather(world * n, np.float64, np.int32 if s == "iterative_LS" else np.uint8) for s in SOLVERS}
+        for s in SOLVERS:
+            d_x[s], d_st[s] = peer[s].shard_outputs()
 
     ev = [tc.Event() for _ in range(9)]
     d_sums = tc.DeviceArray((4, 4), np.float64)      # per-solver reprojection sums, finished on the device
@@ -216,6 +226,8 @@ def run_ours(args, rank, world, local_rank):
         sums_total = 0.0
         for name in SOLVERS:
             ev[k].record(); k += 1
+            if peer is not None:
+                peer[name].arm()
             if name == "linear_eigen":
                 tc.linear_eigen(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name])
             elif name == "linear_LS":
@@ -233,6 +245,8 @@ def run_ours(args, rank, world, local_rank):
                 dist.all_gather_into_tensor(gather_buf, d_x[name])
         ev[8].record()
         sums_total = float(d_sums.to_host()[:, 0:2].sum())      # the step's result comes back to the host (synchronises)
+        if peer is not None:
+            dist.barrier()                                        # every rank's stores have landed: gathered arrays valid
         if timed is not None:
             for i, name in enumerate(SOLVERS):
                 timed[name].append(ev[2 * i].elapsed_ms(ev[2 * i + 1]))
@@ -317,7 +331,9 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "synthetic 2-camera rig (%s), %d points per GPU, all four solvers FP64 + fused two-view "
                                "reprojection error / good mask after each (BASELINE.json configs[1])" % (args.rig, n),
                    "points_per_gpu": n, "rig": args.rig, "sharding": "contiguous point ranges, no data-path collective"
-                   + (", NCCL all-gather of x" if args.gather else ""),
+                   + (", NCCL all-gather of x" if args.gather else "")
+                   + (", x and status gathered by peer stores from inside the solver kernels (CUDA IPC / NVLink)"
+                      if args.p2p_gather else ""),
                    "l2": "inputs (%.0f MB) exceed the 126 MB L2, no explicit flush" % (32.0 * n / 1e6)},
         "roofline": {"kernel": "k_linear_ls<f64>", "bound": "hbm", "achieved": ls["hbm_gbs"], "peak": hbm_peak,
                      "unit": "GB/s", "frac": ls["hbm_frac"],

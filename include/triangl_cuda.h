@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define TRGL_VERSION 102
+#define TRGL_VERSION 103
 
 enum { TRGL_F64 = 0, TRGL_F32IO = 1, TRGL_F32 = 2, TRGL_F64_OUT32 = 3, TRGL_F32_OUT64 = 4 };
 enum { TRGL_MEM_HOST = 0, TRGL_MEM_DEVICE = 1 };
@@ -202,6 +202,25 @@ int trgl_eval_errors_2d(const void* proj, const double* exact, double* errors, d
  * IEEE bit patterns (8 histogram passes), mean of the two middle elements for even n, NaN if any element is NaN or
  * n == 0.  median: host double.  Synchronises the stream. */
 int trgl_median(const double* values, int64_t n, int mem, double* median, void* stream);
+
+/* ---- multi-GPU: the result gather fused into the solver's stores ---- */
+
+/* One process per GPU.  Every rank allocates the gathered arrays x_all (N_total,3) and status_all (N_total,) with
+ * trgl_device_alloc, exports them (trgl_ipc_export -> 64-byte CUDA IPC handle), exchanges the handles out of band
+ * (torch.distributed / MPI / a pipe) and maps its peers' arrays with trgl_ipc_import (peer access over NVLink / NVSwitch
+ * is enabled by the mapping).  Before a solver call on its shard [lo, lo+n) a rank then passes, for each peer,
+ * the addresses of that shard inside the peer's arrays:
+ *     x_mirrors[r] = peer_r.x_all + 3*lo (elements of x's dtype),  status_mirrors[r] = peer_r.status_all + lo
+ * with trgl_set_result_mirrors (at most 7 peers).  The table applies to the NEXT device-mode solver call of the calling
+ * host thread (trgl_linear_ls / iterative_ls / linear_eigen / polynomial and their _px twins) and is cleared by it.
+ * That kernel repeats every store of x and status to all mirrors, so when it has finished on every rank (stream
+ * synchronise + a barrier of the caller's choice) each rank holds the complete result -- no all-gather pass, no second
+ * read of x from HBM, and the NVLink traffic overlaps the solve.  The reference has no multi-process code (SURVEY.md
+ * F10); this replaces the ncclAllGather of SURVEY.md 8e. */
+int trgl_set_result_mirrors(void* const* x_mirrors, void* const* status_mirrors, int count);
+int trgl_ipc_export(void* device_ptr, void* handle64);            /* device_ptr from trgl_device_alloc */
+int trgl_ipc_import(const void* handle64, void** device_ptr);     /* in ANOTHER process than the exporter */
+int trgl_ipc_close(void* device_ptr);
 
 /* ---- bench / diagnostics ---- */
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */

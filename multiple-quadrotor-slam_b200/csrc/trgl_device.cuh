@@ -118,12 +118,27 @@ struct PreUndistort {
     }
 };
 
+// ---- result mirrors: the gather of a multi-GPU run fused into the solver's own stores --------------------------------
+// Each entry is the address, in a PEER GPU's memory (mapped through CUDA IPC, reachable over NVLink / NVSwitch), of the
+// slot this rank's shard occupies in that peer's gathered (N_total,3) result / (N_total,) status array.  Every store of
+// x and status is repeated to all mirrors, so when the kernel ends the shard is already in place on every rank: no
+// separate all-gather pass re-reads x from HBM, and the NVLink traffic overlaps the solve tile by tile.
+constexpr int kMaxMirrors = 7;
+struct Mirrors { int count; int pad_; void* x[kMaxMirrors]; void* status[kMaxMirrors]; };
+
+template <typename TS>
+__device__ __forceinline__ void store_status(TS* __restrict__ status, const Mirrors& mir, int64_t i, TS v) {
+    status[i] = v;
+    for (int r = 0; r < mir.count; ++r) static_cast<TS*>(mir.status[r])[i] = v;
+}
+
 // ---- coalesced store of the (n,3) AoS result ---------------------------------------------------------------
 // Each warp owns 32 consecutive points starting at warp_base.  The 96 scalars are transposed through a per-warp
 // shared-memory row (stride-3 writes are bank-conflict free) and leave as three 32-wide contiguous stores.
 template <typename TO>
 __device__ __forceinline__ void store_x_warp(TO* __restrict__ xout, int64_t warp_base, int64_t n,
-                                             TO x0, TO x1, TO x2, TO* __restrict__ stage /* [96] of this warp */) {
+                                             TO x0, TO x1, TO x2, TO* __restrict__ stage /* [96] of this warp */,
+                                             const Mirrors& mir) {
     const int lane = threadIdx.x & 31;
 
     stage[lane * 3 + 0] = x0;
@@ -137,6 +152,14 @@ __device__ __forceinline__ void store_x_warp(TO* __restrict__ xout, int64_t warp
     for (int k = 0; k < 3; ++k) {
         const int idx = k * 32 + lane;
         if (idx < cnt) __stcs(dst + idx, stage[idx]);
+    }
+    for (int r = 0; r < mir.count; ++r) {           // same three contiguous rows into every peer's gather buffer
+        TO* __restrict__ peer = static_cast<TO*>(mir.x[r]) + warp_base * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int idx = k * 32 + lane;
+            if (idx < cnt) peer[idx] = stage[idx];
+        }
     }
     __syncwarp();
 }

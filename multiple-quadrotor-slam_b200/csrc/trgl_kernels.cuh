@@ -17,7 +17,8 @@ constexpr int kWarps = kThreads / 32;
 template <typename TI, typename TC, typename TO, int PPT, class PRE = PreNone>
 __global__ void __launch_bounds__(kThreads)
 k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-            TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ PRE pre) {
+            TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ PRE pre,
+            const __grid_constant__ Mirrors mir) {
     __shared__ TO stage[kWarps][96];
     const int warp = threadIdx.x >> 5;
     const int64_t block_base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT);
@@ -40,8 +41,8 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
         if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs))
             solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
         store_x_warp<TO>(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
-                         static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage[warp]);
-        if (i < n) status[i] = 1;
+                         static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage[warp], mir);
+        if (i < n) store_status<uint8_t>(status, mir, i, 1);
     }
 }
 
@@ -53,7 +54,7 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
 template <typename TI, typename TC, typename TO, int PPT, int DEPTH, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_linear_ls_ring(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-                 TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n) {
+                 TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ Mirrors mir) {
     constexpr int TILE = kThreads * PPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TI* ring = reinterpret_cast<TI*>(smem_raw);                                   // [DEPTH][2 views][TILE*2]
@@ -100,8 +101,8 @@ k_linear_ls_ring(const TI* __restrict__ u1, const TI* __restrict__ u2, const __g
             if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs))
                 solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
             store_x_warp<TO>(x, tile + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                             static_cast<TO>(xs[2]), stage + warp * 96);
-            if (i < n) status[i] = 1;
+                             static_cast<TO>(xs[2]), stage + warp * 96, mir);
+            if (i < n) store_status<uint8_t>(status, mir, i, 1);
         }
         if (++slot == DEPTH) slot = 0;
     }
@@ -114,7 +115,7 @@ k_linear_ls_ring(const TI* __restrict__ u1, const TI* __restrict__ u2, const __g
 template <typename TI, typename TC, typename TO, int PPT, int STAGES, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_linear_ls_tma(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-                TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n) {
+                TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ Mirrors mir) {
     constexpr int TILE = kThreads * PPT;
     constexpr uint32_t kTileBytes = TILE * 2 * sizeof(TI);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -170,8 +171,8 @@ k_linear_ls_tma(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gr
             if (!ls_point_fast<TC>(cams, a, b, c, d, xs))
                 solve_point_careful<TC>(cams, a, b, c, d, TC(1), TC(1), xs);
             store_x_warp<TO>(x, tile_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
-                             static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage_out + warp * 96);
-            if (i < n) status[i] = 1;
+                             static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage_out + warp * 96, mir);
+            if (i < n) store_status<uint8_t>(status, mir, i, 1);
         }
         __syncthreads();                        // every thread has consumed stage s
         if (threadIdx.x == 0) {
@@ -236,7 +237,7 @@ struct IterSmem {
 template <typename TC, typename TO>
 __device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*q_state)[kQueueCap], const int64_t* q_idx,
                                                int slot, TO* __restrict__ x, int32_t* __restrict__ status,
-                                               TC tolerance, int py_semantics) {
+                                               TC tolerance, int py_semantics, const Mirrors& mir) {
     const TC a = q_state[0][slot], b = q_state[1][slot], c = q_state[2][slot], d = q_state[3][slot];
     TC w1 = q_state[4][slot], w2 = q_state[5][slot], d1 = q_state[6][slot], d2 = q_state[7][slot], d1n = d1, d2n = d2;
     const int64_t dst = q_idx[slot];
@@ -251,14 +252,19 @@ __device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*
     x[3 * dst + 0] = static_cast<TO>(xs[0]);
     x[3 * dst + 1] = static_cast<TO>(xs[1]);
     x[3 * dst + 2] = static_cast<TO>(xs[2]);
-    status[dst] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+    for (int r = 0; r < mir.count; ++r) {
+        TO* __restrict__ peer = static_cast<TO*>(mir.x[r]) + 3 * dst;
+        peer[0] = static_cast<TO>(xs[0]); peer[1] = static_cast<TO>(xs[1]); peer[2] = static_cast<TO>(xs[2]);
+    }
+    store_status<int32_t>(status, mir, dst, iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n)));
 }
 
 template <typename TI, typename TC, typename TO, class PRE = PreNone>
 __global__ void __launch_bounds__(kThreads, 2)
 k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
-               const TC tolerance, const int py_semantics, const __grid_constant__ PRE pre_stage) {
+               const TC tolerance, const int py_semantics, const __grid_constant__ PRE pre_stage,
+               const __grid_constant__ Mirrors mir) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IterSmem<TI, TC, TO>& sm = *reinterpret_cast<IterSmem<TI, TC, TO>*>(smem_raw);
     auto& pre = sm.pre; auto& q_state = sm.q_state; auto& q_idx = sm.q_idx; auto& stage = sm.stage; int& q_count = sm.q_count;
@@ -300,8 +306,8 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
             }
             // finished points leave through the coalesced path (pending lanes write a placeholder that phase 2 overwrites)
             store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                             static_cast<TO>(xs[2]), stage[warp]);
-            if (i < n && !pending) status[i] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+                             static_cast<TO>(xs[2]), stage[warp], mir);
+            if (i < n && !pending) store_status<int32_t>(status, mir, i, iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n)));
             // every thread learns how many points this tile queued (the barrier also publishes the queue entries);
             // the queue length lives in a register so the drain decision is uniform without re-reading q_count
             count += __syncthreads_count(pending);
@@ -309,12 +315,12 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         if (count >= kThreads) {                         // count < kQueueCap: <= kThreads-1 left over + kThreads pushed
             count -= kThreads;
             if (threadIdx.x == 0) q_count = count;       // nobody pushes before the barrier below
-            iter_ls_phase2<TC, TO>(cams, q_state, q_idx, count + threadIdx.x, x, status, tolerance, py_semantics);
+            iter_ls_phase2<TC, TO>(cams, q_state, q_idx, count + threadIdx.x, x, status, tolerance, py_semantics, mir);
             __syncthreads();
         }
     }
     if (static_cast<int>(threadIdx.x) < count)
-        iter_ls_phase2<TC, TO>(cams, q_state, q_idx, threadIdx.x, x, status, tolerance, py_semantics);
+        iter_ls_phase2<TC, TO>(cams, q_state, q_idx, threadIdx.x, x, status, tolerance, py_semantics, mir);
 }
 
 // ---- linear_eigen_triangulation (triangulation.py:6-25) --------------------------------------------------------
@@ -471,7 +477,7 @@ template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone>
 __global__ void __launch_bounds__(kThreads, 2)
 k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord,
-               const __grid_constant__ PRE pre_stage) {
+               const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir) {
     __shared__ TO stage[kWarps][96];
     __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
     const int warp = threadIdx.x >> 5;
@@ -487,8 +493,8 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         TC xs[3]; bool good;
         eigen_point<TC, ROWS>(cams, a, b, c, d, max_coord, xs, good);
         store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                         static_cast<TO>(xs[2]), stage[warp]);
-        if (i < n) status[i] = good ? 1 : 0;
+                         static_cast<TO>(xs[2]), stage[warp], mir);
+        if (i < n) store_status<uint8_t>(status, mir, i, good ? 1 : 0);
     }
 }
 
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams, const __grid_constant__ HSParams hs,
              TO* __restrict__ x, uint8_t* __restrict__ status, TI* __restrict__ u1c, TI* __restrict__ u2c,
              unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord,
-             const __grid_constant__ PRE pre_stage) {
+             const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir) {
     __shared__ TO stage[kWarps][96];
     __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
     const int warp = threadIdx.x >> 5;
@@ -530,8 +536,8 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
         eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
                               static_cast<TC>(r2y), max_coord, xs, good);
         store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                         static_cast<TO>(xs[2]), stage[warp]);
-        if (i < n) status[i] = good ? 1 : 0;
+                         static_cast<TO>(xs[2]), stage[warp], mir);
+        if (i < n) store_status<uint8_t>(status, mir, i, good ? 1 : 0);
     }
     // one flag update per CTA (two words shared by the whole grid: per-warp atomics would all hit the same L2 line)
     const int f1 = __syncthreads_or(any1), f2 = __syncthreads_or(any2);

@@ -22,6 +22,15 @@ thread_local std::string g_err = "";
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_ppt{4};
 
+// Result mirrors attached to the NEXT device-mode solver call of this host thread (trgl_set_result_mirrors).
+thread_local Mirrors g_next_mirrors = {0, 0, {nullptr}, {nullptr}};
+Mirrors take_mirrors() {
+    Mirrors m = g_next_mirrors;
+    g_next_mirrors.count = 0;
+    return m;
+}
+const Mirrors kNoMirrors = {0, 0, {nullptr}, {nullptr}};
+
 int fail(int code, const char* what) {
     g_err = what;
     return code;
@@ -80,7 +89,8 @@ std::atomic<int> g_variant{-1};         // -1 = auto, 0 = per-thread loads, >= 1
 int g_sm_count = 0;
 
 template <typename TI, typename TC, typename TO, int PPT, int STAGES, int MINB>
-int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n, cudaStream_t s) {
+int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n, cudaStream_t s,
+                  const Mirrors& mir) {
     constexpr int TILE = kThreads * PPT;
     const size_t smem = size_t(STAGES) * 2 * TILE * 2 * sizeof(TI) + kWarps * 96 * sizeof(TO) + STAGES * sizeof(uint64_t);
     auto kern = k_linear_ls_tma<TI, TC, TO, PPT, STAGES, MINB>;
@@ -98,7 +108,7 @@ int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_
     if (per_sm < 1) per_sm = 1;
     const int64_t ntiles = (n + TILE - 1) / TILE;
     const int64_t grid = ntiles < int64_t(g_sm_count) * per_sm ? ntiles : int64_t(g_sm_count) * per_sm;
-    kern<<<static_cast<unsigned>(grid), kThreads, smem, s>>>(a, b, cams, xo, status, n);
+    kern<<<static_cast<unsigned>(grid), kThreads, smem, s>>>(a, b, cams, xo, status, n, mir);
     return TRGL_OK;
 }
 
@@ -123,7 +133,8 @@ unsigned persistent_grid(K kern, int64_t n, size_t dyn_smem = 0) {
 }
 
 template <typename TI, typename TC, typename TO, int PPT, int DEPTH, int MINB>
-int launch_ls_ring(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n, cudaStream_t s) {
+int launch_ls_ring(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n, cudaStream_t s,
+                   const Mirrors& mir) {
     const size_t smem = size_t(DEPTH) * 2 * kThreads * PPT * 2 * sizeof(TI) + kWarps * 96 * sizeof(TO);
     auto kern = k_linear_ls_ring<TI, TC, TO, PPT, DEPTH, MINB>;
     static thread_local std::unordered_map<const void*, int> per_sm_cache;
@@ -135,26 +146,26 @@ int launch_ls_ring(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8
     }
     const int64_t tiles = (n + kThreads * PPT - 1) / (kThreads * PPT);
     const int64_t full = static_cast<int64_t>(g_sm_count) * per_sm;
-    kern<<<static_cast<unsigned>(tiles < full ? tiles : full), kThreads, smem, s>>>(a, b, cams, xo, status, n);
+    kern<<<static_cast<unsigned>(tiles < full ? tiles : full), kThreads, smem, s>>>(a, b, cams, xo, status, n, mir);
     return TRGL_OK;
 }
 
 template <typename TI, typename TC, typename TO>
 void launch_ls_direct(int ppt, const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n,
-                      cudaStream_t s, const Undist2* pre) {
+                      cudaStream_t s, const Undist2* pre, const Mirrors& mir) {
     if (pre) {      // pixel inputs: the undistortion makes the kernel FP64-bound, one point per thread is enough
         const PreUndistort pu{*pre};
-        k_linear_ls<TI, TC, TO, 1, PreUndistort><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, pu);
+        k_linear_ls<TI, TC, TO, 1, PreUndistort><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, pu, mir);
         return;
     }
     const PreNone none{};
-    if (ppt == 1) k_linear_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, none);
-    else if (ppt == 2) k_linear_ls<TI, TC, TO, 2><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n, none);
-    else k_linear_ls<TI, TC, TO, 4><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, none);
+    if (ppt == 1) k_linear_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, none, mir);
+    else if (ppt == 2) k_linear_ls<TI, TC, TO, 2><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n, none, mir);
+    else k_linear_ls<TI, TC, TO, 4><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, none, mir);
 }
 
 int launch_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
-                     int64_t n, int mode, cudaStream_t s, const Undist2* pre = nullptr) {
+                     int64_t n, int mode, cudaStream_t s, const Undist2* pre = nullptr, const Mirrors& mir = kNoMirrors) {
     if (n == 0) return TRGL_OK;
     const int ppt = g_ppt.load();
     int variant = g_variant.load();
@@ -174,19 +185,19 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
         TO* xo = static_cast<TO*>(x);
         int rc = TRGL_OK;
         switch (variant) {
-            case 1: rc = launch_ls_tma<TI, TC, TO, 2, 4, 3>(a, b, cams, xo, status, n, s); break;
-            case 2: rc = launch_ls_tma<TI, TC, TO, 4, 3, 2>(a, b, cams, xo, status, n, s); break;
-            case 3: rc = launch_ls_tma<TI, TC, TO, 1, 6, 3>(a, b, cams, xo, status, n, s); break;
-            case 4: rc = launch_ls_tma<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s); break;
-            case 5: rc = launch_ls_tma<TI, TC, TO, 4, 4, 1>(a, b, cams, xo, status, n, s); break;
-            case 6: rc = launch_ls_tma<TI, TC, TO, 1, 8, 3>(a, b, cams, xo, status, n, s); break;
-            case 7: rc = launch_ls_ring<TI, TC, TO, 1, 8, 2>(a, b, cams, xo, status, n, s); break;
-            case 8: rc = launch_ls_ring<TI, TC, TO, 2, 4, 2>(a, b, cams, xo, status, n, s); break;
-            case 9: rc = launch_ls_ring<TI, TC, TO, 4, 2, 2>(a, b, cams, xo, status, n, s); break;
-            case 10: rc = launch_ls_ring<TI, TC, TO, 4, 3, 2>(a, b, cams, xo, status, n, s); break;
-            case 11: rc = launch_ls_ring<TI, TC, TO, 2, 4, 3>(a, b, cams, xo, status, n, s); break;
-            case 12: rc = launch_ls_ring<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s); break;
-            default: launch_ls_direct<TI, TC, TO>(ppt, a, b, cams, xo, status, n, s, pre);
+            case 1: rc = launch_ls_tma<TI, TC, TO, 2, 4, 3>(a, b, cams, xo, status, n, s, mir); break;
+            case 2: rc = launch_ls_tma<TI, TC, TO, 4, 3, 2>(a, b, cams, xo, status, n, s, mir); break;
+            case 3: rc = launch_ls_tma<TI, TC, TO, 1, 6, 3>(a, b, cams, xo, status, n, s, mir); break;
+            case 4: rc = launch_ls_tma<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s, mir); break;
+            case 5: rc = launch_ls_tma<TI, TC, TO, 4, 4, 1>(a, b, cams, xo, status, n, s, mir); break;
+            case 6: rc = launch_ls_tma<TI, TC, TO, 1, 8, 3>(a, b, cams, xo, status, n, s, mir); break;
+            case 7: rc = launch_ls_ring<TI, TC, TO, 1, 8, 2>(a, b, cams, xo, status, n, s, mir); break;
+            case 8: rc = launch_ls_ring<TI, TC, TO, 2, 4, 2>(a, b, cams, xo, status, n, s, mir); break;
+            case 9: rc = launch_ls_ring<TI, TC, TO, 4, 2, 2>(a, b, cams, xo, status, n, s, mir); break;
+            case 10: rc = launch_ls_ring<TI, TC, TO, 4, 3, 2>(a, b, cams, xo, status, n, s, mir); break;
+            case 11: rc = launch_ls_ring<TI, TC, TO, 2, 4, 3>(a, b, cams, xo, status, n, s, mir); break;
+            case 12: rc = launch_ls_ring<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s, mir); break;
+            default: launch_ls_direct<TI, TC, TO>(ppt, a, b, cams, xo, status, n, s, pre, mir);
         }
         if (rc) return rc;
     })
@@ -196,7 +207,8 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
 }
 
 int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
-                        int64_t n, double tol, int semantics, int mode, cudaStream_t s, const Undist2* pre = nullptr) {
+                        int64_t n, double tol, int semantics, int mode, cudaStream_t s, const Undist2* pre = nullptr,
+                        const Mirrors& mir = kNoMirrors) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
@@ -206,12 +218,12 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
             auto kern = k_iterative_ls<TI, TC, TO, PreUndistort>;
             kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
                 static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
-                static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, PreUndistort{*pre});
+                static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, PreUndistort{*pre}, mir);
         } else {
             auto kern = k_iterative_ls<TI, TC, TO, PreNone>;
             kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
                 static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
-                static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, PreNone{});
+                static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, PreNone{}, mir);
         }
     })
     g_launches++;
@@ -223,18 +235,19 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
     {                                                                                                          \
         auto kern = k_linear_eigen<TI, TC, TO, ROWS, PRE>;                                                     \
         kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n,         \
-                                                           static_cast<TC>(maxc), prearg);                     \
+                                                           static_cast<TC>(maxc), prearg, mir);                \
     }
 #define POLY_LAUNCH(ROWS, PRE, prearg)                                                                         \
     {                                                                                                          \
         auto kern = k_polynomial<TI, TC, TO, ROWS, PRE>;                                                       \
         kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status,        \
                                                            static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, \
-                                                           static_cast<TC>(maxc), prearg);                     \
+                                                           static_cast<TC>(maxc), prearg, mir);                \
     }
 
 int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
-                        int64_t n, double maxc, int rows, int mode, cudaStream_t s, const Undist2* pre = nullptr) {
+                        int64_t n, double maxc, int rows, int mode, cudaStream_t s, const Undist2* pre = nullptr,
+                        const Mirrors& mir = kNoMirrors) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
@@ -250,7 +263,7 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
 
 int launch_polynomial(const void* u1, const void* u2, const double* P1, const double* P2, const HSParams& hs, void* x,
                       uint8_t* status, void* u1c, void* u2c, unsigned int* flags, int64_t n, double maxc, int rows,
-                      int mode, cudaStream_t s, const Undist2* pre = nullptr) {
+                      int mode, cudaStream_t s, const Undist2* pre = nullptr, const Mirrors& mir = kNoMirrors) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
     MODE_SWITCH(mode, {
@@ -426,6 +439,10 @@ int check_common(const void* u1, const void* u2, const double* P1, const double*
         ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & static_cast<uintptr_t>(2 * mi.in_bytes - 1)))
         return fail(TRGL_E_BADARG, "device u1/u2 must be aligned to one (x,y) pair (16 bytes float64, 8 bytes float32)");
     if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    if (g_next_mirrors.count && (mem != TRGL_MEM_DEVICE || n == 0)) {
+        g_next_mirrors.count = 0;
+        if (mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "result mirrors need device buffers (TRGL_MEM_DEVICE)");
+    }
     return TRGL_OK;
 }
 
@@ -605,6 +622,37 @@ int trgl_event_elapsed_ms(void* start, void* stop, float* ms) {
     return TRGL_OK;
 }
 
+// ---- result mirrors / CUDA IPC (multi-GPU gather fused into the solver stores) ----------------------------------------
+int trgl_set_result_mirrors(void* const* x_mirrors, void* const* status_mirrors, int count) {
+    if (count < 0 || count > kMaxMirrors) return fail(TRGL_E_BADARG, "at most 7 result mirrors");
+    if (count > 0 && (!x_mirrors || !status_mirrors)) return fail(TRGL_E_BADARG, "NULL mirror table");
+    g_next_mirrors.count = count;
+    for (int r = 0; r < count; ++r) {
+        if (!x_mirrors[r] || !status_mirrors[r]) { g_next_mirrors.count = 0; return fail(TRGL_E_BADARG, "NULL mirror pointer"); }
+        g_next_mirrors.x[r] = x_mirrors[r]; g_next_mirrors.status[r] = status_mirrors[r];
+    }
+    return TRGL_OK;
+}
+int trgl_ipc_export(void* device_ptr, void* handle64) {
+    if (!device_ptr || !handle64) return fail(TRGL_E_BADARG, "NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, device_ptr));
+    std::memcpy(handle64, &h, sizeof(h));
+    return TRGL_OK;
+}
+int trgl_ipc_import(const void* handle64, void** device_ptr) {
+    if (!device_ptr || !handle64) return fail(TRGL_E_BADARG, "NULL pointer");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    CK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TRGL_OK;
+}
+int trgl_ipc_close(void* device_ptr) {
+    if (device_ptr) CK(cudaIpcCloseMemHandle(device_ptr));
+    return TRGL_OK;
+}
+
 int64_t trgl_launch_count(void) { return g_launches.load(); }
 int trgl_set_stream_variant(int variant) {
     const int old = g_variant.load();
@@ -622,7 +670,8 @@ static int impl_linear_ls(const void* u1, const void* u2, const double* P1, cons
                           int64_t n, int mode, int mem, void* stream, const Undist2* pre) {
     int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
     if (rc || n == 0) return rc;
-    if (mem == TRGL_MEM_DEVICE) return launch_linear_ls(u1, u2, P1, P2, x, status, n, mode, static_cast<cudaStream_t>(stream), pre);
+    if (mem == TRGL_MEM_DEVICE)
+        return launch_linear_ls(u1, u2, P1, P2, x, status, n, mode, static_cast<cudaStream_t>(stream), pre, take_mirrors());
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
@@ -649,7 +698,8 @@ static int impl_iterative_ls(const void* u1, const void* u2, const double* P1, c
     if (semantics != TRGL_ITER_C && semantics != TRGL_ITER_PY) return fail(TRGL_E_BADARG, "unknown iterative semantics");
     if (n == 0) return TRGL_OK;
     if (mem == TRGL_MEM_DEVICE)
-        return launch_iterative_ls(u1, u2, P1, P2, x, status, n, tolerance, semantics, mode, static_cast<cudaStream_t>(stream), pre);
+        return launch_iterative_ls(u1, u2, P1, P2, x, status, n, tolerance, semantics, mode, static_cast<cudaStream_t>(stream), pre,
+                                   take_mirrors());
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 4}};
@@ -677,7 +727,8 @@ static int impl_linear_eigen(const void* u1, const void* u2, const double* P1, c
     if (rows != 4 && rows != 6) return fail(TRGL_E_BADARG, "rows must be 4 or 6");
     if (n == 0) return TRGL_OK;
     if (mem == TRGL_MEM_DEVICE)
-        return launch_linear_eigen(u1, u2, P1, P2, x, status, n, max_coordinate_value, rows, mode, static_cast<cudaStream_t>(stream), pre);
+        return launch_linear_eigen(u1, u2, P1, P2, x, status, n, max_coordinate_value, rows, mode, static_cast<cudaStream_t>(stream), pre,
+                                   take_mirrors());
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
@@ -716,7 +767,8 @@ static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, c
         if (rc) return rc;
         unsigned int* fl = sc.flags + 2 * kSlots;
         CK(cudaMemsetAsync(fl, 0, 2 * sizeof(unsigned int), s));
-        rc = launch_polynomial(u1, u2, P1, P2, hs, x, status, u1_corr, u2_corr, fl, n, max_coordinate_value, rows, mode, s, pre);
+        rc = launch_polynomial(u1, u2, P1, P2, hs, x, status, u1_corr, u2_corr, fl, n, max_coordinate_value, rows, mode, s, pre,
+                               take_mirrors());
         if (rc) return rc;
         if (all_nan) {
             CK(cudaMemcpyAsync(hflags, fl, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));

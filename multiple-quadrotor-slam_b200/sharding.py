@@ -81,6 +81,55 @@ def gather_shards(x_shard, n_total, device=None):
     return res.view(np.bool_) if x_shard.dtype == np.bool_ else res
 
 
+class PeerGather:
+    """
+    The result gather fused into the solver kernels (include/triangl_cuda.h "result mirrors"): every rank owns full-size
+    `x_all (n_total,3)` / `status_all (n_total,)` device arrays, maps its peers' copies through CUDA IPC (handles are
+    exchanged with `all_gather_object` of the default process group -- NCCL or gloo, plumbing only), and each solver call
+    on the local shard stores straight into all of them over NVLink.  After `finish()` every rank holds the full result.
+    """
+
+    def __init__(self, n_total, x_dtype=np.float64, status_dtype=np.uint8):
+        import triangl_cuda as tc
+        dist = _dist()
+        self.tc = tc
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world - 1 > 7:
+            raise ValueError("at most 8 ranks (7 peers)")
+        self.n_total = n_total
+        self.lo, self.hi = shard_range(n_total, self.rank, self.world)
+        self.x_all = tc.DeviceArray((n_total, 3), x_dtype)
+        self.status_all = tc.DeviceArray((n_total,), status_dtype)
+        mine = (tc.ipc_export(self.x_all), tc.ipc_export(self.status_all))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine)
+        self.peers = []
+        for r, (hx, hs) in enumerate(handles):
+            if r != self.rank:
+                self.peers.append((tc.ipc_import(hx), tc.ipc_import(hs)))
+        self.xb = 3 * np.dtype(x_dtype).itemsize
+        self.sb = np.dtype(status_dtype).itemsize
+
+    def shard_outputs(self):
+        """(x, status) views of this rank's shard inside its own gathered arrays: pass them as x= / status=."""
+        n = self.hi - self.lo
+        return self.x_all.view(3 * self.lo, (n, 3)), self.status_all.view(self.lo, (n,))
+
+    def arm(self):
+        """Attach the peers' shard addresses to the next device-mode solver call of this thread."""
+        self.tc.set_result_mirrors([(px + self.lo * self.xb, ps + self.lo * self.sb) for (px, ps) in self.peers])
+
+    def finish(self):
+        """All ranks' kernels have completed: the gathered arrays are valid everywhere."""
+        self.tc.synchronize()
+        _dist().barrier()
+
+    def close(self):
+        for (px, ps) in self.peers:
+            self.tc.ipc_close(px); self.tc.ipc_close(ps)
+        self.peers = []
+
+
 def triangulate_sharded(solve_fn, u1, P1, u2, P2, gather=True, device=None, **kwargs):
     """
     Shard one (u1, P1, u2, P2) batch over the ranks of the default process group.

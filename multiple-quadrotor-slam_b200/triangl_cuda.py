@@ -32,6 +32,7 @@ EXPORTS = [
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
     "trgl_set_points_per_thread", "trgl_set_stream_variant",
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
+    "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -82,6 +83,10 @@ def lib():
     L.trgl_reproj_error.argtypes = [vp, vp, dp, dp, dp, dp, vp, dp, dp, i64, cint, cint, cint, vp]
     L.trgl_pair_reproj.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, dp, i64, cint, cint, vp]
     L.trgl_pair_reproj_async.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, vp, i64, cint, vp]
+    L.trgl_set_result_mirrors.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), cint]
+    L.trgl_ipc_export.argtypes = [vp, vp]
+    L.trgl_ipc_import.argtypes = [vp, ctypes.POINTER(vp)]
+    L.trgl_ipc_close.argtypes = [vp]
     L.trgl_eval_errors_3d.argtypes = [vp, vp, cint, vp, cint, dbl, dbl, vp, dp, i64, cint, cint, vp]
     L.trgl_eval_errors_2d.argtypes = [vp, vp, vp, dp, i64, cint, cint, vp]
     L.trgl_median.argtypes = [vp, i64, cint, dp, vp]
@@ -565,6 +570,33 @@ def median(values, stream=None):
     out = np.zeros(1)
     check(lib().trgl_median(_ptr(values), n, MEM_DEVICE if dev else MEM_HOST, _dp(out), stream))
     return float(out[0])
+
+
+def set_result_mirrors(mirrors):
+    """mirrors: list of (x_address, status_address) in peer GPUs' memory for the NEXT device-mode solver call of this
+    thread (see include/triangl_cuda.h, "result gather fused into the solver's stores")."""
+    k = len(mirrors)
+    xs = (ctypes.c_void_p * max(k, 1))(*[int(m[0]) for m in mirrors])
+    ss = (ctypes.c_void_p * max(k, 1))(*[int(m[1]) for m in mirrors])
+    check(lib().trgl_set_result_mirrors(xs, ss, k))
+
+
+def ipc_export(dev):
+    """64-byte CUDA IPC handle of a DeviceArray (or raw device address from trgl_device_alloc)."""
+    h = ctypes.create_string_buffer(64)
+    check(lib().trgl_ipc_export(ctypes.c_void_p(dev.data_ptr() if hasattr(dev, "data_ptr") else int(dev)), h))
+    return h.raw
+
+
+def ipc_import(handle):
+    """Map a peer process's exported buffer; returns the device address valid in this process."""
+    p = ctypes.c_void_p()
+    check(lib().trgl_ipc_import(ctypes.create_string_buffer(handle, 64), ctypes.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr):
+    check(lib().trgl_ipc_close(ctypes.c_void_p(ptr)))
 
 
 def launch_count():

@@ -591,3 +591,71 @@ def test_device_mode_is_reentrant_per_stream(tri):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+# ---- result mirrors: the multi-GPU gather fused into the solver stores -------------------------------------------------
+@pytest.mark.parametrize("name", ["linear_eigen", "linear_LS", "iterative_LS", "polynomial"])
+def test_result_mirrors_receive_every_store(tri, name):
+    """Two mirror buffers (here on the same GPU; across GPUs they are IPC-mapped peer memory) must end up bit-identical to
+    the primary output, for every solver, at a ragged size, at an offset inside a larger 'gathered' array."""
+    import triangl_cuda as tc
+    n, lo, total = 70001, 12345, 100000
+    u1, P1, u2, P2, _ = rig.make_correspondences(n, "rotating", sigma=0.8)
+    d1, d2 = tc.to_device(u1), tc.to_device(u2)
+    sdt = np.int32 if name == "iterative_LS" else np.uint8
+    fn = {"linear_eigen": tc.linear_eigen, "linear_LS": tc.linear_ls, "iterative_LS": tc.iterative_ls,
+          "polynomial": lambda *a, **k: tc.polynomial(*a, check_all_nan=False, **k)[:2]}[name]
+    gathered = [(tc.DeviceArray((total, 3), np.float64), tc.DeviceArray((total,), sdt)) for _ in range(2)]
+    for gx, gs in gathered:
+        tc.check(tc.lib().trgl_memset_d(gx.ptr, 0xff, gx.nbytes, None)); tc.check(tc.lib().trgl_memset_d(gs.ptr, 0x7f, gs.nbytes, None))
+    tc.set_result_mirrors([(gx.ptr + lo * 24, gs.ptr + lo * np.dtype(sdt).itemsize) for gx, gs in gathered])
+    x, st = fn(d1, P1, d2, P2)
+    x2, st2 = fn(d1, P1, d2, P2)                       # the table is consumed by ONE call: this one has no mirrors
+    tc.synchronize()
+    xh, sth = x.to_host(), st.to_host()
+    assert np.array_equal(x2.to_host(), xh, equal_nan=True)
+    for gx, gs in gathered:
+        gxh, gsh = gx.to_host(), gs.to_host()
+        assert np.array_equal(gxh[lo:lo + n], xh, equal_nan=True) and np.array_equal(gsh[lo:lo + n], sth)
+        assert np.isnan(gxh[:lo]).all() and np.isnan(gxh[lo + n:]).all()          # nothing outside the shard was touched
+        assert (gsh[:lo].view(np.uint8) == 0x7f).all() and (gsh[lo + n:].view(np.uint8) == 0x7f).all()
+    with pytest.raises(tc.TrianglCudaError):            # host buffers cannot be mirrored
+        tc.set_result_mirrors([(gathered[0][0].ptr, gathered[0][1].ptr)])
+        tri.linear_LS_triangulation(u1, P1, u2, P2)
+
+
+def _ipc_child(handles, n, lo, q):
+    import numpy as np
+    import synthetic_rig as rig
+    import triangl_cuda as tc
+    try:
+        px, ps = tc.ipc_import(handles[0]), tc.ipc_import(handles[1])
+        u1, P1, u2, P2, _ = rig.make_correspondences(n, "rotating", sigma=0.8)
+        tc.set_result_mirrors([(px + lo * 24, ps + lo * 4)])
+        x, st = tc.iterative_ls(tc.to_device(u1), P1, tc.to_device(u2), P2)
+        tc.synchronize()
+        q.put(("ok", x.to_host(), st.to_host()))
+        tc.ipc_close(px); tc.ipc_close(ps)
+    except Exception as exc:        # noqa: BLE001
+        q.put(("error", repr(exc), None))
+
+
+def test_result_mirrors_across_processes_via_cuda_ipc(tri):
+    """The exporter / importer pair of the multi-GPU gather: another PROCESS maps this process's gathered arrays through a
+    CUDA IPC handle and its solver kernel stores its shard into them (same GPU here; peer GPUs in bench.py --p2p-gather)."""
+    import multiprocessing as mp
+    import triangl_cuda as tc
+    n, lo, total = 30001, 5000, 40000
+    gx, gs = tc.DeviceArray((total, 3), np.float64), tc.DeviceArray((total,), np.int32)
+    tc.check(tc.lib().trgl_memset_d(gx.ptr, 0xff, gx.nbytes, None)); tc.check(tc.lib().trgl_memset_d(gs.ptr, 0x7f, gs.nbytes, None))
+    tc.synchronize()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_ipc_child, args=((tc.ipc_export(gx), tc.ipc_export(gs)), n, lo, q))
+    p.start()
+    tag, xc, stc = q.get(timeout=120)
+    p.join(timeout=60)
+    assert tag == "ok", xc
+    tc.synchronize()
+    assert np.array_equal(gx.to_host()[lo:lo + n], xc, equal_nan=True) and np.array_equal(gs.to_host()[lo:lo + n], stc)
+    assert np.isnan(gx.to_host()[:lo]).all()
