@@ -44,6 +44,17 @@ METRIC = "triangulated_points_per_sec"
 UNIT = "points/s"
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,7 +179,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---- GPU arm ---------------------------------------------------------------------------------------------------
@@ -355,7 +366,7 @@ def run_ours(args, rank, world, local_rank):
         out["cpu_baseline"] = {"value": 4.0 * sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                "sample": "%d points x 4 solvers, same rig and seed" % sample,
                                "per_solver_points_per_sec": {s: sample / parts[s] for s in SOLVERS}}
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -448,7 +459,7 @@ def run_slam(args):
             out["sizes"][str(B)] = row
     finally:
         tri.set_triangl_output_dtype(float)
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---- multi-quadrotor scene: 8 cameras pairwise, correspondences sharded over the ranks (BASELINE.json configs[3]) ---
@@ -552,7 +563,7 @@ def run_scene(args, rank, world, local_rank):
         dist.all_reduce(lt)
         launches = int(lt[0])
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": 4.0 * total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -561,12 +572,19 @@ def run_scene(args, rank, world, local_rank):
                                    % (n, total, ", NCCL all-gather of x after each solver" if args.gather else ""),
                        "points_per_gpu": n, "pairs": 28, "segments_on_rank0": len(mine),
                        "gather_bytes_per_step": (4 * 24 * total) if args.gather else 0},
-            "gpu_launches": launches, "clocks": clocks}))
+            "gpu_launches": launches, "clocks": clocks})
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
+    # rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL / torch print an "NCCL version ..." banner
+    # at communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to
+    # the saved original stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.workload == "slam":
         return run_slam(args)

@@ -213,16 +213,19 @@ __device__ __forceinline__ int iter_ls_status(int it, double d1n, double d2n) { 
     return st;
 }
 
-// Persistent CTAs (one grid-stride loop over 256-point tiles, next tile's four input scalars prefetched into registers
-// while the current tile is solved) with a block-level work queue in shared memory for the divergent tail:
+// Persistent CTAs (one grid-stride loop over 256-point tiles, the next tile's four input scalars prefetched with cp.async
+// while the current tile is solved) with a block-level FIFO work queue in shared memory for the divergent tail:
 //   phase 1: every thread runs the first kPhase1 iterations of its point (on translating rigs every point converges
 //            at the second solve; on rotating rigs ~70 % do).  Finished points leave through the coalesced store.
-//   queue  : points still running push their four input scalars and loop state (w1,w2,d1,d2) to the queue.
-//   phase 2: whenever the queue holds >= 256 entries the block runs the remaining iterations on a full batch, so
+//   queue  : points still running push their four input scalars and loop state (w1,w2,d1,d2) to a circular queue.
+//   phase 2: whenever the queue holds >= 256 entries the block runs the remaining iterations on the OLDEST 256, so
 //            every warp is dense instead of idling on the ~30 % of lanes that need all 10 solves; the remainder is
 //            flushed after the last tile.
+//   mirrors: with result mirrors (multi-GPU gather) a tile is copied to the peers, fully coalesced, as soon as no point
+//            of it is queued any more -- FIFO order makes that "every tile before the one of the oldest queued entry" --
+//            instead of repeating phase 2's scattered 8-byte stores over NVLink.
 constexpr int kPhase1 = 2;
-constexpr int kQueueCap = 2 * kThreads;
+constexpr int kQueueCap = 2 * kThreads;                  // power of two
 
 // Shared memory of one k_iterative_ls CTA (dynamic: 49 KB in the all-double mode, just above the static limit).
 template <typename TI, typename TC, typename TO>
@@ -231,13 +234,13 @@ struct IterSmem {
     TC q_state[8][kQueueCap];                // queue: a b c d w1 w2 d1 d2
     int64_t q_idx[kQueueCap];                //        global point index
     TO stage[kWarps][96];                    // coalesced (n,3) store staging
-    int q_count;
+    unsigned int q_tail;                     // total number of pushes so far (slot = position & (kQueueCap-1))
 };
 
 template <typename TC, typename TO>
 __device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*q_state)[kQueueCap], const int64_t* q_idx,
                                                int slot, TO* __restrict__ x, int32_t* __restrict__ status,
-                                               TC tolerance, int py_semantics, const Mirrors& mir) {
+                                               TC tolerance, int py_semantics) {
     const TC a = q_state[0][slot], b = q_state[1][slot], c = q_state[2][slot], d = q_state[3][slot];
     TC w1 = q_state[4][slot], w2 = q_state[5][slot], d1 = q_state[6][slot], d2 = q_state[7][slot], d1n = d1, d2n = d2;
     const int64_t dst = q_idx[slot];
@@ -252,11 +255,22 @@ __device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*
     x[3 * dst + 0] = static_cast<TO>(xs[0]);
     x[3 * dst + 1] = static_cast<TO>(xs[1]);
     x[3 * dst + 2] = static_cast<TO>(xs[2]);
-    for (int r = 0; r < mir.count; ++r) {
-        TO* __restrict__ peer = static_cast<TO*>(mir.x[r]) + 3 * dst;
-        peer[0] = static_cast<TO>(xs[0]); peer[1] = static_cast<TO>(xs[1]); peer[2] = static_cast<TO>(xs[2]);
+    status[dst] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+}
+
+// Copy one finished 256-point tile of x / status from local HBM to every mirror (whole CTA, coalesced).
+template <typename TO>
+__device__ __forceinline__ void mirror_tile(const TO* __restrict__ x, const int32_t* __restrict__ status, const Mirrors& mir,
+                                            int64_t base, int64_t n) {
+    const int cnt = (n - base) >= kThreads ? kThreads : static_cast<int>(n - base);
+    for (int idx = threadIdx.x; idx < cnt * 3; idx += kThreads) {
+        const TO v = __ldcg(x + base * 3 + idx);
+        for (int r = 0; r < mir.count; ++r) static_cast<TO*>(mir.x[r])[base * 3 + idx] = v;
     }
-    store_status<int32_t>(status, mir, dst, iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n)));
+    if (static_cast<int>(threadIdx.x) < cnt) {
+        const int32_t v = __ldcg(status + base + threadIdx.x);
+        for (int r = 0; r < mir.count; ++r) static_cast<int32_t*>(mir.status[r])[base + threadIdx.x] = v;
+    }
 }
 
 template <typename TI, typename TC, typename TO, class PRE = PreNone>
@@ -267,13 +281,17 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
                const __grid_constant__ Mirrors mir) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IterSmem<TI, TC, TO>& sm = *reinterpret_cast<IterSmem<TI, TC, TO>*>(smem_raw);
-    auto& pre = sm.pre; auto& q_state = sm.q_state; auto& q_idx = sm.q_idx; auto& stage = sm.stage; int& q_count = sm.q_count;
+    auto& pre = sm.pre; auto& q_state = sm.q_state; auto& q_idx = sm.q_idx; auto& stage = sm.stage;
+    const Mirrors local_only = {0, 0, {nullptr}, {nullptr}};       // this kernel mirrors whole tiles, see above
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
-    if (threadIdx.x == 0) q_count = 0;
+    const int64_t first = static_cast<int64_t>(blockIdx.x) * kThreads;
+    if (threadIdx.x == 0) sm.q_tail = 0u;
     __syncthreads();
-    int64_t tile = static_cast<int64_t>(blockIdx.x) * kThreads;
-    int count = 0;                                       // queue length, identical in every thread
+    int64_t tile = first;
+    int64_t mirrored = first;                            // next tile of this CTA to copy to the mirrors
+    unsigned int head = 0u;                              // position of the oldest queued entry  } identical in
+    int count = 0;                                       // queue length                         } every thread
     pre.issue(u1, u2, tile + threadIdx.x, n);
     for (; tile < n; tile += stride) {
         const int64_t i = tile + threadIdx.x;
@@ -294,11 +312,11 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
             const bool pending = (it < 0) && (i < n);
             const unsigned ball = __ballot_sync(0xffffffffu, pending);
             if (ball) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&q_count, __popc(ball));
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(&sm.q_tail, static_cast<unsigned int>(__popc(ball)));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (pending) {
-                    const int slot = base + __popc(ball & ((1u << lane) - 1u));
+                    const int slot = static_cast<int>((base + __popc(ball & ((1u << lane) - 1u))) & (kQueueCap - 1));
                     q_state[0][slot] = a; q_state[1][slot] = b; q_state[2][slot] = c; q_state[3][slot] = d;
                     q_state[4][slot] = w1; q_state[5][slot] = w2; q_state[6][slot] = d1; q_state[7][slot] = d2;
                     q_idx[slot] = i;
@@ -306,21 +324,35 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
             }
             // finished points leave through the coalesced path (pending lanes write a placeholder that phase 2 overwrites)
             store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                             static_cast<TO>(xs[2]), stage[warp], mir);
-            if (i < n && !pending) store_status<int32_t>(status, mir, i, iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n)));
-            // every thread learns how many points this tile queued (the barrier also publishes the queue entries);
-            // the queue length lives in a register so the drain decision is uniform without re-reading q_count
+                             static_cast<TO>(xs[2]), stage[warp], local_only);
+            if (i < n && !pending) status[i] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+            // every thread learns how many points this tile queued (the barrier also publishes the queue entries and
+            // this tile's stores); head / count live in registers so the drain decision is uniform
             count += __syncthreads_count(pending);
         }
         if (count >= kThreads) {                         // count < kQueueCap: <= kThreads-1 left over + kThreads pushed
-            count -= kThreads;
-            if (threadIdx.x == 0) q_count = count;       // nobody pushes before the barrier below
-            iter_ls_phase2<TC, TO>(cams, q_state, q_idx, count + threadIdx.x, x, status, tolerance, py_semantics, mir);
-            __syncthreads();
+            iter_ls_phase2<TC, TO>(cams, q_state, q_idx, static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x, status,
+                                   tolerance, py_semantics);
+            head += kThreads; count -= kThreads;
+            __syncthreads();                             // the drained slots may be overwritten, the results are visible
+        }
+        if (mir.count) {
+            // tiles before the one that holds the oldest queued point are final (pushes are in tile order)
+            int64_t safe = tile + stride;
+            if (count > 0) {
+                const int64_t oldest = q_idx[head & (kQueueCap - 1)];
+                safe = oldest - ((oldest - first) % stride);
+            }
+            for (; mirrored < safe; mirrored += stride) mirror_tile<TO>(x, status, mir, mirrored, n);
         }
     }
     if (static_cast<int>(threadIdx.x) < count)
-        iter_ls_phase2<TC, TO>(cams, q_state, q_idx, threadIdx.x, x, status, tolerance, py_semantics, mir);
+        iter_ls_phase2<TC, TO>(cams, q_state, q_idx, static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x, status,
+                               tolerance, py_semantics);
+    if (mir.count) {
+        __syncthreads();
+        for (; mirrored < n; mirrored += stride) mirror_tile<TO>(x, status, mir, mirrored, n);
+    }
 }
 
 // ---- linear_eigen_triangulation (triangulation.py:6-25) --------------------------------------------------------
