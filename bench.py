@@ -66,6 +66,13 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="N > 1: all-gather x over NCCL inside the timed step")
+    ap.add_argument("--separate-eval", action="store_true",
+                    help="run the two-view reprojection / good-mask evaluation as its own pass after every solver "
+                         "(trgl_pair_reproj_async) instead of in the solver kernels' epilogue (trgl_set_fused_eval)")
+    ap.add_argument("--fuse-ls-eval", action="store_true",
+                    help="also fuse the evaluation into linear_LS.  Default: the three FP64-bound solvers carry it in their "
+                         "epilogue (it hides behind the solve), the HBM-bound linear_LS is followed by the stand-alone "
+                         "pass (fusing it there turns an HBM-bound kernel into an FP64-bound one for an 11 %% gain)")
     ap.add_argument("--p2p-gather", action="store_true",
                     help="N > 1: gather x/status by storing into every peer's buffer from inside the solver kernels "
                          "(CUDA IPC + NVLink, sharding.PeerGather) instead of a separate NCCL all-gather")
@@ -232,6 +239,10 @@ def run_ours(args, rank, world, local_rank):
     ev = [tc.Event() for _ in range(9)]
     d_sums = tc.DeviceArray((4, 4), np.float64)      # per-solver reprojection sums, finished on the device
 
+    fused = {s: tc.FusedEval(n, np.float64, 0, np.inf, want_errors=False, want_good=False, sums=d_sums.view(4 * si, (4,)))
+             for si, s in enumerate(SOLVERS)
+             if not args.separate_eval and (s != "linear_LS" or args.fuse_ls_eval)}
+
     def device_step(timed):
         k = 0
         sums_total = 0.0
@@ -239,20 +250,24 @@ def run_ours(args, rank, world, local_rank):
             ev[k].record(); k += 1
             if peer is not None:
                 peer[name].arm()
+            fe = fused.get(name)                     # evaluation in the solver's epilogue: no second pass over x, u1, u2
             if name == "linear_eigen":
-                tc.linear_eigen(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name])
+                tc.linear_eigen(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name], evaluate=fe)
             elif name == "linear_LS":
-                tc.linear_ls(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name])
+                tc.linear_ls(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name], evaluate=fe)
             elif name == "iterative_LS":
-                tc.iterative_ls(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name])
+                tc.iterative_ls(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name], evaluate=fe)
             else:
-                tc.polynomial(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name], check_all_nan=False)
+                tc.polynomial(d_u1, P1, d_u2, P2, x=d_x[name], status=d_st[name], check_all_nan=False, evaluate=fe)
             ev[k].record(); k += 1
         for si, name in enumerate(SOLVERS):
+            if name in fused:
+                continue
             # asynchronous variant: the grid-level sums are finished inside the kernel, nothing to wait for per solver
             tc.pair_reproj(d_x[name], d_u1, P1, d_u2, P2, d_st[name], 0, np.inf, want_errors=False, want_good=False,
                            sums_device=d_sums.view(4 * si, (4,)))
-            if gather_buf is not None:
+        if gather_buf is not None:
+            for name in SOLVERS:
                 dist.all_gather_into_tensor(gather_buf, d_x[name])
         ev[8].record()
         sums_total = float(d_sums.to_host()[:, 0:2].sum())      # the step's result comes back to the host (synchronises)
@@ -339,8 +354,11 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "synthetic 2-camera rig (%s), %d points per GPU, all four solvers FP64 + fused two-view "
-                               "reprojection error / good mask after each (BASELINE.json configs[1])" % (args.rig, n),
+        "config": {"workload": "synthetic 2-camera rig (%s), %d points per GPU, all four solvers FP64 + two-view "
+                               "reprojection error / good mask %s (BASELINE.json configs[1])"
+                               % (args.rig, n, "as its own pass after each" if args.separate_eval else
+                                  ("in each solver kernel's epilogue" if args.fuse_ls_eval else
+                                   "in the epilogue of the three FP64-bound solver kernels, as its own pass after linear_LS")),
                    "points_per_gpu": n, "rig": args.rig, "sharding": "contiguous point ranges, no data-path collective"
                    + (", NCCL all-gather of x" if args.gather else "")
                    + (", x and status gathered by peer stores from inside the solver kernels (CUDA IPC / NVLink)"

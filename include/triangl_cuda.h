@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define TRGL_VERSION 103
+#define TRGL_VERSION 104
 
 enum { TRGL_F64 = 0, TRGL_F32IO = 1, TRGL_F32 = 2, TRGL_F64_OUT32 = 3, TRGL_F32_OUT64 = 4 };
 enum { TRGL_MEM_HOST = 0, TRGL_MEM_DEVICE = 1 };
@@ -129,6 +129,16 @@ int trgl_pair_reproj_async(const void* x, const void* u1, const void* u2, const 
                            const void* status, int status_is_i32, int min_status, double max_sq_err,
                            void* err1, void* err2, uint8_t* good, double* sums_device,
                            int64_t n, int mode, void* stream);
+
+/* The same evaluation FUSED into the solver kernel: request it with trgl_set_fused_eval, then make a device-mode solver
+ * call (any of the four, or their _px twins) from the same host thread; the request applies to that one call.  The kernel
+ * evaluates every point from the registers the solve just produced -- x rounded to its storage type exactly as a separate
+ * pass would read it back, the normalised observations, the status just written, the call's own P1 / P2 -- so err1, err2
+ * and good are bit-identical to trgl_pair_reproj, while the second pass over x, u1, u2 and status (57-60 B/point)
+ * disappears.  sums_device: 4 doubles in DEVICE memory (same meaning as `sums` above), finished inside the kernel by a
+ * last-block reduction; nothing is synchronised.  err1 / err2 (n elements of x's dtype) and good (n bytes) may be NULL.
+ * Supported where u and x have the same storage type (TRGL_F64, TRGL_F32IO, TRGL_F32); device buffers only. */
+int trgl_set_fused_eval(int min_status, double max_sq_err, void* err1, void* err2, uint8_t* good, double* sums_device);
 
 /* ---- input normalisation in front of the solvers ---- */
 

@@ -4,24 +4,21 @@
 #include "trgl_device.cuh"
 #include "trgl_hartley_sturm.cuh"
 #include "trgl_tma.cuh"
+#include "trgl_eval.cuh"
 
 namespace trgl {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 
 // ---- linear_LS_triangulation (triangulation.c:65-83) -----------------------------------------------------------
 // Per point: straight-line fast solve, (rare) careful redo, immediate coalesced store.  Measured on B200: storing each
 // point as soon as it is solved beats "solve all PPT points, then store" by 0.81 vs 0.65 of the HBM peak, and keeping
 // the 4x4 row block alive for an inline refinement path costs 2x (0.39).
-template <typename TI, typename TC, typename TO, int PPT, class PRE = PreNone>
-__global__ void __launch_bounds__(kThreads)
-k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-            TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ PRE pre,
-            const __grid_constant__ Mirrors mir) {
-    __shared__ TO stage[kWarps][96];
+template <typename TI, typename TC, typename TO, int PPT, class PRE, bool EVAL, class MIR>
+__device__ __forceinline__ void ls_tile(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC>& cams,
+                                        TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const PRE& pre,
+                                        const MIR& mir, const EvalArg<EVAL>& ev, const int64_t block_base,
+                                        TO* __restrict__ stage_warp, double (&acc)[4]) {
     const int warp = threadIdx.x >> 5;
-    const int64_t block_base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT);
     TC in[PPT][4];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
@@ -40,9 +37,30 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
         if constexpr (PRE::kActive) pre.template apply<TI, TC>(in[p][0], in[p][1], in[p][2], in[p][3]);
         if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs))
             solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
-        store_x_warp<TO>(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
-                         static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage[warp], mir);
-        if (i < n) store_status<uint8_t>(status, mir, i, 1);
+        store_x_warp(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
+                         static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage_warp, mir);
+        if (i < n) store_status(status, mir, i, static_cast<uint8_t>(1));
+        fused_eval_point<EVAL, TO, TC>(ev, i < n, i, in[p][0], in[p][1], in[p][2], in[p][3], xs, 1, acc);
+    }
+}
+
+template <typename TI, typename TC, typename TO, int PPT, class PRE = PreNone, bool EVAL = false, class MIR = Mirrors>
+__global__ void __launch_bounds__(kThreads)
+k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
+            TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ PRE pre,
+            const __grid_constant__ MIR mir, const __grid_constant__ EvalArg<EVAL> ev) {
+    __shared__ TO stage[kWarps][96];
+    double acc[4] = {0, 0, 0, 0};
+    if constexpr (EVAL) {
+        // grid-stride loop over tiles (capped grid): the evaluation sums are reduced per CTA at the end of the kernel
+        const int64_t stride = static_cast<int64_t>(gridDim.x) * (kThreads * PPT);
+        for (int64_t base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT); base < n; base += stride)
+            ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR>(u1, u2, cams, x, status, n, pre, mir, ev, base, stage[threadIdx.x >> 5], acc);
+        fused_eval_finish<EVAL>(ev, acc);
+    } else {
+        // one tile per CTA
+        ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR>(u1, u2, cams, x, status, n, pre, mir, ev,
+                                            static_cast<int64_t>(blockIdx.x) * (kThreads * PPT), stage[threadIdx.x >> 5], acc);
     }
 }
 
@@ -100,9 +118,9 @@ k_linear_ls_ring(const TI* __restrict__ u1, const TI* __restrict__ u2, const __g
             TC xs[3];
             if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs))
                 solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
-            store_x_warp<TO>(x, tile + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+            store_x_warp(x, tile + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
                              static_cast<TO>(xs[2]), stage + warp * 96, mir);
-            if (i < n) store_status<uint8_t>(status, mir, i, 1);
+            if (i < n) store_status(status, mir, i, static_cast<uint8_t>(1));
         }
         if (++slot == DEPTH) slot = 0;
     }
@@ -170,9 +188,9 @@ k_linear_ls_tma(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gr
             TC xs[3];
             if (!ls_point_fast<TC>(cams, a, b, c, d, xs))
                 solve_point_careful<TC>(cams, a, b, c, d, TC(1), TC(1), xs);
-            store_x_warp<TO>(x, tile_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
+            store_x_warp(x, tile_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
                              static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage_out + warp * 96, mir);
-            if (i < n) store_status<uint8_t>(status, mir, i, 1);
+            if (i < n) store_status(status, mir, i, static_cast<uint8_t>(1));
         }
         __syncthreads();                        // every thread has consumed stage s
         if (threadIdx.x == 0) {
@@ -237,10 +255,10 @@ struct IterSmem {
     unsigned int q_tail;                     // total number of pushes so far (slot = position & (kQueueCap-1))
 };
 
-template <typename TC, typename TO>
+template <typename TC, typename TO, bool EVAL>
 __device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*q_state)[kQueueCap], const int64_t* q_idx,
                                                int slot, TO* __restrict__ x, int32_t* __restrict__ status,
-                                               TC tolerance, int py_semantics) {
+                                               TC tolerance, int py_semantics, const EvalArg<EVAL>& ev, double (&acc)[4]) {
     const TC a = q_state[0][slot], b = q_state[1][slot], c = q_state[2][slot], d = q_state[3][slot];
     TC w1 = q_state[4][slot], w2 = q_state[5][slot], d1 = q_state[6][slot], d2 = q_state[7][slot], d1n = d1, d2n = d2;
     const int64_t dst = q_idx[slot];
@@ -255,7 +273,9 @@ __device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*
     x[3 * dst + 0] = static_cast<TO>(xs[0]);
     x[3 * dst + 1] = static_cast<TO>(xs[1]);
     x[3 * dst + 2] = static_cast<TO>(xs[2]);
-    status[dst] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+    const int st = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+    status[dst] = st;
+    fused_eval_point<EVAL, TO, TC>(ev, true, dst, a, b, c, d, xs, st, acc);
 }
 
 // Copy one finished 256-point tile of x / status from local HBM to every mirror (whole CTA, coalesced).
@@ -273,12 +293,12 @@ __device__ __forceinline__ void mirror_tile(const TO* __restrict__ x, const int3
     }
 }
 
-template <typename TI, typename TC, typename TO, class PRE = PreNone>
+template <typename TI, typename TC, typename TO, class PRE = PreNone, bool EVAL = false>
 __global__ void __launch_bounds__(kThreads, 2)
 k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
                const TC tolerance, const int py_semantics, const __grid_constant__ PRE pre_stage,
-               const __grid_constant__ Mirrors mir) {
+               const __grid_constant__ Mirrors mir, const __grid_constant__ EvalArg<EVAL> ev) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IterSmem<TI, TC, TO>& sm = *reinterpret_cast<IterSmem<TI, TC, TO>*>(smem_raw);
     auto& pre = sm.pre; auto& q_state = sm.q_state; auto& q_idx = sm.q_idx; auto& stage = sm.stage;
@@ -292,6 +312,7 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
     int64_t mirrored = first;                            // next tile of this CTA to copy to the mirrors
     unsigned int head = 0u;                              // position of the oldest queued entry  } identical in
     int count = 0;                                       // queue length                         } every thread
+    double acc[4] = {0, 0, 0, 0};                        // fused evaluation sums of this thread
     pre.issue(u1, u2, tile + threadIdx.x, n);
     for (; tile < n; tile += stride) {
         const int64_t i = tile + threadIdx.x;
@@ -323,16 +344,20 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
                 }
             }
             // finished points leave through the coalesced path (pending lanes write a placeholder that phase 2 overwrites)
-            store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+            store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
                              static_cast<TO>(xs[2]), stage[warp], local_only);
-            if (i < n && !pending) status[i] = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+            if (i < n && !pending) {
+                const int st = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+                status[i] = st;
+                fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, st, acc);
+            }
             // every thread learns how many points this tile queued (the barrier also publishes the queue entries and
             // this tile's stores); head / count live in registers so the drain decision is uniform
             count += __syncthreads_count(pending);
         }
         if (count >= kThreads) {                         // count < kQueueCap: <= kThreads-1 left over + kThreads pushed
-            iter_ls_phase2<TC, TO>(cams, q_state, q_idx, static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x, status,
-                                   tolerance, py_semantics);
+            iter_ls_phase2<TC, TO, EVAL>(cams, q_state, q_idx, static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x,
+                                         status, tolerance, py_semantics, ev, acc);
             head += kThreads; count -= kThreads;
             __syncthreads();                             // the drained slots may be overwritten, the results are visible
         }
@@ -347,12 +372,13 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         }
     }
     if (static_cast<int>(threadIdx.x) < count)
-        iter_ls_phase2<TC, TO>(cams, q_state, q_idx, static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x, status,
-                               tolerance, py_semantics);
+        iter_ls_phase2<TC, TO, EVAL>(cams, q_state, q_idx, static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x, status,
+                                     tolerance, py_semantics, ev, acc);
     if (mir.count) {
         __syncthreads();
         for (; mirrored < n; mirrored += stride) mirror_tile<TO>(x, status, mir, mirrored, n);
     }
+    fused_eval_finish<EVAL>(ev, acc);
 }
 
 // ---- linear_eigen_triangulation (triangulation.py:6-25) --------------------------------------------------------
@@ -505,11 +531,13 @@ __device__ __forceinline__ void eigen_point(const Cams<TC>& cams, TC u1x, TC u1y
 
 // Persistent CTAs: grid-stride loop over 256-point tiles, the next tile's inputs are prefetched into registers while the
 // current tile is solved (the solve is ~700 instructions per point, so one tile of lookahead hides the HBM latency).
-template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone>
+template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
 __global__ void __launch_bounds__(kThreads, 2)
 k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord,
-               const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir) {
+               const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
+               const __grid_constant__ EvalArg<EVAL> ev) {
+    double acc[4] = {0, 0, 0, 0};
     __shared__ TO stage[kWarps][96];
     __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
     const int warp = threadIdx.x >> 5;
@@ -524,20 +552,24 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
         TC xs[3]; bool good;
         eigen_point<TC, ROWS>(cams, a, b, c, d, max_coord, xs, good);
-        store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+        store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
                          static_cast<TO>(xs[2]), stage[warp], mir);
-        if (i < n) store_status<uint8_t>(status, mir, i, good ? 1 : 0);
+        if (i < n) store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
+        fused_eval_point<EVAL, TO, TC>(ev, i < n, i, a, b, c, d, xs, good ? 1 : 0, acc);
     }
+    fused_eval_finish<EVAL>(ev, acc);
 }
 
 // ---- polynomial_triangulation (triangulation.py:198-232) -------------------------------------------------------
 // Hartley-Sturm correction of the match (cv2.correctMatches) followed by the linear-eigen solve, fused.
-template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone>
+template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
 __global__ void __launch_bounds__(kThreads, 2)
 k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams, const __grid_constant__ HSParams hs,
              TO* __restrict__ x, uint8_t* __restrict__ status, TI* __restrict__ u1c, TI* __restrict__ u2c,
              unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord,
-             const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir) {
+             const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
+             const __grid_constant__ EvalArg<EVAL> ev) {
+    double acc[4] = {0, 0, 0, 0};
     __shared__ TO stage[kWarps][96];
     __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
     const int warp = threadIdx.x >> 5;
@@ -567,9 +599,11 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
         TC xs[3]; bool good;
         eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
                               static_cast<TC>(r2y), max_coord, xs, good);
-        store_x_warp<TO>(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+        store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
                          static_cast<TO>(xs[2]), stage[warp], mir);
-        if (i < n) store_status<uint8_t>(status, mir, i, good ? 1 : 0);
+        if (i < n) store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
+        // the harness / SLAM evaluate against the ORIGINAL observations, not the corrected ones
+        fused_eval_point<EVAL, TO, TC>(ev, i < n, i, a, b, c, d, xs, good ? 1 : 0, acc);
     }
     // one flag update per CTA (two words shared by the whole grid: per-warp atomics would all hit the same L2 line)
     const int f1 = __syncthreads_or(any1), f2 = __syncthreads_or(any2);
@@ -577,6 +611,7 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
         if (f1) atomicOr(&not_nan_count[0], 1u);
         if (f2) atomicOr(&not_nan_count[1], 1u);
     }
+    fused_eval_finish<EVAL>(ev, acc);
 }
 
 // ---- cv2.undistortPoints as a standalone kernel (slam2.py:551-552; output dtype = input dtype) ---------------------

@@ -5,6 +5,7 @@
 //                    slam2.py:556,589 status filters)
 #pragma once
 #include "trgl_device.cuh"
+#include "trgl_eval.cuh"
 #include <cmath>
 
 namespace trgl {
@@ -35,53 +36,6 @@ inline ProjParams make_proj_params(const double* K, const double* dist, const do
     p.k1 = dist ? dist[0] : 0.0; p.k2 = dist ? dist[1] : 0.0; p.p1 = dist ? dist[2] : 0.0;
     p.p2 = dist ? dist[3] : 0.0; p.k3 = dist ? dist[4] : 0.0;
     return p;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
-
-template <int NV>
-__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ partials) {
-    __shared__ double sm[NV][kThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const double s = warp_sum(v[k]);
-        if (lane == 0) sm[k][warp] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) s += sm[threadIdx.x][w];
-        partials[blockIdx.x * NV + threadIdx.x] = s;
-    }
-}
-
-// Same, followed by the grid-level sum inside the kernel when `final_out` is given: the last CTA to arrive (ticket on
-// `counter`, which it resets for the next launch) adds the per-block partials in block order -- the order the host uses --
-// and writes NV doubles to device memory, so the caller needs no synchronisation to own the result in stream order.
-template <int NV>
-__device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], double* __restrict__ partials,
-                                                      unsigned int* __restrict__ counter, double* __restrict__ final_out) {
-    block_reduce_store<NV>(v, partials);
-    if (final_out == nullptr) return;
-    __shared__ bool is_last;
-    __threadfence();                                   // the partials of this CTA are visible device-wide ...
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);     // ... before its ticket is
-    __syncthreads();
-    if (is_last) {
-        if (threadIdx.x < NV) {
-            double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[b * NV + threadIdx.x]);
-            final_out[threadIdx.x] = s;
-        }
-        if (threadIdx.x == 0) *counter = 0u;
-    }
 }
 
 template <typename TX, typename TP>
@@ -130,25 +84,7 @@ k_pair_reproj(const TO* __restrict__ x, const TI* __restrict__ u1, const TI* __r
         double a1, b1, a2, b2;
         load_uv<double>(u1, i, a1, b1);
         load_uv<double>(u2, i, a2, b2);
-        double e[2], depth[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const double* P = c == 0 ? cams.P1 : cams.P2;
-            const double px = fma(P[0], X, fma(P[1], Y, fma(P[2], Z, P[3])));
-            const double py = fma(P[4], X, fma(P[5], Y, fma(P[6], Z, P[7])));
-            const double pz = fma(P[8], X, fma(P[9], Y, fma(P[10], Z, P[11])));
-            const double iz = 1.0 / pz;
-            const double dx = fma(px, iz, -(c == 0 ? a1 : a2)), dy = fma(py, iz, -(c == 0 ? b1 : b2));
-            e[c] = fma(dx, dx, dy * dy);
-            depth[c] = pz;
-        }
-        const bool st_ok = static_cast<int>(status[i]) > min_status;
-        const bool g = st_ok && (e[0] <= max_sq_err) && (e[1] <= max_sq_err) && (depth[0] > 0.0) && (depth[1] > 0.0);
-        if (err1) err1[i] = static_cast<TO>(e[0]);
-        if (err2) err2[i] = static_cast<TO>(e[1]);
-        if (good) good[i] = g ? 1 : 0;
-        if (g) { acc[0] += e[0]; acc[1] += e[1]; acc[2] += 1.0; }
-        if (st_ok) acc[3] += 1.0;
+        eval_point<TO>(cams, min_status, max_sq_err, a1, b1, a2, b2, X, Y, Z, static_cast<int>(status[i]), i, err1, err2, good, acc);
     }
     block_reduce_finalize<4>(acc, partials, counter, final_out);
 }

@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 
 using namespace trgl;
@@ -30,6 +31,10 @@ Mirrors take_mirrors() {
     return m;
 }
 const Mirrors kNoMirrors = {0, 0, {nullptr}, {nullptr}};
+
+// Fused evaluation requested for the NEXT device-mode solver call of this host thread (trgl_set_fused_eval).
+struct PendingEval { bool armed; int min_status; double max_sq_err; void* err1; void* err2; uint8_t* good; double* sums; };
+thread_local PendingEval g_next_eval = {false, 0, 0.0, nullptr, nullptr, nullptr, nullptr};
 
 int fail(int code, const char* what) {
     g_err = what;
@@ -150,40 +155,49 @@ int launch_ls_ring(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8
     return TRGL_OK;
 }
 
-template <typename TI, typename TC, typename TO>
-void launch_ls_direct(int ppt, const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n,
-                      cudaStream_t s, const Undist2* pre, const Mirrors& mir) {
-    if (pre) {      // pixel inputs: the undistortion makes the kernel FP64-bound, one point per thread is enough
-        const PreUndistort pu{*pre};
-        k_linear_ls<TI, TC, TO, 1, PreUndistort><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, pu, mir);
-        return;
-    }
-    const PreNone none{};
-    if (ppt == 1) k_linear_ls<TI, TC, TO, 1><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, none, mir);
-    else if (ppt == 2) k_linear_ls<TI, TC, TO, 2><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n, none, mir);
-    else k_linear_ls<TI, TC, TO, 4><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, none, mir);
+// ---- pre-stage / fused-evaluation dispatch -----------------------------------------------------------------------
+// f(prearg) is called with PreUndistort{...} or PreNone{}; g(std::bool_constant<EVAL>, EvalArg<EVAL>) likewise.  The
+// fused evaluation is instantiated for the modes whose input and output storage types agree (F64, F32IO, F32).
+template <typename F>
+void with_pre(const Undist2* pre, F&& f) {
+    if (pre) f(PreUndistort{*pre}); else f(PreNone{});
+}
+template <typename F>
+void with_eval(const FusedEval* ev, F&& f) {
+    if (ev) f(std::true_type{}, EvalArg<true>{*ev}); else f(std::false_type{}, EvalArg<false>{});
+}
+template <typename TI, typename TO, bool EV>
+constexpr bool eval_supported() { return !EV || std::is_same<TI, TO>::value; }
+int eval_unsupported() { return fail(TRGL_E_BADARG, "the fused evaluation needs u and x of the same storage type (F64, F32IO, F32)"); }
+
+// Persistent grid of the evaluation-fused linear_LS kernel (its block partials must fit the reduction scratch).
+unsigned ls_eval_grid(int64_t n, int per_block) {
+    if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    const int64_t tiles = (n + per_block - 1) / per_block;
+    const int64_t cap = static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148) * 8;
+    return static_cast<unsigned>(tiles < cap ? tiles : cap);
 }
 
 int launch_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
-                     int64_t n, int mode, cudaStream_t s, const Undist2* pre = nullptr, const Mirrors& mir = kNoMirrors) {
+                     int64_t n, int mode, cudaStream_t s, const Undist2* pre = nullptr, const Mirrors& mir = kNoMirrors,
+                     const FusedEval* ev = nullptr) {
     if (n == 0) return TRGL_OK;
     const int ppt = g_ppt.load();
     int variant = g_variant.load();
-    // auto: per-thread vector loads with 4 points in flight.  Measured on B200 (profiles/r01b_sweep_100M.jsonl): 0.84 of
-    // the measured copy peak at 100 M points vs 0.74 for the bulk-async pipeline (variants 1-6, kept selectable), and
-    // 0.82 at 10 M points.
+    // auto: per-thread vector loads with 4 points in flight.  Measured on B200 (profiles/): 0.84-0.86 of the measured
+    // copy peak at 10 M - 100 M points vs 0.74 for the bulk-async pipeline (variants 1-6) and 0.78 for the per-thread
+    // cp.async ring (7-12), both kept selectable.
     // FP32 arithmetic mode: the per-thread cp.async ring (2 points/thread, 4 stages) is 1.18x faster (0.63 vs 0.54 of the
     // copy peak at 29 B/point; the kernel is FP32-issue bound there and the ring frees the load registers).
     if (variant < 0) variant = (mode == TRGL_F32) ? 8 : 0;
     // cp.async.bulk needs 16-byte aligned global addresses; fall back to per-thread loads otherwise
     if ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & 15) variant = 0;
-    if (pre) variant = 0;
-    if (variant >= 7 && ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & 7)) variant = 0;
+    if (pre || ev) variant = 0;                    // the pre-stage and the fused evaluation live in the direct kernel
+    int rc = TRGL_OK;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
         TO* xo = static_cast<TO*>(x);
-        int rc = TRGL_OK;
         switch (variant) {
             case 1: rc = launch_ls_tma<TI, TC, TO, 2, 4, 3>(a, b, cams, xo, status, n, s, mir); break;
             case 2: rc = launch_ls_tma<TI, TC, TO, 4, 3, 2>(a, b, cams, xo, status, n, s, mir); break;
@@ -197,10 +211,29 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
             case 10: rc = launch_ls_ring<TI, TC, TO, 4, 3, 2>(a, b, cams, xo, status, n, s, mir); break;
             case 11: rc = launch_ls_ring<TI, TC, TO, 2, 4, 3>(a, b, cams, xo, status, n, s, mir); break;
             case 12: rc = launch_ls_ring<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s, mir); break;
-            default: launch_ls_direct<TI, TC, TO>(ppt, a, b, cams, xo, status, n, s, pre, mir);
+            default:
+                with_eval(ev, [&](auto E, auto evarg) {
+                    constexpr bool EV = decltype(E)::value;
+                    if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
+                        if (pre) {      // pixel inputs: the undistortion makes the kernel FP64-bound, one point per thread
+                            const unsigned grid = EV ? ls_eval_grid(n, kThreads) : grid_for(n, kThreads);
+                            k_linear_ls<TI, TC, TO, 1, PreUndistort, EV><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreUndistort{*pre}, mir, evarg);
+                        } else if (!EV && ppt == 4 && mir.count == 0) {
+                            // THE hot path: no pre-stage, no epilogue, no mirrors compiled in
+                            k_linear_ls<TI, TC, TO, 4, PreNone, false, NoMirrors><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, NoMirrors{}, EvalArg<false>{});
+                        } else if (EV || ppt == 4) {
+                            const unsigned grid = EV ? ls_eval_grid(n, kThreads * 4) : grid_for(n, kThreads * 4);
+                            k_linear_ls<TI, TC, TO, 4, PreNone, EV><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, evarg);
+                        } else if (ppt == 2) {
+                            k_linear_ls<TI, TC, TO, 2, PreNone, false><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, EvalArg<false>{});
+                        } else {
+                            k_linear_ls<TI, TC, TO, 1, PreNone, false><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, EvalArg<false>{});
+                        }
+                    }
+                });
         }
-        if (rc) return rc;
     })
+    if (rc) return rc;
     g_launches++;
     CK(cudaGetLastError());
     return TRGL_OK;
@@ -208,54 +241,58 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
 
 int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
                         int64_t n, double tol, int semantics, int mode, cudaStream_t s, const Undist2* pre = nullptr,
-                        const Mirrors& mir = kNoMirrors) {
+                        const Mirrors& mir = kNoMirrors, const FusedEval* ev = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
+    int rc = TRGL_OK;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         constexpr size_t smem = sizeof(IterSmem<TI, TC, TO>);
-        if (pre) {
-            auto kern = k_iterative_ls<TI, TC, TO, PreUndistort>;
-            kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
-                static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
-                static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, PreUndistort{*pre}, mir);
-        } else {
-            auto kern = k_iterative_ls<TI, TC, TO, PreNone>;
-            kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
-                static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
-                static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, PreNone{}, mir);
-        }
+        with_pre(pre, [&](auto prearg) {
+            using PRE = decltype(prearg);
+            with_eval(ev, [&](auto E, auto evarg) {
+                constexpr bool EV = decltype(E)::value;
+                if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
+                    auto kern = k_iterative_ls<TI, TC, TO, PRE, EV>;
+                    kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
+                        static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
+                        static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, prearg, mir, evarg);
+                }
+            });
+        });
     })
+    if (rc) return rc;
     g_launches++;
     CK(cudaGetLastError());
     return TRGL_OK;
 }
 
-#define EIGEN_LAUNCH(ROWS, PRE, prearg)                                                                        \
-    {                                                                                                          \
-        auto kern = k_linear_eigen<TI, TC, TO, ROWS, PRE>;                                                     \
-        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n,         \
-                                                           static_cast<TC>(maxc), prearg, mir);                \
-    }
-#define POLY_LAUNCH(ROWS, PRE, prearg)                                                                         \
-    {                                                                                                          \
-        auto kern = k_polynomial<TI, TC, TO, ROWS, PRE>;                                                       \
-        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status,        \
-                                                           static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, \
-                                                           static_cast<TC>(maxc), prearg, mir);                \
-    }
-
 int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                         int64_t n, double maxc, int rows, int mode, cudaStream_t s, const Undist2* pre = nullptr,
-                        const Mirrors& mir = kNoMirrors) {
+                        const Mirrors& mir = kNoMirrors, const FusedEval* ev = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
+    int rc = TRGL_OK;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
-        if (pre) { if (rows == 4) EIGEN_LAUNCH(4, PreUndistort, PreUndistort{*pre}) else EIGEN_LAUNCH(6, PreUndistort, PreUndistort{*pre}) }
-        else { if (rows == 4) EIGEN_LAUNCH(4, PreNone, PreNone{}) else EIGEN_LAUNCH(6, PreNone, PreNone{}) }
+        with_pre(pre, [&](auto prearg) {
+            using PRE = decltype(prearg);
+            with_eval(ev, [&](auto E, auto evarg) {
+                constexpr bool EV = decltype(E)::value;
+                if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
+                    if (rows == 4) {
+                        auto kern = k_linear_eigen<TI, TC, TO, 4, PRE, EV>;
+                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg);
+                    } else {
+                        auto kern = k_linear_eigen<TI, TC, TO, 6, PRE, EV>;
+                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg);
+                    }
+                }
+            });
+        });
     })
+    if (rc) return rc;
     g_launches++;
     CK(cudaGetLastError());
     return TRGL_OK;
@@ -263,15 +300,31 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
 
 int launch_polynomial(const void* u1, const void* u2, const double* P1, const double* P2, const HSParams& hs, void* x,
                       uint8_t* status, void* u1c, void* u2c, unsigned int* flags, int64_t n, double maxc, int rows,
-                      int mode, cudaStream_t s, const Undist2* pre = nullptr, const Mirrors& mir = kNoMirrors) {
+                      int mode, cudaStream_t s, const Undist2* pre = nullptr, const Mirrors& mir = kNoMirrors,
+                      const FusedEval* ev = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
+    int rc = TRGL_OK;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
-        if (pre) { if (rows == 4) POLY_LAUNCH(4, PreUndistort, PreUndistort{*pre}) else POLY_LAUNCH(6, PreUndistort, PreUndistort{*pre}) }
-        else { if (rows == 4) POLY_LAUNCH(4, PreNone, PreNone{}) else POLY_LAUNCH(6, PreNone, PreNone{}) }
+        with_pre(pre, [&](auto prearg) {
+            using PRE = decltype(prearg);
+            with_eval(ev, [&](auto E, auto evarg) {
+                constexpr bool EV = decltype(E)::value;
+                if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
+                    if (rows == 4) {
+                        auto kern = k_polynomial<TI, TC, TO, 4, PRE, EV>;
+                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg);
+                    } else {
+                        auto kern = k_polynomial<TI, TC, TO, 6, PRE, EV>;
+                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg);
+                    }
+                }
+            });
+        });
     })
+    if (rc) return rc;
     g_launches++;
     CK(cudaGetLastError());
     return TRGL_OK;
@@ -327,6 +380,23 @@ int scratch_for(cudaStream_t s, Scratch& out) {
         sc.counter = sc.flags + kFlagWords;
     }
     out = sc;
+    return TRGL_OK;
+}
+
+// Consume the pending fused-evaluation request: cameras of this call, reduction scratch of this stream.
+int take_eval(const double* P1, const double* P2, cudaStream_t s, FusedEval& fe, const FusedEval*& out) {
+    out = nullptr;
+    if (!g_next_eval.armed) return TRGL_OK;
+    const PendingEval pe = g_next_eval;
+    g_next_eval.armed = false;
+    Scratch sc;
+    int rc = scratch_for(s, sc);
+    if (rc) return rc;
+    for (int i = 0; i < 12; ++i) { fe.cams.P1[i] = P1[i]; fe.cams.P2[i] = P2[i]; }
+    fe.max_sq_err = pe.max_sq_err; fe.min_status = pe.min_status; fe.pad_ = 0;
+    fe.err1 = pe.err1; fe.err2 = pe.err2; fe.good = pe.good;
+    fe.partials = sc.partials; fe.counter = sc.counter; fe.sums_out = pe.sums;
+    out = &fe;
     return TRGL_OK;
 }
 
@@ -442,6 +512,12 @@ int check_common(const void* u1, const void* u2, const double* P1, const double*
     if (g_next_mirrors.count && (mem != TRGL_MEM_DEVICE || n == 0)) {
         g_next_mirrors.count = 0;
         if (mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "result mirrors need device buffers (TRGL_MEM_DEVICE)");
+    }
+    if (g_next_eval.armed && (mem != TRGL_MEM_DEVICE || n == 0)) {
+        const PendingEval pe = g_next_eval;
+        g_next_eval.armed = false;
+        if (mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "the fused evaluation needs device buffers (TRGL_MEM_DEVICE)");
+        cudaMemsetAsync(pe.sums, 0, 4 * sizeof(double), nullptr);        // n == 0: all sums are zero
     }
     return TRGL_OK;
 }
@@ -633,6 +709,13 @@ int trgl_set_result_mirrors(void* const* x_mirrors, void* const* status_mirrors,
     }
     return TRGL_OK;
 }
+int trgl_set_fused_eval(int min_status, double max_sq_err, void* err1, void* err2, uint8_t* good, double* sums_device) {
+    if (!sums_device) return fail(TRGL_E_BADARG, "sums_device is NULL");
+    g_next_eval.armed = true;
+    g_next_eval.min_status = min_status; g_next_eval.max_sq_err = max_sq_err;
+    g_next_eval.err1 = err1; g_next_eval.err2 = err2; g_next_eval.good = good; g_next_eval.sums = sums_device;
+    return TRGL_OK;
+}
 int trgl_ipc_export(void* device_ptr, void* handle64) {
     if (!device_ptr || !handle64) return fail(TRGL_E_BADARG, "NULL pointer");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -670,8 +753,12 @@ static int impl_linear_ls(const void* u1, const void* u2, const double* P1, cons
                           int64_t n, int mode, int mem, void* stream, const Undist2* pre) {
     int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
     if (rc || n == 0) return rc;
-    if (mem == TRGL_MEM_DEVICE)
-        return launch_linear_ls(u1, u2, P1, P2, x, status, n, mode, static_cast<cudaStream_t>(stream), pre, take_mirrors());
+    if (mem == TRGL_MEM_DEVICE) {
+        FusedEval fe; const FusedEval* evp;
+        rc = take_eval(P1, P2, static_cast<cudaStream_t>(stream), fe, evp);
+        if (rc) return rc;
+        return launch_linear_ls(u1, u2, P1, P2, x, status, n, mode, static_cast<cudaStream_t>(stream), pre, take_mirrors(), evp);
+    }
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
@@ -697,9 +784,13 @@ static int impl_iterative_ls(const void* u1, const void* u2, const double* P1, c
     if (rc) return rc;
     if (semantics != TRGL_ITER_C && semantics != TRGL_ITER_PY) return fail(TRGL_E_BADARG, "unknown iterative semantics");
     if (n == 0) return TRGL_OK;
-    if (mem == TRGL_MEM_DEVICE)
+    if (mem == TRGL_MEM_DEVICE) {
+        FusedEval fe; const FusedEval* evp;
+        rc = take_eval(P1, P2, static_cast<cudaStream_t>(stream), fe, evp);
+        if (rc) return rc;
         return launch_iterative_ls(u1, u2, P1, P2, x, status, n, tolerance, semantics, mode, static_cast<cudaStream_t>(stream), pre,
-                                   take_mirrors());
+                                   take_mirrors(), evp);
+    }
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 4}};
@@ -726,9 +817,13 @@ static int impl_linear_eigen(const void* u1, const void* u2, const double* P1, c
     if (rc) return rc;
     if (rows != 4 && rows != 6) return fail(TRGL_E_BADARG, "rows must be 4 or 6");
     if (n == 0) return TRGL_OK;
-    if (mem == TRGL_MEM_DEVICE)
+    if (mem == TRGL_MEM_DEVICE) {
+        FusedEval fe; const FusedEval* evp;
+        rc = take_eval(P1, P2, static_cast<cudaStream_t>(stream), fe, evp);
+        if (rc) return rc;
         return launch_linear_eigen(u1, u2, P1, P2, x, status, n, max_coordinate_value, rows, mode, static_cast<cudaStream_t>(stream), pre,
-                                   take_mirrors());
+                                   take_mirrors(), evp);
+    }
     ModeInfo mi; mode_info(mode, mi);
     HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
@@ -767,8 +862,11 @@ static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, c
         if (rc) return rc;
         unsigned int* fl = sc.flags + 2 * kSlots;
         CK(cudaMemsetAsync(fl, 0, 2 * sizeof(unsigned int), s));
+        FusedEval fe; const FusedEval* evp;
+        rc = take_eval(P1, P2, s, fe, evp);
+        if (rc) return rc;
         rc = launch_polynomial(u1, u2, P1, P2, hs, x, status, u1_corr, u2_corr, fl, n, max_coordinate_value, rows, mode, s, pre,
-                               take_mirrors());
+                               take_mirrors(), evp);
         if (rc) return rc;
         if (all_nan) {
             CK(cudaMemcpyAsync(hflags, fl, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));

@@ -32,7 +32,7 @@ EXPORTS = [
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
     "trgl_set_points_per_thread", "trgl_set_stream_variant",
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
-    "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
+    "trgl_set_fused_eval", "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -83,6 +83,7 @@ def lib():
     L.trgl_reproj_error.argtypes = [vp, vp, dp, dp, dp, dp, vp, dp, dp, i64, cint, cint, cint, vp]
     L.trgl_pair_reproj.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, dp, i64, cint, cint, vp]
     L.trgl_pair_reproj_async.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, vp, i64, cint, vp]
+    L.trgl_set_fused_eval.argtypes = [cint, dbl, vp, vp, vp, vp]
     L.trgl_set_result_mirrors.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), cint]
     L.trgl_ipc_export.argtypes = [vp, vp]
     L.trgl_ipc_import.argtypes = [vp, ctypes.POINTER(vp)]
@@ -367,12 +368,13 @@ def undistort_points(src, K, dist=None, dst=None, stream=None):
 
 
 def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=None, status=None, stream=None,
-              pixel=None):
+              pixel=None, evaluate=None):
     """pixel: an Intrinsics -> u1,u2 are pixel coordinates, undistorted in registers in front of the solve."""
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
     mem = MEM_DEVICE if dev else MEM_HOST
+    _arm(evaluate, dev)
     if pixel is None:
         check(lib().trgl_linear_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, mode, mem, stream))
     else:
@@ -382,11 +384,12 @@ def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=
 
 
 def iterative_ls(u1, P1, u2, P2, tolerance=3.e-5, semantics=ITER_C, out_dtype=np.float64, compute_dtype=np.float64,
-                 x=None, status=None, stream=None, pixel=None):
+                 x=None, status=None, stream=None, pixel=None, evaluate=None):
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.int32, status)
     mem = MEM_DEVICE if dev else MEM_HOST
+    _arm(evaluate, dev)
     if pixel is None:
         check(lib().trgl_iterative_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, float(tolerance),
                                       semantics, mode, mem, stream))
@@ -397,11 +400,12 @@ def iterative_ls(u1, P1, u2, P2, tolerance=3.e-5, semantics=ITER_C, out_dtype=np
 
 
 def linear_eigen(u1, P1, u2, P2, max_coordinate_value=1.e16, rows=4, out_dtype=np.float64, compute_dtype=np.float64,
-                 x=None, status=None, stream=None, pixel=None):
+                 x=None, status=None, stream=None, pixel=None, evaluate=None):
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
     mem = MEM_DEVICE if dev else MEM_HOST
+    _arm(evaluate, dev)
     if pixel is None:
         check(lib().trgl_linear_eigen(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
                                       float(max_coordinate_value), rows, mode, mem, stream))
@@ -413,7 +417,7 @@ def linear_eigen(u1, P1, u2, P2, max_coordinate_value=1.e16, rows=4, out_dtype=n
 
 def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_dtype=np.float64,
                compute_dtype=np.float64, x=None, status=None, want_corrected=False, check_all_nan=True, stream=None,
-               pixel=None):
+               pixel=None, evaluate=None):
     """Returns x, status, all_nan[, u1_corr, u2_corr]."""
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
     P1 = _P12(P1); P2 = _P12(P2)
@@ -424,6 +428,7 @@ def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_d
     flag = ctypes.c_int(0)
     flag_p = ctypes.byref(flag) if check_all_nan else None
     mem = MEM_DEVICE if dev else MEM_HOST
+    _arm(evaluate, dev)
     if pixel is not None:
         if F is not None:
             raise ValueError("pixel inputs and an explicit F cannot be combined")
@@ -570,6 +575,31 @@ def median(values, stream=None):
     out = np.zeros(1)
     check(lib().trgl_median(_ptr(values), n, MEM_DEVICE if dev else MEM_HOST, _dp(out), stream))
     return float(out[0])
+
+
+class FusedEval:
+    """Two-view evaluation (reprojection errors, good mask, sums) fused into the NEXT device-mode solver call of this
+    thread: pass an instance as `evaluate=` to linear_ls / iterative_ls / linear_eigen / polynomial.  Outputs are device
+    buffers: .sums (4,) = sum err1, sum err2 over good points, #good, #status > min_status; .good (n,) bool;
+    .err1 / .err2 (n,) when want_errors."""
+
+    def __init__(self, n, x_dtype=np.float64, min_status=0, max_sq_err=np.inf, want_errors=False, want_good=True, sums=None):
+        self.min_status, self.max_sq_err = int(min_status), float(max_sq_err)
+        self.sums = sums if sums is not None else DeviceArray((4,), np.float64)
+        self.good = DeviceArray((n,), np.bool_) if want_good else None
+        self.err1 = DeviceArray((n,), x_dtype) if want_errors else None
+        self.err2 = DeviceArray((n,), x_dtype) if want_errors else None
+
+    def arm(self):
+        check(lib().trgl_set_fused_eval(self.min_status, self.max_sq_err, _ptr(self.err1), _ptr(self.err2), _ptr(self.good),
+                                        _ptr(self.sums)))
+
+
+def _arm(evaluate, dev):
+    if evaluate is not None:
+        if not dev:
+            raise ValueError("the fused evaluation needs device-resident inputs")
+        evaluate.arm()
 
 
 def set_result_mirrors(mirrors):

@@ -659,3 +659,49 @@ def test_result_mirrors_across_processes_via_cuda_ipc(tri):
     tc.synchronize()
     assert np.array_equal(gx.to_host()[lo:lo + n], xc, equal_nan=True) and np.array_equal(gs.to_host()[lo:lo + n], stc)
     assert np.isnan(gx.to_host()[:lo]).all()
+
+
+# ---- evaluation fused into the solver kernels ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["linear_eigen", "linear_LS", "iterative_LS", "polynomial"])
+def test_fused_evaluation_equals_separate_pass(tri, name, dtype):
+    """trgl_set_fused_eval: reprojection errors and good mask computed in the solver's epilogue are bit-identical to the
+    stand-alone pass over the stored results (trgl_pair_reproj); the sums agree to rounding, the counts exactly."""
+    import triangl_cuda as tc
+    n = 150001
+    u1, P1, u2, P2, _ = rig.make_correspondences(n, "rotating", sigma=2.0, dtype=dtype)
+    d1, d2 = tc.to_device(u1), tc.to_device(u2)
+    fn = {"linear_eigen": tc.linear_eigen, "linear_LS": tc.linear_ls, "iterative_LS": tc.iterative_ls,
+          "polynomial": lambda *a, **k: tc.polynomial(*a, check_all_nan=False, **k)[:2]}[name]
+    thr = (2.0 / 480) ** 2
+    fe = tc.FusedEval(n, dtype, 0, thr, want_errors=True, want_good=True)
+    x, st = fn(d1, P1, d2, P2, out_dtype=dtype, evaluate=fe)
+    x_plain, st_plain = fn(d1, P1, d2, P2, out_dtype=dtype)                   # the request applied to ONE call
+    e1, e2, good, sums = tc.pair_reproj(x, d1, P1, d2, P2, st, 0, thr)
+    tc.synchronize()
+    assert np.array_equal(x.to_host(), x_plain.to_host(), equal_nan=True) and np.array_equal(st.to_host(), st_plain.to_host())
+    assert np.array_equal(fe.good.to_host(), good.to_host())
+    assert np.array_equal(fe.err1.to_host(), e1.to_host(), equal_nan=True) and np.array_equal(fe.err2.to_host(), e2.to_host(), equal_nan=True)
+    fs = fe.sums.to_host()
+    assert fs[2] == sums[2] and fs[3] == sums[3] and 0 < sums[2] < n
+    assert fs[0] == pytest.approx(sums[0], rel=1e-11) and fs[1] == pytest.approx(sums[1], rel=1e-11)
+
+
+def test_fused_evaluation_with_pixel_inputs_and_small_batches(tri):
+    """Pixel-input solve + evaluation in one kernel (the whole SLAM keyframe triangulation step, slam2.py:551-563), and
+    batch sizes around the tile / queue boundaries."""
+    import triangl_cuda as tc
+    for n in (1, 31, 257, 1000, 20011):
+        px1, P1, px2, P2, K, dist = _pixel_batch(n, dtype=np.float32)
+        intr = tc.Intrinsics(K, dist)
+        d1, d2 = tc.to_device(px1), tc.to_device(px2)
+        fe = tc.FusedEval(n, np.float32, 0, 1e-4, want_errors=True)
+        x, st = tc.iterative_ls(d1, P1, d2, P2, out_dtype=np.float32, pixel=intr, evaluate=fe)
+        n1 = tc.undistort_points(d1, K, dist); n2 = tc.undistort_points(d2, K, dist)
+        e1, e2, good, sums = tc.pair_reproj(x, n1, P1, n2, P2, st, 0, 1e-4)
+        tc.synchronize()
+        assert np.array_equal(fe.good.to_host(), good.to_host()) and np.array_equal(fe.err1.to_host(), e1.to_host(), equal_nan=True)
+        fs = fe.sums.to_host()
+        assert fs[2] == sums[2] and fs[3] == sums[3] and fs[0] == pytest.approx(sums[0], rel=1e-11, abs=1e-30)
+    with pytest.raises((tc.TrianglCudaError, ValueError)):        # host arrays cannot carry a fused evaluation
+        tc.linear_ls(px1, P1, px2, P2, evaluate=fe)
