@@ -348,7 +348,10 @@ def run_ours(args, rank, world, local_rank):
         gbs = ALG_BYTES[s] * n / (ms * 1e-3) / 1e9
         per_solver[s] = {"kernel_ms": ms, "points_per_sec_per_gpu": n / (ms * 1e-3), "alg_bytes_per_point": ALG_BYTES[s],
                          "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "share_of_step": ms / step_ms,
-                         "traffic_bytes_per_point": traffic.get(s)}
+                         "traffic_bytes_per_point": traffic.get(s),
+                         # FP64 vector pipe utilisation of the same kernel under ncu (static, from profiles/): the bound
+                         # of iterative_LS / linear_eigen / polynomial (north_star: "FP64 pipe utilisation")
+                         "fp64_pipe_busy_ncu": (traffic.get("fp64_pipe_busy") or {}).get(s)}
     ls = per_solver["linear_LS"]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -75,9 +75,17 @@ if os.path.isfile(ll):
         f.write("| kernel | grid | launches | mean us | share of all kernel time |\n|---|---|---|---|---|\n")
         for (k, g), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write("| `%s` | %s | %d | %.1f | %.3f |\n" % (k.replace("void ", ""), g, len(v), sum(v) / len(v) / 1e3, sum(v) / tot))
-        # share within the device-resident steps only: bench.py runs (warmup + steps) device-resident steps of
-        # 4 solver + 4 reprojection kernels first, the host-mode (e2e) chunks follow
-        n_dev = 8 * 3
+        # share within the device-resident steps only: bench.py runs (warmup + steps) = 3 device-resident steps first
+        # (launches per step taken from the bench line of the same call), the host-mode (e2e) chunks follow
+        per_step_launches = 8
+        bj = os.path.join(src, "bench_10M.json")
+        if os.path.isfile(bj):
+            try:
+                bd = json.load(open(bj))
+                per_step_launches = int(round(bd["gpu_launches"] / float(bd["steps"])))
+            except Exception:
+                pass
+        n_dev = per_step_launches * 3
         dev = defaultdict(list)
         for r in rows[1:1 + n_dev]:
             v = num(r[vi])
