@@ -255,3 +255,32 @@ def test_P_from_rvec_and_tvec_matches_cv2_rodrigues():
         P = triangulation.P_from_rvec_and_tvec(rvec, tvec)
         assert P.shape == (4, 4) and np.array_equal(P[3], [0, 0, 0, 1])
         assert np.allclose(P[0:3, 0:3], cv2.Rodrigues(rvec)[0], atol=1e-14) and np.array_equal(P[0:3, 3:4], tvec)
+
+
+# ---- bench.py contract (CPU-checkable part) ----------------------------------------------------------------------------
+def _bench_lines(cmd):
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable] + cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [ln for ln in out.stdout.splitlines() if ln.strip()]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    import json
+    lines = _bench_lines(["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "20000"])
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "triangulated_points_per_sec" and d["unit"] == "points/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reference_arm_under_torchrun_only_rank0_prints():
+    import json
+    lines = _bench_lines(["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "1", "--cpu-sample", "20000"])
+    js = [ln for ln in lines if ln.startswith("{")]
+    assert len(js) == 1 and json.loads(js[0])["n_gpus"] == 2
