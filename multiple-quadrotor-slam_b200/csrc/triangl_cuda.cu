@@ -383,6 +383,12 @@ int scratch_for(cudaStream_t s, Scratch& out) {
     return TRGL_OK;
 }
 
+// Result mirrors / fused evaluation apply to ONE solver call: whatever that call's outcome (argument error, n == 0,
+// host mode), the request is gone when it returns.
+struct PendingClear {
+    ~PendingClear() { g_next_mirrors.count = 0; g_next_eval.armed = false; }
+};
+
 // Consume the pending fused-evaluation request: cameras of this call, reduction scratch of this stream.
 int take_eval(const double* P1, const double* P2, cudaStream_t s, FusedEval& fe, const FusedEval*& out) {
     out = nullptr;
@@ -768,11 +774,13 @@ static int impl_linear_ls(const void* u1, const void* u2, const double* P1, cons
 }
 int trgl_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                    int64_t n, int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     return impl_linear_ls(u1, u2, P1, P2, x, status, n, mode, mem, stream, nullptr);
 }
 int trgl_linear_ls_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
                       const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status, int64_t n,
                       int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     Undist2 pre;
     if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
     return impl_linear_ls(px1, px2, P1, P2, x, status, n, mode, mem, stream, &pre);
@@ -800,11 +808,13 @@ static int impl_iterative_ls(const void* u1, const void* u2, const double* P1, c
 }
 int trgl_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
                       int64_t n, double tolerance, int semantics, int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     return impl_iterative_ls(u1, u2, P1, P2, x, status, n, tolerance, semantics, mode, mem, stream, nullptr);
 }
 int trgl_iterative_ls_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
                          const double* dist2, const double* P1, const double* P2, void* x, int32_t* status, int64_t n,
                          double tolerance, int semantics, int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     Undist2 pre;
     if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
     return impl_iterative_ls(px1, px2, P1, P2, x, status, n, tolerance, semantics, mode, mem, stream, &pre);
@@ -833,11 +843,13 @@ static int impl_linear_eigen(const void* u1, const void* u2, const double* P1, c
 }
 int trgl_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                       int64_t n, double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     return impl_linear_eigen(u1, u2, P1, P2, x, status, n, max_coordinate_value, rows, mode, mem, stream, nullptr);
 }
 int trgl_linear_eigen_px(const void* px1, const void* px2, const double* K1, const double* dist1, const double* K2,
                          const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status, int64_t n,
                          double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     Undist2 pre;
     if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
     return impl_linear_eigen(px1, px2, P1, P2, x, status, n, max_coordinate_value, rows, mode, mem, stream, &pre);
@@ -900,6 +912,7 @@ static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, c
 int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const double* P2, const double* F, void* x,
                       uint8_t* status, void* u1_corr, void* u2_corr, int* all_nan, int64_t n,
                       double max_coordinate_value, int rows, int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     return impl_polynomial_F(u1, u2, P1, P2, F, x, status, u1_corr, u2_corr, all_nan, n, max_coordinate_value, rows, mode,
                              mem, stream, nullptr);
 }
@@ -907,6 +920,7 @@ int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const do
 int trgl_polynomial(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                     void* u1_corr, void* u2_corr, int* all_nan, int64_t n, double max_coordinate_value, int rows,
                     int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     if (!P1 || !P2) return fail(TRGL_E_BADARG, "camera matrix pointer is NULL");
     double F[9];
     fundamental_from_P(P1, P2, F);
@@ -918,6 +932,7 @@ int trgl_polynomial_px(const void* px1, const void* px2, const double* K1, const
                        const double* dist2, const double* P1, const double* P2, void* x, uint8_t* status,
                        void* u1_corr, void* u2_corr, int* all_nan, int64_t n, double max_coordinate_value, int rows,
                        int mode, int mem, void* stream) {
+    PendingClear pending_clear;
     if (!P1 || !P2) return fail(TRGL_E_BADARG, "camera matrix pointer is NULL");
     Undist2 pre;
     if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");

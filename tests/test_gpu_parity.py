@@ -705,3 +705,22 @@ def test_fused_evaluation_with_pixel_inputs_and_small_batches(tri):
         assert fs[2] == sums[2] and fs[3] == sums[3] and fs[0] == pytest.approx(sums[0], rel=1e-11, abs=1e-30)
     with pytest.raises((tc.TrianglCudaError, ValueError)):        # host arrays cannot carry a fused evaluation
         tc.linear_ls(px1, P1, px2, P2, evaluate=fe)
+
+
+def test_per_call_requests_do_not_outlive_a_failed_call(tri):
+    """Result mirrors and the fused evaluation are consumed by the next solver call even when that call fails."""
+    import triangl_cuda as tc
+    n = 5000
+    u1, P1, u2, P2, _ = rig.make_correspondences(n, "rotating", sigma=0.8)
+    d1, d2 = tc.to_device(u1), tc.to_device(u2)
+    gx, gs = tc.DeviceArray((n, 3), np.float64), tc.DeviceArray((n,), np.uint8)
+    tc.check(tc.lib().trgl_memset_d(gx.ptr, 0xff, gx.nbytes, None))
+    fe = tc.FusedEval(n, np.float64)
+    tc.check(tc.lib().trgl_memset_d(fe.sums.ptr, 0xff, 32, None))
+    tc.set_result_mirrors([(gx.ptr, gs.ptr)])
+    with pytest.raises(tc.TrianglCudaError):
+        tc.linear_eigen(d1, P1, d2, P2, rows=5, evaluate=fe)            # bad argument: rows must be 4 or 6
+    x, st = tc.linear_eigen(d1, P1, d2, P2)                              # must run without mirrors / evaluation
+    tc.synchronize()
+    assert np.isnan(gx.to_host()).all() and np.isnan(fe.sums.to_host()).all()
+    assert np.isfinite(x.to_host()).all()
