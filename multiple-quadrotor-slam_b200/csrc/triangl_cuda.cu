@@ -432,7 +432,7 @@ struct HostArray { const void* in; void* out; size_t bytes_per_point; };
 // kernel works straight on page-locked, device-mapped host memory (UVA: the cudaHostAlloc pointer is valid on the
 // device).  Inputs are memcpy'd into the staging block by the CPU, ONE kernel reads them over PCIe and writes x / status
 // back into the same block, one stream synchronise, CPU memcpy out: 1 launch + 1 sync instead of 4 copies + launch + sync.
-constexpr int64_t kZeroCopyMax = 16384;
+constexpr int64_t kZeroCopyMax = 32768;
 char* g_zc_buf = nullptr;
 size_t g_zc_cap = 0;
 
