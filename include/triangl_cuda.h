@@ -242,6 +242,11 @@ int64_t trgl_launch_count(void);
 int trgl_set_stream_variant(int variant);
 /* Tuning knob: points per thread of the per-thread-load linear_LS kernel (1, 2 or 4, default 4); returns the previous value. */
 int trgl_set_points_per_thread(int ppt);
+/* Tuning knob: arithmetic of iterative_LS.  0 = auto (default): the two-ray closed form of the re-weighted solve for every
+ * correspondence it certifies (finite camera centres, kappa^2 bound below 1e10, weight ratio in range), the reference's
+ * loop as written (triangulation.c:104-161: re-weighted normal equations / SVD tiers) for the rest; 1 = the reference's
+ * loop for every correspondence.  Both give the same status vector and points within 1e-9.  Returns the previous value. */
+int trgl_set_iterative_path(int general_only);
 
 #ifdef __cplusplus
 }

@@ -6,6 +6,16 @@
 #include "trgl_tma.cuh"
 #include "trgl_eval.cuh"
 
+#ifndef TRGL_EIGEN_MINB
+#define TRGL_EIGEN_MINB 2          // resident CTAs per SM the register allocation is sized for
+#endif
+#ifndef TRGL_POLY_MINB
+#define TRGL_POLY_MINB 2
+#endif
+#ifndef TRGL_ITER_MINB
+#define TRGL_ITER_MINB 2
+#endif
+
 namespace trgl {
 
 
@@ -231,12 +241,118 @@ __device__ __forceinline__ int iter_ls_status(int it, double d1n, double d2n) { 
     return st;
 }
 
+// General path of one correspondence: the reference's loop as written (re-weighted normal equations with the
+// conditioning tiers of solve_blocks).  Taken by the points the closed form below does not certify (low parallax,
+// cameras without a finite centre, non-finite input, exact-zero depths under the Python control flow); instantiated at
+// one place only, in the queue drain, where almost nothing else is live.
+template <typename TC>
+__device__ __forceinline__ int iter_point_general(const Cams<TC>& cams, TC a, TC b, TC c, TC d, TC tolerance, int py_semantics,
+                                               TC xs[3], TC& d1n, TC& d2n) {
+    TC M1[6], v1[3], M2[6], v2[3];
+    point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
+    TC w1 = 1, w2 = 1, d1 = 1, d2 = 1;
+    d1n = 1; d2n = 1;
+    int it = py_semantics ? 9 : 10;                 // value of the loop variable after a loop that never breaks
+#pragma unroll 1
+    for (int k = 0; k < 10; ++k)
+        if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
+            it = k; break;
+        }
+    return it;
+}
+
+// ---- two-ray closed form of the re-weighted solve --------------------------------------------------------------
+// The system of one correspondence is rows (a0, a1) of view 1 scaled by w1 and rows (c0, c1) of view 2 scaled by w2
+// (triangulation.c:30-40,143-146).  Each view's two planes meet in its viewing ray  C_k + t n_k  (n1 = a0 x a1,
+// C_k = camera centre, the null vector of P_k), so M_k = A_k^T A_k has rank 2, adj(M_k) = n_k n_k^T, and by
+// Cauchy-Binet the normal-equation solution of the weighted system is, exactly,
+//     x(kappa) = (X1 + kappa X2) / (1 + kappa),      kappa = (w2/w1)^2 * B/A,
+// where X1 = C1 + (t1/A) n1 is the point of ray 1 that minimises the view-2 residuals, X2 the point of ray 2 that
+// minimises the view-1 residuals, A = (c0.n1)^2 + (c1.n1)^2, B = (a0.n2)^2 + (a1.n2)^2, t1 = -sum_j (c_j.C1 - b_j)(c_j.n1).
+// Only the weight RATIO moves during the iteration, and the depths are the same convex combination of the depths of
+// X1 and X2, so one re-weighting round costs ~24 FP64 instructions instead of a fresh 3x3 solve (~80), with error
+// ~ kappa(A) eps (no squaring: checked against the SVD oracle to < 1e-10 up to kappa^2 = 1e12).
+template <typename T> struct RayGeom { T C1[3], C2[3], E1[3], E2[3]; int ok; int pad_; };   // E1 = P1 [C2;1], E2 = P2 [C1;1]
+template <typename T> struct TwoRay { T X1[3], X2[3], kap, d11, d12, d21, d22; };
+constexpr int kTwoRayState = 13;            // kap d1 d2 d11 d12 d21 d22 X1[3] X2[3]
+
+// kappa in [2^-27, 2^27]: the squared ratio of the weighted row norms of the two views.  Outside (or NaN) the reference's
+// SVD is ill-conditioned by the imbalance itself and the point goes to the general path.
+__device__ __forceinline__ bool kappa_in_range(double kap) {
+    const unsigned e = (static_cast<unsigned>(__double2hiint(kap)) >> 20) & 0xfffu;     // sign + exponent
+    return (e - (1023u - 27u)) <= 54u;
+}
+
+template <typename T> __device__ __forceinline__ T kap_nan();
+template <> __device__ __forceinline__ double kap_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+template <> __device__ __forceinline__ float kap_nan<float>() { return __int_as_float(0x7fc00000); }
+
+template <typename T>
+__device__ __forceinline__ bool tworay_setup(const Cams<T>& cams, const RayGeom<T>& g, T u1x, T u1y, T u2x, T u2y,
+                                             TwoRay<T>& R) {
+    T a0[3], a1[3], c0[3], c1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a0[k] = tfma(u1x, cams.P1[8 + k], -cams.P1[k]);  a1[k] = tfma(u1y, cams.P1[8 + k], -cams.P1[4 + k]);
+        c0[k] = tfma(u2x, cams.P2[8 + k], -cams.P2[k]);  c1[k] = tfma(u2y, cams.P2[8 + k], -cams.P2[4 + k]);
+    }
+    const T n1[3] = {tfma(a0[1], a1[2], -a0[2] * a1[1]), tfma(a0[2], a1[0], -a0[0] * a1[2]), tfma(a0[0], a1[1], -a0[1] * a1[0])};
+    const T n2[3] = {tfma(c0[1], c1[2], -c0[2] * c1[1]), tfma(c0[2], c1[0], -c0[0] * c1[2]), tfma(c0[0], c1[1], -c0[1] * c1[0])};
+    const T s0 = tfma(c0[0], n1[0], tfma(c0[1], n1[1], c0[2] * n1[2])), s1 = tfma(c1[0], n1[0], tfma(c1[1], n1[1], c1[2] * n1[2]));
+    const T r0 = tfma(a0[0], n2[0], tfma(a0[1], n2[1], a0[2] * n2[2])), r1 = tfma(a1[0], n2[0], tfma(a1[1], n2[1], a1[2] * n2[2]));
+    const T A = tfma(s0, s0, s1 * s1), B = tfma(r0, r0, r1 * r1);
+    // residuals of the other view's planes at this view's camera centre: c_j.C1 - b_j = u2 * E2[2] - E2[j]
+    const T e0 = tfma(u2x, g.E2[2], -g.E2[0]), e1 = tfma(u2y, g.E2[2], -g.E2[1]);
+    const T f0 = tfma(u1x, g.E1[2], -g.E1[0]), f1 = tfma(u1y, g.E1[2], -g.E1[1]);
+    const T t1 = -tfma(e0, s0, e1 * s1), t2 = -tfma(f0, r0, f1 * r1);
+    T tr = a0[0] * a0[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k) tr = tfma(a0[k], a0[k], tr);
+        tr = tfma(a1[k], a1[k], tr); tr = tfma(c0[k], c0[k], tr); tr = tfma(c1[k], c1[k], tr);
+    }
+    // det(M1 + M2) = A + B; the same kappa^2 bound as the normal-equation tiers, at the tier-2 limit
+    const bool well = (tr * tr * tr < Tiers<T>::t2() * (A + B)) && (A > T(0)) && (B > T(0));
+    const T iA = fast_rcp(A), iB = fast_rcp(B);
+    const T tau1 = t1 * iA, tau2 = t2 * iB;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { R.X1[k] = tfma(tau1, n1[k], g.C1[k]); R.X2[k] = tfma(tau2, n2[k], g.C2[k]); }
+    R.kap = B * iA;
+    R.d11 = tfma(cams.P1[8], R.X1[0], tfma(cams.P1[9], R.X1[1], tfma(cams.P1[10], R.X1[2], cams.P1[11])));
+    R.d12 = tfma(cams.P1[8], R.X2[0], tfma(cams.P1[9], R.X2[1], tfma(cams.P1[10], R.X2[2], cams.P1[11])));
+    R.d21 = tfma(cams.P2[8], R.X1[0], tfma(cams.P2[9], R.X1[1], tfma(cams.P2[10], R.X1[2], cams.P2[11])));
+    R.d22 = tfma(cams.P2[8], R.X2[0], tfma(cams.P2[9], R.X2[1], tfma(cams.P2[10], R.X2[2], cams.P2[11])));
+    return well && kappa_in_range(static_cast<double>(R.kap));
+}
+
+// One re-weighting round in closed form (triangulation.c:128-148).  Returns 1 when the reference's loop breaks here,
+// 0 to continue, -1 when the point has to be redone by the general path (exact-zero depth under the Python control
+// flow, weight ratio out of range).  `kap_used`, `inv` = kappa and 1 / (1 + kappa) of the round that was evaluated: the
+// solve of that round is x = (X1 + kap_used X2) * inv.
+template <typename T>
+__device__ __forceinline__ int tworay_step(const T d11, const T d12, const T d21, const T d22, T& kap, T& d1, T& d2,
+                                           T& d1n, T& d2n, T& inv, T& kap_used, const T tolerance, const int py_semantics) {
+    kap_used = kap;
+    inv = fast_rcp(T(1) + kap);
+    d1n = tfma(kap, d12, d11) * inv;                                                                  // triangulation.c:133
+    d2n = tfma(kap, d22, d21) * inv;
+    const bool conv = (tabs(d1n - d1) <= tolerance) && (tabs(d2n - d2) <= tolerance);
+    const bool zero = (d1n == T(0)) || (d2n == T(0));                                                 // triangulation.c:138
+    if (conv || (zero && !py_semantics)) return 1;
+    if (zero) return -1;
+    const T r = d1n * fast_rcp(d2n);                // cumulative re-weighting: (w2/w1)^2 *= (d1n/d2n)^2, triangulation.c:143-146
+    kap *= r * r;
+    d1 = d1n; d2 = d2n;
+    return kappa_in_range(static_cast<double>(kap)) ? 0 : -1;
+}
+
 // Persistent CTAs (one grid-stride loop over 256-point tiles, the next tile's four input scalars prefetched with cp.async
 // while the current tile is solved) with a block-level FIFO work queue in shared memory for the divergent tail:
-//   phase 1: every thread runs the first kPhase1 iterations of its point (on translating rigs every point converges
-//            at the second solve; on rotating rigs ~70 % do).  Finished points leave through the coalesced store.
-//   queue  : points still running push their four input scalars and loop state (w1,w2,d1,d2) to a circular queue.
-//   phase 2: whenever the queue holds >= 256 entries the block runs the remaining iterations on the OLDEST 256, so
+//   phase 1: every thread sets up the two-ray form of its point and runs the first kPhase1 rounds (on translating rigs
+//            every point converges at the second solve; on rotating rigs ~70 % do).  Finished points leave through the
+//            coalesced store.
+//   queue  : points still running push their closed-form state (13 scalars) to a circular queue.
+//   phase 2: whenever the queue holds >= 256 entries the block runs the remaining rounds on the OLDEST 256, so
 //            every warp is dense instead of idling on the ~30 % of lanes that need all 10 solves; the remainder is
 //            flushed after the last tile.
 //   mirrors: with result mirrors (multi-GPU gather) a tile is copied to the peers, fully coalesced, as soon as no point
@@ -245,31 +361,54 @@ __device__ __forceinline__ int iter_ls_status(int it, double d1n, double d2n) { 
 constexpr int kPhase1 = 2;
 constexpr int kQueueCap = 2 * kThreads;                  // power of two
 
-// Shared memory of one k_iterative_ls CTA (dynamic: 49 KB in the all-double mode, just above the static limit).
+// Shared memory of one k_iterative_ls CTA (dynamic: above the static limit in the all-double mode).
 template <typename TI, typename TC, typename TO>
 struct IterSmem {
     PairPrefetch<TI, kThreads> pre;          // cp.async landing zone of the next tile
-    TC q_state[8][kQueueCap];                // queue: a b c d w1 w2 d1 d2
+    TC q_state[kTwoRayState][kQueueCap];     // queue: closed-form state of the point
     int64_t q_idx[kQueueCap];                //        global point index
     TO stage[kWarps][96];                    // coalesced (n,3) store staging
     unsigned int q_tail;                     // total number of pushes so far (slot = position & (kQueueCap-1))
 };
 
-template <typename TC, typename TO, bool EVAL>
-__device__ __forceinline__ void iter_ls_phase2(const Cams<TC>& cams, const TC (*q_state)[kQueueCap], const int64_t* q_idx,
+// The four input scalars of point i again (phase 2 needs them for the evaluation epilogue and for the general path):
+// they were read a few tiles ago, so this is an L2 hit.
+template <typename TI, typename TC, class PRE>
+__device__ __forceinline__ void reload_inputs(const TI* __restrict__ u1, const TI* __restrict__ u2, const PRE& pre_stage,
+                                              int64_t i, TC& a, TC& b, TC& c, TC& d) {
+    load_uv<TC>(u1, i, a, b);
+    load_uv<TC>(u2, i, c, d);
+    if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
+}
+
+template <typename TI, typename TC, typename TO, class PRE, bool EVAL>
+__device__ __forceinline__ void iter_ls_phase2(const TI* __restrict__ u1, const TI* __restrict__ u2, const PRE& pre_stage,
+                                               const Cams<TC>& cams, const TC (*q_state)[kQueueCap], const int64_t* q_idx,
                                                int slot, TO* __restrict__ x, int32_t* __restrict__ status,
                                                TC tolerance, int py_semantics, const EvalArg<EVAL>& ev, double (&acc)[4]) {
-    const TC a = q_state[0][slot], b = q_state[1][slot], c = q_state[2][slot], d = q_state[3][slot];
-    TC w1 = q_state[4][slot], w2 = q_state[5][slot], d1 = q_state[6][slot], d2 = q_state[7][slot], d1n = d1, d2n = d2;
+    TC kap = q_state[0][slot], d1 = q_state[1][slot], d2 = q_state[2][slot];
     const int64_t dst = q_idx[slot];
-    TC M1[6], v1[3], M2[6], v2[3], xs[3];
-    point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
+    TC a = 0, b = 0, c = 0, d = 0;
+    if constexpr (EVAL) reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, dst, a, b, c, d);     // in flight during the rounds
+    TC d1n = d1, d2n = d2, xs[3];
     int it = py_semantics ? 9 : 10;                 // value of the loop variable after a loop that never breaks
+    int r = -1;
+    if (kap == kap) {                               // NaN marks a point that phase 1 could not certify
+        const TC d11 = q_state[3][slot], d12 = q_state[4][slot], d21 = q_state[5][slot], d22 = q_state[6][slot];
+        TC inv = 1, kap_used = kap;
 #pragma unroll 1
-    for (int k = kPhase1; k < 10; ++k)
-        if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
-            it = k; break;
+        for (int k = kPhase1; k < 10; ++k) {
+            r = tworay_step<TC>(d11, d12, d21, d22, kap, d1, d2, d1n, d2n, inv, kap_used, tolerance, py_semantics);
+            if (r) { if (r > 0) it = k; break; }
         }
+        // the last solve that was evaluated is the result (triangulation.c:130,150)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xs[k] = tfma(kap_used, q_state[10 + k][slot], q_state[7 + k][slot]) * inv;
+    }
+    if (r < 0) {                                    // the reference's loop as written, from the first solve
+        if constexpr (!EVAL) reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, dst, a, b, c, d);
+        it = iter_point_general<TC>(cams, a, b, c, d, tolerance, py_semantics, xs, d1n, d2n);
+    }
     x[3 * dst + 0] = static_cast<TO>(xs[0]);
     x[3 * dst + 1] = static_cast<TO>(xs[1]);
     x[3 * dst + 2] = static_cast<TO>(xs[2]);
@@ -294,9 +433,9 @@ __device__ __forceinline__ void mirror_tile(const TO* __restrict__ x, const int3
 }
 
 template <typename TI, typename TC, typename TO, class PRE = PreNone, bool EVAL = false>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, TRGL_ITER_MINB)
 k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-               TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
+               const __grid_constant__ RayGeom<TC> geom, TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
                const TC tolerance, const int py_semantics, const __grid_constant__ PRE pre_stage,
                const __grid_constant__ Mirrors mir, const __grid_constant__ EvalArg<EVAL> ev) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -314,23 +453,32 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
     int count = 0;                                       // queue length                         } every thread
     double acc[4] = {0, 0, 0, 0};                        // fused evaluation sums of this thread
     pre.issue(u1, u2, tile + threadIdx.x, n);
-    for (; tile < n; tile += stride) {
-        const int64_t i = tile + threadIdx.x;
-        TC a, b, c, d;
-        pre.take(i, n, a, b, c, d);
-        pre.issue(u1, u2, i + stride, n);                // next tile of this CTA lands while this one is solved
-        if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
-        {
-            TC M1[6], v1[3], M2[6], v2[3], xs[3] = {0, 0, 0};
-            point_blocks<TC>(cams, a, b, c, d, M1, v1, M2, v2);
-            TC w1 = 1, w2 = 1, d1 = 1, d2 = 1, d1n = 1, d2n = 1;
-            int it = -1;
+    for (;; tile += stride) {
+        const bool have_tile = tile < n;                 // block-uniform; the pass after the last tile only flushes the queue
+        if (have_tile) {
+            const int64_t i = tile + threadIdx.x;
+            TC a, b, c, d;
+            pre.take(i, n, a, b, c, d);
+            pre.issue(u1, u2, i + stride, n);            // next tile of this CTA lands while this one is solved
+            if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
+            TwoRay<TC> R;
+            TC xs[3] = {0, 0, 0};
+            TC kap = 0, d1 = 1, d2 = 1, d1n = 1, d2n = 1, inv = 1, kap_used = 1;
+            int it = -1, r = -1;
+            if (geom.ok && tworay_setup<TC>(cams, geom, a, b, c, d, R)) {
+                kap = R.kap;
 #pragma unroll 1
-            for (int k = 0; k < kPhase1; ++k)
-                if (iter_ls_step<TC>(cams, a, b, c, d, M1, v1, M2, v2, w1, w2, d1, d2, d1n, d2n, xs, tolerance, py_semantics)) {
-                    it = k; break;
+                for (int k = 0; k < kPhase1; ++k) {
+                    r = tworay_step<TC>(R.d11, R.d12, R.d21, R.d22, kap, d1, d2, d1n, d2n, inv, kap_used, tolerance, py_semantics);
+                    if (r) { if (r > 0) it = k; break; }
                 }
-            const bool pending = (it < 0) && (i < n);
+            }
+            if (r > 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) xs[k] = tfma(kap_used, R.X2[k], R.X1[k]) * inv;
+            }
+            // r == 0: still iterating; r < 0: not certified -> queued with kappa = NaN, the drain runs the general path
+            const bool pending = (r <= 0) && (i < n);
             const unsigned ball = __ballot_sync(0xffffffffu, pending);
             if (ball) {
                 unsigned int base = 0;
@@ -338,8 +486,11 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (pending) {
                     const int slot = static_cast<int>((base + __popc(ball & ((1u << lane) - 1u))) & (kQueueCap - 1));
-                    q_state[0][slot] = a; q_state[1][slot] = b; q_state[2][slot] = c; q_state[3][slot] = d;
-                    q_state[4][slot] = w1; q_state[5][slot] = w2; q_state[6][slot] = d1; q_state[7][slot] = d2;
+                    q_state[0][slot] = (r == 0) ? kap : kap_nan<TC>();
+                    q_state[1][slot] = d1; q_state[2][slot] = d2;
+                    q_state[3][slot] = R.d11; q_state[4][slot] = R.d12; q_state[5][slot] = R.d21; q_state[6][slot] = R.d22;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { q_state[7 + k][slot] = R.X1[k]; q_state[10 + k][slot] = R.X2[k]; }
                     q_idx[slot] = i;
                 }
             }
@@ -355,28 +506,25 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
             // this tile's stores); head / count live in registers so the drain decision is uniform
             count += __syncthreads_count(pending);
         }
-        if (count >= kThreads) {                         // count < kQueueCap: <= kThreads-1 left over + kThreads pushed
-            iter_ls_phase2<TC, TO, EVAL>(cams, q_state, q_idx, static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x,
-                                         status, tolerance, py_semantics, ev, acc);
-            head += kThreads; count -= kThreads;
+        if (count >= kThreads || (!have_tile && count > 0)) {    // count < kQueueCap: <= kThreads-1 left over + kThreads pushed
+            const int take = count < kThreads ? count : kThreads;
+            if (static_cast<int>(threadIdx.x) < take)
+                iter_ls_phase2<TI, TC, TO, PRE, EVAL>(u1, u2, pre_stage, cams, q_state, q_idx,
+                                                      static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x, status,
+                                                      tolerance, py_semantics, ev, acc);
+            head += take; count -= take;
             __syncthreads();                             // the drained slots may be overwritten, the results are visible
         }
         if (mir.count) {
             // tiles before the one that holds the oldest queued point are final (pushes are in tile order)
-            int64_t safe = tile + stride;
+            int64_t safe = have_tile ? tile + stride : n + stride;
             if (count > 0) {
                 const int64_t oldest = q_idx[head & (kQueueCap - 1)];
                 safe = oldest - ((oldest - first) % stride);
             }
-            for (; mirrored < safe; mirrored += stride) mirror_tile<TO>(x, status, mir, mirrored, n);
+            for (; mirrored < safe && mirrored < n; mirrored += stride) mirror_tile<TO>(x, status, mir, mirrored, n);
         }
-    }
-    if (static_cast<int>(threadIdx.x) < count)
-        iter_ls_phase2<TC, TO, EVAL>(cams, q_state, q_idx, static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x, status,
-                                     tolerance, py_semantics, ev, acc);
-    if (mir.count) {
-        __syncthreads();
-        for (; mirrored < n; mirrored += stride) mirror_tile<TO>(x, status, mir, mirrored, n);
+        if (!have_tile) break;
     }
     fused_eval_finish<EVAL>(ev, acc);
 }
@@ -532,7 +680,7 @@ __device__ __forceinline__ void eigen_point(const Cams<TC>& cams, TC u1x, TC u1y
 // Persistent CTAs: grid-stride loop over 256-point tiles, the next tile's inputs are prefetched into registers while the
 // current tile is solved (the solve is ~700 instructions per point, so one tile of lookahead hides the HBM latency).
 template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, TRGL_EIGEN_MINB)
 k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord,
                const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
@@ -563,7 +711,7 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
 // ---- polynomial_triangulation (triangulation.py:198-232) -------------------------------------------------------
 // Hartley-Sturm correction of the match (cv2.correctMatches) followed by the linear-eigen solve, fused.
 template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, TRGL_POLY_MINB)
 k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams, const __grid_constant__ HSParams hs,
              TO* __restrict__ x, uint8_t* __restrict__ status, TI* __restrict__ u1c, TI* __restrict__ u2c,
              unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord,

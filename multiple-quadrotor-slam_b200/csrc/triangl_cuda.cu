@@ -74,6 +74,46 @@ Cams<T> make_cams(const double* P1, const double* P2) {
     return c;
 }
 
+// Camera centres (null vectors of P1, P2) and the cross terms E1 = P1 [C2;1], E2 = P2 [C1;1] of the two-ray closed form
+// (trgl_kernels.cuh).  ok = 0 when a camera has no finite, well-defined centre (left 3x3 block singular to ~1e-12:
+// affine / degenerate matrices): the kernel then runs the general path for every point.
+template <typename T>
+RayGeom<T> make_ray_geom(const double* P1, const double* P2) {
+    RayGeom<T> g{};
+    double C[2][3];
+    bool ok = true;
+    for (int cam = 0; cam < 2; ++cam) {
+        const double* P = cam == 0 ? P1 : P2;
+        const double m[9] = {P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10]};
+        const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+        const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+        double fro = 0;
+        for (double v : m) fro += v * v;
+        if (!(std::fabs(det) > 1e-12 * fro * std::sqrt(fro)) || !std::isfinite(det)) { ok = false; break; }
+        const double inv[9] = {c00, m[2] * m[7] - m[1] * m[8], m[1] * m[5] - m[2] * m[4],
+                               c01, m[0] * m[8] - m[2] * m[6], m[2] * m[3] - m[0] * m[5],
+                               c02, m[1] * m[6] - m[0] * m[7], m[0] * m[4] - m[1] * m[3]};
+        for (int r = 0; r < 3; ++r)
+            C[cam][r] = -(inv[3 * r + 0] * P[3] + inv[3 * r + 1] * P[7] + inv[3 * r + 2] * P[11]) / det;
+        // one refinement step of M C = -p4 (the cofactor inverse is only kappa(M) eps accurate)
+        double res[3];
+        for (int r = 0; r < 3; ++r)
+            res[r] = -(P[4 * r + 3] + m[3 * r + 0] * C[cam][0] + m[3 * r + 1] * C[cam][1] + m[3 * r + 2] * C[cam][2]);
+        for (int r = 0; r < 3; ++r)
+            C[cam][r] += (inv[3 * r + 0] * res[0] + inv[3 * r + 1] * res[1] + inv[3 * r + 2] * res[2]) / det;
+        for (int r = 0; r < 3; ++r) ok = ok && std::isfinite(C[cam][r]);
+    }
+    if (ok) {
+        for (int r = 0; r < 3; ++r) {
+            g.C1[r] = static_cast<T>(C[0][r]); g.C2[r] = static_cast<T>(C[1][r]);
+            g.E1[r] = static_cast<T>(P1[4 * r + 0] * C[1][0] + P1[4 * r + 1] * C[1][1] + P1[4 * r + 2] * C[1][2] + P1[4 * r + 3]);
+            g.E2[r] = static_cast<T>(P2[4 * r + 0] * C[0][0] + P2[4 * r + 1] * C[0][1] + P2[4 * r + 2] * C[0][2] + P2[4 * r + 3]);
+        }
+    }
+    g.ok = ok ? 1 : 0;
+    return g;
+}
+
 inline unsigned grid_for(int64_t n, int per_block) { return static_cast<unsigned>((n + per_block - 1) / per_block); }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -92,6 +132,7 @@ inline unsigned grid_for(int64_t n, int per_block) { return static_cast<unsigned
 // Launch geometry of the bulk-async variants: persistent grid of SMs x (CTAs that fit in shared memory).
 std::atomic<int> g_variant{-1};         // -1 = auto, 0 = per-thread loads, >= 1 = bulk-async pipeline (trgl_set_stream_variant)
 int g_sm_count = 0;
+std::atomic<int> g_iter_general{0};     // 1 = iterative_LS runs the reference's loop for every point (trgl_set_iterative_path)
 
 template <typename TI, typename TC, typename TO, int PPT, int STAGES, int MINB>
 int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n, cudaStream_t s,
@@ -247,6 +288,8 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
     int rc = TRGL_OK;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
+        RayGeom<TC> geom = make_ray_geom<TC>(P1, P2);
+        if (g_iter_general) geom.ok = 0;
         constexpr size_t smem = sizeof(IterSmem<TI, TC, TO>);
         with_pre(pre, [&](auto prearg) {
             using PRE = decltype(prearg);
@@ -255,7 +298,7 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
                 if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
                     auto kern = k_iterative_ls<TI, TC, TO, PRE, EV>;
                     kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
-                        static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, static_cast<TO*>(x), status, n,
+                        static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, geom, static_cast<TO*>(x), status, n,
                         static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, prearg, mir, evarg);
                 }
             });
@@ -746,6 +789,11 @@ int64_t trgl_launch_count(void) { return g_launches.load(); }
 int trgl_set_stream_variant(int variant) {
     const int old = g_variant.load();
     if (variant >= -1 && variant <= 12) g_variant.store(variant);
+    return old;
+}
+int trgl_set_iterative_path(int general_only) {
+    const int old = g_iter_general.load();
+    g_iter_general.store(general_only ? 1 : 0);
     return old;
 }
 int trgl_set_points_per_thread(int ppt) {

@@ -16,7 +16,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtriangl_cuda.so")
+# TRGL_CUDA_LIB: another build of the same library (tools/ab_variants.sh compares compile-time variants on the GPU box)
+LIB_PATH = os.environ.get("TRGL_CUDA_LIB") or os.path.join(_HERE, "libtriangl_cuda.so")
 
 F64, F32IO, F32, F64_OUT32, F32_OUT64 = 0, 1, 2, 3, 4
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -30,7 +31,7 @@ EXPORTS = [
     "trgl_event_create", "trgl_event_destroy", "trgl_event_record", "trgl_event_elapsed_ms",
     "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
-    "trgl_set_points_per_thread", "trgl_set_stream_variant",
+    "trgl_set_points_per_thread", "trgl_set_stream_variant", "trgl_set_iterative_path",
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
     "trgl_set_fused_eval", "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
@@ -639,6 +640,11 @@ def set_points_per_thread(ppt):
 
 def set_stream_variant(v):
     return lib().trgl_set_stream_variant(int(v))
+
+
+def set_iterative_path(general_only):
+    """0 = two-ray closed form where certified (default), 1 = the reference's loop for every point; returns the old value."""
+    return lib().trgl_set_iterative_path(int(general_only))
 
 
 def synchronize():

@@ -11,6 +11,9 @@ Generate the committed parity fixtures under tests/golden/ (run in the build con
 3. cv2_undistort.npz : cv2.undistortPoints outputs (cv2 4.13) pinning the input-normalisation stage.
 4. slam_replay_svo.npz : per-keyframe batches of the recorded slam2 run on the reference's SVO dataset + the reference's
    own results on them.
+5. formats.npz : what the reference's own dataset_tools.py (lines 1-269 exec'd, with the two Python-2 idioms
+   `colors != None` / `colors == None` read as identity tests) loads from one of its shipped .pcd maps and TUM
+   trajectories, and writes back for them.
 """
 import json
 import os
@@ -157,8 +160,41 @@ def slam_replay_fixture():
         len(steps), off[-1], min(np.diff(off)), max(np.diff(off)), int(np.median(np.diff(off)))))
 
 
+def formats_fixture():
+    """5. formats.npz : the reference's PCD / TUM readers and writers (dataset_tools.py:71-272) on files it ships."""
+    import tempfile
+    import types
+    path = os.path.join(REFERENCE_ROOT, "Work/python_libs/dataset_tools.py")
+    src = open(path).read().split("\n")[:269]
+    src = "\n".join(src).replace("colors != None", "colors is not None").replace("colors == None", "colors is None")
+    mod = types.ModuleType("dataset_tools_reference")
+    exec(compile(src, path, "exec"), mod.__dict__)
+    base = os.path.join(REFERENCE_ROOT, "Work/SLAM/datasets/SVO/sin2_tex2_h1_v8_d")
+    pcd_text = open(os.path.join(base, "map_out-slam2.pcd")).read()
+    pcd_plain_text = open(os.path.join(base, "init_points.pcd")).read()
+    traj_text = open(os.path.join(base, "traj_out.cam0-slam2.txt")).read()
+    pts, cols, alpha = mod.load_3D_points_from_pcd_file(os.path.join(base, "map_out-slam2.pcd"), use_alpha=True)
+    pts3, cols3, _ = mod.load_3D_points_from_pcd_file(os.path.join(base, "map_out-slam2.pcd"))
+    ptsp, colsp, alphap = mod.load_3D_points_from_pcd_file(os.path.join(base, "init_points.pcd"))
+    ts, locs, quats = mod.load_cam_trajectory_TUM(os.path.join(base, "traj_out.cam0-slam2.txt"))
+    with tempfile.TemporaryDirectory() as tmp:
+        f = os.path.join(tmp, "o")
+        mod.save_3D_points_to_pcd_file(f, pts, cols);  saved_bgra = open(f).read()
+        mod.save_3D_points_to_pcd_file(f, pts, cols3); saved_bgr = open(f).read()
+        mod.save_3D_points_to_pcd_file(f, ptsp);       saved_plain = open(f).read()
+        mod.save_cam_trajectory_TUM(f, (ts[:25], locs[:25], quats[:25])); saved_traj = open(f).read()
+    assert colsp is None and not alphap
+    np.savez_compressed(os.path.join(GOLDEN, "formats.npz"), pcd_text=pcd_text, pcd_plain_text=pcd_plain_text,
+                        traj_text=traj_text, points=pts, colors_bgra=cols, found_alpha=alpha, colors_bgr=cols3,
+                        points_plain=ptsp, timestps=ts, locations=locs, quaternions=quats, saved_bgra=saved_bgra,
+                        saved_bgr=saved_bgr, saved_plain=saved_plain, saved_traj=saved_traj)
+    print("wrote formats.npz: %d coloured points, %d plain points, %d poses" % (len(pts), len(ptsp), len(ts)))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "undistort":
+    if len(sys.argv) > 1 and sys.argv[1] == "formats":
+        formats_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "undistort":
         cv2_undistort_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "slam":
         slam_replay_fixture()
@@ -167,3 +203,4 @@ if __name__ == "__main__":
         golden_cells()
         cv2_undistort_fixture()
         slam_replay_fixture()
+        formats_fixture()

@@ -107,6 +107,61 @@ def test_iterative_ls_vs_oracle(tri, rig_name, sigma, semantics):
 
 
 @pytest.mark.parametrize("rig_name", RIG_NAMES)
+@pytest.mark.parametrize("sigma", [0.8, 20.0])
+def test_iterative_ls_closed_form_equals_reference_loop(tri, rig_name, sigma):
+    """The two-ray closed form (default) and the reference's loop as written (trgl_set_iterative_path(1)) are the same
+    function: identical status vector away from knife-edge convergence tests, points within 1e-9."""
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(50021, rig_name, sigma)
+    x, st = tri.iterative_LS_triangulation(u1, P1, u2, P2)
+    old = tc.set_iterative_path(1)
+    try:
+        xg, stg = tri.iterative_LS_triangulation(u1, P1, u2, P2)
+    finally:
+        tc.set_iterative_path(old)
+    assert old == 0
+    knife = iterative_margin(u1, P1, u2, P2) < 1e-9
+    ok = ls_well_posed(u1, P1, u2, P2) & ~knife
+    assert ok.mean() > 0.9
+    assert np.array_equal(st[ok], stg[ok])
+    assert rel_err(x, xg)[ok].max() < TOL64
+    # away from the certified set both still agree to the conditioning of the system
+    A, _ = orc.build_Ab(u1, P1, u2, P2)
+    s = np.linalg.svd(A, compute_uv=False)
+    same = st == stg
+    assert np.all(rel_err(x, xg)[same & ~knife] < np.maximum(TOL64, (s[:, 0] / s[:, 2])[same & ~knife] ** 2 * 1e-13))
+
+
+def test_iterative_ls_uncertified_points_take_the_reference_loop(tri):
+    """Cameras without a finite centre (affine P), identical cameras (rank 2) and a 1e-5 baseline: none of them is
+    certified by the closed form, all must still match the oracle."""
+    u1, P1, u2, P2, X = rig.make_correspondences(4001, "rotating", 0.5)
+    # (a) affine cameras: third row (0,0,0,1) -> no centre; depths are exactly 1, every point stops at the first solve
+    Pa1 = P1.copy(); Pa2 = P2.copy()
+    Pa1[2] = (0, 0, 0, 1); Pa2[2] = (0, 0, 0, 1)
+    x, st = tri.iterative_LS_triangulation(u1, Pa1, u2, Pa2)
+    xo, so, _, margin = orc.iterative_LS_core(u1, Pa1, u2, Pa2)
+    ok = ls_well_posed(u1, Pa1, u2, Pa2) & (margin > 1e-9)
+    assert ok.mean() > 0.9
+    assert np.array_equal(st[ok], so[ok]) and rel_err(x, xo)[ok].max() < TOL64
+    # (b) identical cameras: minimum-norm solutions of rank-2 systems
+    x, st = tri.iterative_LS_triangulation(u1, P1, u1, P1)
+    xo, so, _, margin = orc.iterative_LS_core(u1, P1, u1, P1)
+    keep = margin > 1e-9
+    assert np.isfinite(x).all()
+    assert np.array_equal(st[keep], so[keep]) and rel_err(x, xo)[keep].max() < 1e-8
+    # (c) 1e-5 baseline: kappa^2 ~ 1e7..1e10, straddles the certification limit
+    u1, P1, u2, P2, X = rig.make_correspondences(20011, (1e-5, 0., 0.), 0.1)
+    x, st = tri.iterative_LS_triangulation(u1, P1, u2, P2)
+    xo, so, _, margin = orc.iterative_LS_core(u1, P1, u2, P2)
+    keep = margin > 1e-9
+    assert np.array_equal(st[keep], so[keep])
+    A, _ = orc.build_Ab(u1, P1, u2, P2)
+    s = np.linalg.svd(A, compute_uv=False)
+    assert np.all(rel_err(x, xo)[keep] < np.maximum(TOL64, (s[:, 0] / s[:, 2])[keep] * 1e-13))
+
+
+@pytest.mark.parametrize("rig_name", RIG_NAMES)
 @pytest.mark.parametrize("sigma", [0.0, 0.8, 8.0])
 @pytest.mark.parametrize("rows", [4, 6])
 def test_linear_eigen_vs_oracle(tri, rig_name, sigma, rows):
