@@ -142,6 +142,19 @@ int trgl_set_fused_eval(int min_status, double max_sq_err, void* err1, void* err
 
 /* ---- input normalisation in front of the solvers ---- */
 
+/* Multi-view linear least-squares triangulation: the 2m x 3 generalisation of
+ * trgl_linear_ls for a point seen by m >= 2 cameras (the multi-quadrotor scene).  The reference has no such call -- every
+ * triangulation in Work/ is two-view (triangulation.py:31-94) -- so this extends its interface in its own conventions:
+ *   u      : (m, n, 2) observations in normalised coordinates, view-major (each view a contiguous (n,2) array)
+ *   valid  : (m, n) uint8, 1 = view v observes point i; NULL = every view observes every point
+ *   P      : (m, 12) rows 0-2 of the camera matrices (host doubles)
+ *   x      : (n,3) minimum-norm least-squares solution of the rows of the observing views (cvSolve(DECOMP_SVD) rule);
+ *            a point nobody observes gets (0,0,0)
+ *   status : (n,) uint8, 1 when at least min_views views observe the point
+ * With m = 2, valid = NULL this is trgl_linear_ls.  Arithmetic is float64 (TRGL_F32 runs as TRGL_F32IO). */
+int trgl_multiview_ls(const void* u, const uint8_t* valid, const double* P, int m, void* x, uint8_t* status, int64_t n,
+                      int min_views, int mode, int mem, void* stream);
+
 /* cv2.undistortPoints(src, K, dist) with the default criteria (5 fixed-point iterations) and no R / P:
  * call sites Work/SLAM/application/own/slam2.py:551-552, Work/triangulation_comparison/triangulation_comparison.py:164-173,
  * Work/calibration/calibrate.py:252-253.  src, dst: (n,2) pixel / normalised coordinates, both float32 (in_is_f32 = 1)
@@ -242,11 +255,18 @@ int64_t trgl_launch_count(void);
 int trgl_set_stream_variant(int variant);
 /* Tuning knob: points per thread of the per-thread-load linear_LS kernel (1, 2 or 4, default 4); returns the previous value. */
 int trgl_set_points_per_thread(int ppt);
-/* Tuning knob: arithmetic of iterative_LS.  0 = auto (default): the two-ray closed form of the re-weighted solve for every
- * correspondence it certifies (finite camera centres, kappa^2 bound below 1e10, weight ratio in range), the reference's
- * loop as written (triangulation.c:104-161: re-weighted normal equations / SVD tiers) for the rest; 1 = the reference's
- * loop for every correspondence.  Both give the same status vector and points within 1e-9.  Returns the previous value. */
-int trgl_set_iterative_path(int general_only);
+/* Tuning / test knob: the two-ray closed forms.  1 = on (default): iterative_LS runs the closed form of the re-weighted
+ * solve for every correspondence it certifies (finite camera centres, kappa^2 bound below 1e10, weight ratio in range)
+ * and polynomial takes the certified intersection of the two viewing rays of the corrected match; everything else goes
+ * through the reference's arithmetic as written (triangulation.c:104-161 re-weighted normal equations / SVD tiers;
+ * cv2.triangulatePoints' smallest singular vector).  0 = the reference's arithmetic for every correspondence.  Both give
+ * the same status vectors and points within 1e-9.  Returns the previous value. */
+int trgl_set_two_ray(int enabled);
+/* Test knob: the hot kernels of iterative_LS, linear_eigen, polynomial and multiview_LS hand the correspondences they do
+ * not certify to a follow-up kernel through a list of one slot per point of the batch (at most 2^26); when more points
+ * are deferred than the list holds, the follow-up kernel redoes every point instead.  This limits the list to
+ * max_points (1 .. 2^26) so that the overflow path can be exercised on small batches.  Returns the previous limit. */
+int64_t trgl_set_deferred_capacity(int64_t max_points);
 
 #ifdef __cplusplus
 }

@@ -128,7 +128,12 @@ __device__ __forceinline__ void hs_epipole(const double e[3], double x, double y
     if (f < 0.0) { ex = -ex; ey = -ey; f = -f; }
 }
 
-__device__ __forceinline__ void hs_correct(const HSParams& hs, double x1, double y1, double x2, double y2,
+// SLOW = true: the complete correction (follow-up kernel, CPU-like robustness).  SLOW = false: the certified fast path
+// only, for the hot kernel -- returns false, leaving the outputs undefined, when the certificate does not hold or the
+// bracketed Newton iteration needs more than kHsFastIters rounds; the caller then defers the point.
+constexpr int kHsFastIters = 12;
+template <bool SLOW>
+__device__ __forceinline__ bool hs_correct(const HSParams& hs, double x1, double y1, double x2, double y2,
                                            double& n1x, double& n1y, double& n2x, double& n2y) {
     const double* F = hs.F;
     // F' = T2^-T F T1^-1  (both points moved to the origin)
@@ -156,7 +161,10 @@ __device__ __forceinline__ void hs_correct(const HSParams& hs, double x1, double
     double k[7];
     hs_coeffs(a, b, c, d, f1, f2, k);
 
-    double t;
+    double t = DBL_MAX;
+    bool certified = true;      // single exit below: a `return` inside the branches would keep the lanes that leave the
+                                // Newton loop at different rounds apart until the end of the function (measured: the
+                                // closest-point epilogue then ran once per exit group, +85 FP64 instructions per point)
     bool finite_coeffs = true;
 #pragma unroll
     for (int i = 0; i < 7; ++i) finite_coeffs = finite_coeffs && (fabs(k[i]) <= DBL_MAX);
@@ -177,47 +185,48 @@ __device__ __forceinline__ void hs_correct(const HSParams& hs, double x1, double
         // only stop on a 2-ulp bracket.  (Demanding a 2-ulp Newton step made single lanes bisect for ~50 rounds.)
         double lo = -T0, hi = T0;
         t = 0.0;
+        bool done = false;
 #pragma unroll 1
-        for (int it = 0; it < 64; ++it) {
+        for (int it = 0; it < (SLOW ? 64 : kHsFastIters); ++it) {
             double g = k[6], dg = 0.0;
 #pragma unroll
             for (int i = 5; i >= 0; --i) { dg = fma(dg, t, g); g = fma(g, t, k[i]); }
-            if (g == 0.0) break;
+            if (g == 0.0) { done = true; break; }
             if (g < 0.0) lo = t; else hi = t;
             double tn = fma(-g, fast_rcp(dg), t);          // g' > 0 on the bracket (certificate)
-            if (tn == t) break;                            // Newton step below half an ulp: converged
+            if (tn == t) { done = true; break; }           // Newton step below half an ulp: converged
             const bool newton = (tn >= lo && tn <= hi);
             if (!newton) tn = 0.5 * (lo + hi);
             const double step = fabs(tn - t);
             t = tn;
-            if ((newton && step <= 1e-8 * fabs(tn)) || (hi - lo) <= 4e-16 * fabs(tn)) break;
+            if ((newton && step <= 1e-8 * fabs(tn)) || (hi - lo) <= 4e-16 * fabs(tn)) { done = true; break; }
         }
+        if constexpr (!SLOW) certified = done;
     } else if (finite_coeffs) {
-        t = hs_select_dk(k, a, b, c, d, f1, f2);
-    } else {
-        t = DBL_MAX;
+        if constexpr (SLOW) t = hs_select_dk(k, a, b, c, d, f1, f2);
+        else certified = false;
     }
-    if (t == DBL_MAX) {
-        // t = inf wins (or non-finite system): the reference evaluates inf/inf -> NaN for both points
-        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-        n1x = n1y = n2x = n2y = qnan;
-        return;
-    }
-    // closest points to the origin on the two epipolar lines, then back through R^T and T^-1
+    // hot kernel (all 32 lanes are here): re-converge the lanes that left the Newton loop at different rounds
+    if constexpr (!SLOW) __syncwarp();
+    // closest points to the origin on the two epipolar lines, then back through R^T and T^-1.  t == DBL_MAX: t = inf
+    // wins (or non-finite system) -- the reference evaluates inf/inf -> NaN for both points.
+    const bool at_inf = (t == DBL_MAX);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     {
         const double iz = fast_rcp(fma(t * t, f1s, 1.0));
         const double hx = t * t * f1 * iz, hy = t * iz;
-        n1x = fma(e1x, hx, -e1y * hy) + x1;
-        n1y = fma(e1y, hx, e1x * hy) + y1;
+        n1x = at_inf ? qnan : fma(e1x, hx, -e1y * hy) + x1;
+        n1y = at_inf ? qnan : fma(e1y, hx, e1x * hy) + y1;
     }
     {
         const double ct_d = fma(c, t, d), at_b = fma(a, t, b);
         const double hz = fma(f2 * f2 * ct_d, ct_d, at_b * at_b);
         const double iz = (hz > 0.0) ? fast_rcp(hz) : 1.0 / hz;
         const double hx = f2 * ct_d * ct_d * iz, hy = -at_b * ct_d * iz;
-        n2x = fma(e2x, hx, -e2y * hy) + x2;
-        n2y = fma(e2y, hx, e2x * hy) + y2;
+        n2x = at_inf ? qnan : fma(e2x, hx, -e2y * hy) + x2;
+        n2y = at_inf ? qnan : fma(e2y, hx, e2x * hy) + y2;
     }
+    return certified;
 }
 
 }  // namespace trgl

@@ -7,16 +7,155 @@
 #include "trgl_eval.cuh"
 
 #ifndef TRGL_EIGEN_MINB
-#define TRGL_EIGEN_MINB 2          // resident CTAs per SM the register allocation is sized for
+#define TRGL_EIGEN_MINB 3          // resident CTAs per SM the register allocation is sized for (76-80 registers)
+#endif
+#ifndef TRGL_EVAL_MINB
+#define TRGL_EVAL_MINB 2           // linear_eigen / polynomial with the evaluation epilogue: measured faster with 128 registers
 #endif
 #ifndef TRGL_POLY_MINB
-#define TRGL_POLY_MINB 2
+#define TRGL_POLY_MINB 3
 #endif
 #ifndef TRGL_ITER_MINB
-#define TRGL_ITER_MINB 2
+#define TRGL_ITER_MINB 3          // 80 registers with the evaluation epilogue, no spills
 #endif
 
 namespace trgl {
+
+// ---- two-ray closed form of the re-weighted solve --------------------------------------------------------------
+// The system of one correspondence is rows (a0, a1) of view 1 scaled by w1 and rows (c0, c1) of view 2 scaled by w2
+// (triangulation.c:30-40,143-146).  Each view's two planes meet in its viewing ray  C_k + t n_k  (n1 = a0 x a1,
+// C_k = camera centre, the null vector of P_k), so M_k = A_k^T A_k has rank 2, adj(M_k) = n_k n_k^T, and by
+// Cauchy-Binet the normal-equation solution of the weighted system is, exactly,
+//     x(kappa) = (X1 + kappa X2) / (1 + kappa),      kappa = (w2/w1)^2 * B/A,
+// where X1 = C1 + (t1/A) n1 is the point of ray 1 that minimises the view-2 residuals, X2 the point of ray 2 that
+// minimises the view-1 residuals, A = (c0.n1)^2 + (c1.n1)^2, B = (a0.n2)^2 + (a1.n2)^2, t1 = -sum_j (c_j.C1 - b_j)(c_j.n1).
+// Only the weight RATIO moves during the iteration, and the depths are the same convex combination of the depths of
+// X1 and X2, so one re-weighting round costs ~24 FP64 instructions instead of a fresh 3x3 solve (~80), with error
+// ~ kappa(A) eps (no squaring: agrees with the SVD solve to < 1e-10 up to kappa^2 = 1e12, see tests).
+template <typename T> struct RayGeom { T C1[3], C2[3], E1[3], E2[3]; int ok; int pad_; };   // E1 = P1 [C2;1], E2 = P2 [C1;1]
+template <typename T> struct TwoRay { T X1[3], X2[3], kap, d11, d12, d21, d22; };
+constexpr int kTwoRayState = 13;            // kap d1 d2 d11 d12 d21 d22 X1[3] X2[3]
+
+// kappa in [2^-27, 2^27]: the squared ratio of the weighted row norms of the two views.  Outside (or NaN) the reference's
+// SVD is ill-conditioned by the imbalance itself and the point goes to the general path.
+__device__ __forceinline__ bool kappa_in_range(double kap) {
+    const unsigned e = (static_cast<unsigned>(__double2hiint(kap)) >> 20) & 0xfffu;     // sign + exponent
+    return (e - (1023u - 27u)) <= 54u;
+}
+
+
+template <typename T>
+__device__ __forceinline__ bool tworay_setup(const Cams<T>& cams, const RayGeom<T>& g, T u1x, T u1y, T u2x, T u2y,
+                                             TwoRay<T>& R) {
+    T a0[3], a1[3], c0[3], c1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a0[k] = tfma(u1x, cams.P1[8 + k], -cams.P1[k]);  a1[k] = tfma(u1y, cams.P1[8 + k], -cams.P1[4 + k]);
+        c0[k] = tfma(u2x, cams.P2[8 + k], -cams.P2[k]);  c1[k] = tfma(u2y, cams.P2[8 + k], -cams.P2[4 + k]);
+    }
+    const T n1[3] = {tfma(a0[1], a1[2], -a0[2] * a1[1]), tfma(a0[2], a1[0], -a0[0] * a1[2]), tfma(a0[0], a1[1], -a0[1] * a1[0])};
+    const T n2[3] = {tfma(c0[1], c1[2], -c0[2] * c1[1]), tfma(c0[2], c1[0], -c0[0] * c1[2]), tfma(c0[0], c1[1], -c0[1] * c1[0])};
+    const T s0 = tfma(c0[0], n1[0], tfma(c0[1], n1[1], c0[2] * n1[2])), s1 = tfma(c1[0], n1[0], tfma(c1[1], n1[1], c1[2] * n1[2]));
+    const T r0 = tfma(a0[0], n2[0], tfma(a0[1], n2[1], a0[2] * n2[2])), r1 = tfma(a1[0], n2[0], tfma(a1[1], n2[1], a1[2] * n2[2]));
+    const T A = tfma(s0, s0, s1 * s1), B = tfma(r0, r0, r1 * r1);
+    // residuals of the other view's planes at this view's camera centre: c_j.C1 - b_j = u2 * E2[2] - E2[j]
+    const T e0 = tfma(u2x, g.E2[2], -g.E2[0]), e1 = tfma(u2y, g.E2[2], -g.E2[1]);
+    const T f0 = tfma(u1x, g.E1[2], -g.E1[0]), f1 = tfma(u1y, g.E1[2], -g.E1[1]);
+    const T t1 = -tfma(e0, s0, e1 * s1), t2 = -tfma(f0, r0, f1 * r1);
+    T tr = a0[0] * a0[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k) tr = tfma(a0[k], a0[k], tr);
+        tr = tfma(a1[k], a1[k], tr); tr = tfma(c0[k], c0[k], tr); tr = tfma(c1[k], c1[k], tr);
+    }
+    // det(M1 + M2) = A + B; the same kappa^2 bound as the normal-equation tiers, at the tier-2 limit
+    const bool well = (tr * tr * tr < Tiers<T>::t2() * (A + B)) && (A > T(0)) && (B > T(0));
+    const T iA = fast_rcp(A), iB = fast_rcp(B);
+    const T tau1 = t1 * iA, tau2 = t2 * iB;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { R.X1[k] = tfma(tau1, n1[k], g.C1[k]); R.X2[k] = tfma(tau2, n2[k], g.C2[k]); }
+    R.kap = B * iA;
+    R.d11 = tfma(cams.P1[8], R.X1[0], tfma(cams.P1[9], R.X1[1], tfma(cams.P1[10], R.X1[2], cams.P1[11])));
+    R.d12 = tfma(cams.P1[8], R.X2[0], tfma(cams.P1[9], R.X2[1], tfma(cams.P1[10], R.X2[2], cams.P1[11])));
+    R.d21 = tfma(cams.P2[8], R.X1[0], tfma(cams.P2[9], R.X1[1], tfma(cams.P2[10], R.X1[2], cams.P2[11])));
+    R.d22 = tfma(cams.P2[8], R.X2[0], tfma(cams.P2[9], R.X2[1], tfma(cams.P2[10], R.X2[2], cams.P2[11])));
+    return well && kappa_in_range(static_cast<double>(R.kap));
+}
+
+// Intersection of the two viewing rays, for matches that satisfy the epipolar constraint (the output of the Hartley-Sturm
+// correction): the DLT matrix then has an exact null vector, and the smallest singular vector cv2.triangulatePoints
+// returns, dehomogenised, IS the least-squares point (X1 A + X2 B) / (A + B) of the two-ray form (they differ by
+// O(residual^2 / gap); agrees with the SVD solve to < 2e-10 on all rigs, see tests).  Returns false -- the caller then runs
+// the eigen solver -- unless (i) the system is well conditioned (same kappa^2 bound as above) and (ii) each ray passes
+// through the other view's planes: squared residual of view 2 at X1 = ee - t1^2/A <= res_tol * ee, likewise for view 1.
+template <typename T>
+__device__ __forceinline__ bool tworay_intersection(const Cams<T>& cams, const RayGeom<T>& g, T u1x, T u1y, T u2x, T u2y,
+                                                    T res_tol, T x[3]) {
+    T a0[3], a1[3], c0[3], c1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a0[k] = tfma(u1x, cams.P1[8 + k], -cams.P1[k]);  a1[k] = tfma(u1y, cams.P1[8 + k], -cams.P1[4 + k]);
+        c0[k] = tfma(u2x, cams.P2[8 + k], -cams.P2[k]);  c1[k] = tfma(u2y, cams.P2[8 + k], -cams.P2[4 + k]);
+    }
+    const T n1[3] = {tfma(a0[1], a1[2], -a0[2] * a1[1]), tfma(a0[2], a1[0], -a0[0] * a1[2]), tfma(a0[0], a1[1], -a0[1] * a1[0])};
+    const T n2[3] = {tfma(c0[1], c1[2], -c0[2] * c1[1]), tfma(c0[2], c1[0], -c0[0] * c1[2]), tfma(c0[0], c1[1], -c0[1] * c1[0])};
+    const T s0 = tfma(c0[0], n1[0], tfma(c0[1], n1[1], c0[2] * n1[2])), s1 = tfma(c1[0], n1[0], tfma(c1[1], n1[1], c1[2] * n1[2]));
+    const T r0 = tfma(a0[0], n2[0], tfma(a0[1], n2[1], a0[2] * n2[2])), r1 = tfma(a1[0], n2[0], tfma(a1[1], n2[1], a1[2] * n2[2]));
+    const T A = tfma(s0, s0, s1 * s1), B = tfma(r0, r0, r1 * r1);
+    const T e0 = tfma(u2x, g.E2[2], -g.E2[0]), e1 = tfma(u2y, g.E2[2], -g.E2[1]);
+    const T f0 = tfma(u1x, g.E1[2], -g.E1[0]), f1 = tfma(u1y, g.E1[2], -g.E1[1]);
+    const T t1 = -tfma(e0, s0, e1 * s1), t2 = -tfma(f0, r0, f1 * r1);
+    T tr = a0[0] * a0[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k) tr = tfma(a0[k], a0[k], tr);
+        tr = tfma(a1[k], a1[k], tr); tr = tfma(c0[k], c0[k], tr); tr = tfma(c1[k], c1[k], tr);
+    }
+    const T D = A + B;
+    const T eeA = tfma(e0, e0, e1 * e1) * A, ffB = tfma(f0, f0, f1 * f1) * B;
+    const bool ok = (tr * tr * tr < Tiers<T>::t2() * D) &&
+                    (tfma(-t1, t1, eeA) <= res_tol * eeA) && (tfma(-t2, t2, ffB) <= res_tol * ffB);
+    const T inv = fast_rcp(D);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[k] = tfma(A, g.C1[k], tfma(t1, n1[k], tfma(B, g.C2[k], t2 * n2[k]))) * inv;
+    return ok;
+}
+
+// One re-weighting round in closed form (triangulation.c:128-148).  Returns 1 when the reference's loop breaks here,
+// 0 to continue, -1 when the point has to be redone by the general path (exact-zero depth under the Python control
+// flow, weight ratio out of range).  `kap_used`, `inv` = kappa and 1 / (1 + kappa) of the round that was evaluated: the
+// solve of that round is x = (X1 + kap_used X2) * inv.
+template <typename T>
+__device__ __forceinline__ int tworay_step(const T d11, const T d12, const T d21, const T d22, T& kap, T& d1, T& d2,
+                                           T& d1n, T& d2n, T& inv, T& kap_used, const T tolerance, const int py_semantics) {
+    kap_used = kap;
+    inv = fast_rcp(T(1) + kap);
+    d1n = tfma(kap, d12, d11) * inv;                                                                  // triangulation.c:133
+    d2n = tfma(kap, d22, d21) * inv;
+    const bool conv = (tabs(d1n - d1) <= tolerance) && (tabs(d2n - d2) <= tolerance);
+    const bool zero = (d1n == T(0)) || (d2n == T(0));                                                 // triangulation.c:138
+    if (conv || (zero && !py_semantics)) return 1;
+    if (zero) return -1;
+    const T r = d1n * fast_rcp(d2n);                // cumulative re-weighting: (w2/w1)^2 *= (d1n/d2n)^2, triangulation.c:143-146
+    kap *= r * r;
+    d1 = d1n; d2 = d2n;
+    return kappa_in_range(static_cast<double>(kap)) ? 0 : -1;
+}
+
+// Uncertified points leave the hot kernels through a deferred list in global memory and are solved by a small follow-up
+// kernel (k_iterative_general / k_linear_eigen_general) with the reference's arithmetic as written.  Keeping that
+// ~120-register path -- and the subroutine calls of its SVD tier -- out of the hot kernels is what lets them run without
+// a single spill and at 3 CTAs per SM: with the call inside, ptxas kept the loop state of the persistent loop in local
+// memory (profiles/r01f).
+struct Deferred {
+    int64_t* idx;                 // [cap] indices of the points to redo
+    unsigned int* ctl;            // ctl[0] = number of deferred points (may exceed cap), ctl[1] = ticket of the follow-up kernel
+    unsigned int cap;
+};
+__device__ __forceinline__ void defer_point(const Deferred& df, int64_t i) {
+    const unsigned int k = atomicAdd(&df.ctl[0], 1u);
+    if (k < df.cap) df.idx[k] = i;            // on overflow the follow-up kernel redoes every point instead
+}
 
 
 // ---- linear_LS_triangulation (triangulation.c:65-83) -----------------------------------------------------------
@@ -261,114 +400,31 @@ __device__ __forceinline__ int iter_point_general(const Cams<TC>& cams, TC a, TC
     return it;
 }
 
-// ---- two-ray closed form of the re-weighted solve --------------------------------------------------------------
-// The system of one correspondence is rows (a0, a1) of view 1 scaled by w1 and rows (c0, c1) of view 2 scaled by w2
-// (triangulation.c:30-40,143-146).  Each view's two planes meet in its viewing ray  C_k + t n_k  (n1 = a0 x a1,
-// C_k = camera centre, the null vector of P_k), so M_k = A_k^T A_k has rank 2, adj(M_k) = n_k n_k^T, and by
-// Cauchy-Binet the normal-equation solution of the weighted system is, exactly,
-//     x(kappa) = (X1 + kappa X2) / (1 + kappa),      kappa = (w2/w1)^2 * B/A,
-// where X1 = C1 + (t1/A) n1 is the point of ray 1 that minimises the view-2 residuals, X2 the point of ray 2 that
-// minimises the view-1 residuals, A = (c0.n1)^2 + (c1.n1)^2, B = (a0.n2)^2 + (a1.n2)^2, t1 = -sum_j (c_j.C1 - b_j)(c_j.n1).
-// Only the weight RATIO moves during the iteration, and the depths are the same convex combination of the depths of
-// X1 and X2, so one re-weighting round costs ~24 FP64 instructions instead of a fresh 3x3 solve (~80), with error
-// ~ kappa(A) eps (no squaring: checked against the SVD oracle to < 1e-10 up to kappa^2 = 1e12).
-template <typename T> struct RayGeom { T C1[3], C2[3], E1[3], E2[3]; int ok; int pad_; };   // E1 = P1 [C2;1], E2 = P2 [C1;1]
-template <typename T> struct TwoRay { T X1[3], X2[3], kap, d11, d12, d21, d22; };
-constexpr int kTwoRayState = 13;            // kap d1 d2 d11 d12 d21 d22 X1[3] X2[3]
-
-// kappa in [2^-27, 2^27]: the squared ratio of the weighted row norms of the two views.  Outside (or NaN) the reference's
-// SVD is ill-conditioned by the imbalance itself and the point goes to the general path.
-__device__ __forceinline__ bool kappa_in_range(double kap) {
-    const unsigned e = (static_cast<unsigned>(__double2hiint(kap)) >> 20) & 0xfffu;     // sign + exponent
-    return (e - (1023u - 27u)) <= 54u;
-}
-
-template <typename T> __device__ __forceinline__ T kap_nan();
-template <> __device__ __forceinline__ double kap_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
-template <> __device__ __forceinline__ float kap_nan<float>() { return __int_as_float(0x7fc00000); }
-
-template <typename T>
-__device__ __forceinline__ bool tworay_setup(const Cams<T>& cams, const RayGeom<T>& g, T u1x, T u1y, T u2x, T u2y,
-                                             TwoRay<T>& R) {
-    T a0[3], a1[3], c0[3], c1[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        a0[k] = tfma(u1x, cams.P1[8 + k], -cams.P1[k]);  a1[k] = tfma(u1y, cams.P1[8 + k], -cams.P1[4 + k]);
-        c0[k] = tfma(u2x, cams.P2[8 + k], -cams.P2[k]);  c1[k] = tfma(u2y, cams.P2[8 + k], -cams.P2[4 + k]);
-    }
-    const T n1[3] = {tfma(a0[1], a1[2], -a0[2] * a1[1]), tfma(a0[2], a1[0], -a0[0] * a1[2]), tfma(a0[0], a1[1], -a0[1] * a1[0])};
-    const T n2[3] = {tfma(c0[1], c1[2], -c0[2] * c1[1]), tfma(c0[2], c1[0], -c0[0] * c1[2]), tfma(c0[0], c1[1], -c0[1] * c1[0])};
-    const T s0 = tfma(c0[0], n1[0], tfma(c0[1], n1[1], c0[2] * n1[2])), s1 = tfma(c1[0], n1[0], tfma(c1[1], n1[1], c1[2] * n1[2]));
-    const T r0 = tfma(a0[0], n2[0], tfma(a0[1], n2[1], a0[2] * n2[2])), r1 = tfma(a1[0], n2[0], tfma(a1[1], n2[1], a1[2] * n2[2]));
-    const T A = tfma(s0, s0, s1 * s1), B = tfma(r0, r0, r1 * r1);
-    // residuals of the other view's planes at this view's camera centre: c_j.C1 - b_j = u2 * E2[2] - E2[j]
-    const T e0 = tfma(u2x, g.E2[2], -g.E2[0]), e1 = tfma(u2y, g.E2[2], -g.E2[1]);
-    const T f0 = tfma(u1x, g.E1[2], -g.E1[0]), f1 = tfma(u1y, g.E1[2], -g.E1[1]);
-    const T t1 = -tfma(e0, s0, e1 * s1), t2 = -tfma(f0, r0, f1 * r1);
-    T tr = a0[0] * a0[0];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (k) tr = tfma(a0[k], a0[k], tr);
-        tr = tfma(a1[k], a1[k], tr); tr = tfma(c0[k], c0[k], tr); tr = tfma(c1[k], c1[k], tr);
-    }
-    // det(M1 + M2) = A + B; the same kappa^2 bound as the normal-equation tiers, at the tier-2 limit
-    const bool well = (tr * tr * tr < Tiers<T>::t2() * (A + B)) && (A > T(0)) && (B > T(0));
-    const T iA = fast_rcp(A), iB = fast_rcp(B);
-    const T tau1 = t1 * iA, tau2 = t2 * iB;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { R.X1[k] = tfma(tau1, n1[k], g.C1[k]); R.X2[k] = tfma(tau2, n2[k], g.C2[k]); }
-    R.kap = B * iA;
-    R.d11 = tfma(cams.P1[8], R.X1[0], tfma(cams.P1[9], R.X1[1], tfma(cams.P1[10], R.X1[2], cams.P1[11])));
-    R.d12 = tfma(cams.P1[8], R.X2[0], tfma(cams.P1[9], R.X2[1], tfma(cams.P1[10], R.X2[2], cams.P1[11])));
-    R.d21 = tfma(cams.P2[8], R.X1[0], tfma(cams.P2[9], R.X1[1], tfma(cams.P2[10], R.X1[2], cams.P2[11])));
-    R.d22 = tfma(cams.P2[8], R.X2[0], tfma(cams.P2[9], R.X2[1], tfma(cams.P2[10], R.X2[2], cams.P2[11])));
-    return well && kappa_in_range(static_cast<double>(R.kap));
-}
-
-// One re-weighting round in closed form (triangulation.c:128-148).  Returns 1 when the reference's loop breaks here,
-// 0 to continue, -1 when the point has to be redone by the general path (exact-zero depth under the Python control
-// flow, weight ratio out of range).  `kap_used`, `inv` = kappa and 1 / (1 + kappa) of the round that was evaluated: the
-// solve of that round is x = (X1 + kap_used X2) * inv.
-template <typename T>
-__device__ __forceinline__ int tworay_step(const T d11, const T d12, const T d21, const T d22, T& kap, T& d1, T& d2,
-                                           T& d1n, T& d2n, T& inv, T& kap_used, const T tolerance, const int py_semantics) {
-    kap_used = kap;
-    inv = fast_rcp(T(1) + kap);
-    d1n = tfma(kap, d12, d11) * inv;                                                                  // triangulation.c:133
-    d2n = tfma(kap, d22, d21) * inv;
-    const bool conv = (tabs(d1n - d1) <= tolerance) && (tabs(d2n - d2) <= tolerance);
-    const bool zero = (d1n == T(0)) || (d2n == T(0));                                                 // triangulation.c:138
-    if (conv || (zero && !py_semantics)) return 1;
-    if (zero) return -1;
-    const T r = d1n * fast_rcp(d2n);                // cumulative re-weighting: (w2/w1)^2 *= (d1n/d2n)^2, triangulation.c:143-146
-    kap *= r * r;
-    d1 = d1n; d2 = d2n;
-    return kappa_in_range(static_cast<double>(kap)) ? 0 : -1;
-}
-
 // Persistent CTAs (one grid-stride loop over 256-point tiles, the next tile's four input scalars prefetched with cp.async
-// while the current tile is solved) with a block-level FIFO work queue in shared memory for the divergent tail:
-//   phase 1: every thread sets up the two-ray form of its point and runs the first kPhase1 rounds (on translating rigs
+// while the current tile is solved); inside a CTA every WARP is autonomous -- it owns the 32-point slice of each tile, a
+// FIFO work queue in shared memory for its divergent tail, and its own store staging, so the kernel has no block barrier
+// and no atomic:
+//   phase 1: every lane sets up the two-ray form of its point and runs the first kPhase1 rounds (on translating rigs
 //            every point converges at the second solve; on rotating rigs ~70 % do).  Finished points leave through the
 //            coalesced store.
-//   queue  : points still running push their closed-form state (13 scalars) to a circular queue.
-//   phase 2: whenever the queue holds >= 256 entries the block runs the remaining rounds on the OLDEST 256, so
-//            every warp is dense instead of idling on the ~30 % of lanes that need all 10 solves; the remainder is
-//            flushed after the last tile.
-//   mirrors: with result mirrors (multi-GPU gather) a tile is copied to the peers, fully coalesced, as soon as no point
-//            of it is queued any more -- FIFO order makes that "every tile before the one of the oldest queued entry" --
-//            instead of repeating phase 2's scattered 8-byte stores over NVLink.
+//   queue  : lanes still running push their closed-form state (13 scalars) to the warp's circular queue (slot = ballot
+//            prefix; head / count are warp-uniform registers).
+//   phase 2: whenever the queue holds >= 32 entries the warp runs the remaining rounds on the OLDEST 32, so the warp is
+//            dense instead of idling on the ~30 % of lanes that need all 10 solves; the remainder is flushed after the
+//            last tile.
+//   mirrors: with result mirrors (multi-GPU gather) a 32-point slice is copied to the peers, fully coalesced, as soon as
+//            no point of it is queued any more -- FIFO order makes that "every slice before the one of the oldest queued
+//            entry" -- instead of repeating phase 2's scattered 8-byte stores over NVLink.
 constexpr int kPhase1 = 2;
-constexpr int kQueueCap = 2 * kThreads;                  // power of two
+constexpr int kWarpQueueCap = 64;                        // per warp: <= 31 left over + 32 pushed; power of two
 
 // Shared memory of one k_iterative_ls CTA (dynamic: above the static limit in the all-double mode).
 template <typename TI, typename TC, typename TO>
 struct IterSmem {
-    PairPrefetch<TI, kThreads> pre;          // cp.async landing zone of the next tile
-    TC q_state[kTwoRayState][kQueueCap];     // queue: closed-form state of the point
-    int64_t q_idx[kQueueCap];                //        global point index
-    TO stage[kWarps][96];                    // coalesced (n,3) store staging
-    unsigned int q_tail;                     // total number of pushes so far (slot = position & (kQueueCap-1))
+    PairPrefetch<TI, kThreads> pre;                      // cp.async landing zone of the next tile
+    TC q_state[kWarps][kTwoRayState][kWarpQueueCap];     // per-warp queue: closed-form state of the point
+    int64_t q_idx[kWarps][kWarpQueueCap];                //                 global point index
+    TO stage[kWarps][96];                                // coalesced (n,3) store staging
 };
 
 // The four input scalars of point i again (phase 2 needs them for the evaluation epilogue and for the general path):
@@ -383,52 +439,53 @@ __device__ __forceinline__ void reload_inputs(const TI* __restrict__ u1, const T
 
 template <typename TI, typename TC, typename TO, class PRE, bool EVAL>
 __device__ __forceinline__ void iter_ls_phase2(const TI* __restrict__ u1, const TI* __restrict__ u2, const PRE& pre_stage,
-                                               const Cams<TC>& cams, const TC (*q_state)[kQueueCap], const int64_t* q_idx,
+                                               const Cams<TC>& cams, const TC (*q_state)[kWarpQueueCap], const int64_t* q_idx,
                                                int slot, TO* __restrict__ x, int32_t* __restrict__ status,
-                                               TC tolerance, int py_semantics, const EvalArg<EVAL>& ev, double (&acc)[4]) {
+                                               TC tolerance, int py_semantics, const EvalArg<EVAL>& ev, const Deferred& df,
+                                               double (&acc)[4]) {
     TC kap = q_state[0][slot], d1 = q_state[1][slot], d2 = q_state[2][slot];
     const int64_t dst = q_idx[slot];
-    TC a = 0, b = 0, c = 0, d = 0;
-    if constexpr (EVAL) reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, dst, a, b, c, d);     // in flight during the rounds
-    TC d1n = d1, d2n = d2, xs[3];
-    int it = py_semantics ? 9 : 10;                 // value of the loop variable after a loop that never breaks
     int r = -1;
-    if (kap == kap) {                               // NaN marks a point that phase 1 could not certify
+    {
+        TC a = 0, b = 0, c = 0, d = 0;
+        if constexpr (EVAL) reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, dst, a, b, c, d);     // in flight during the rounds
         const TC d11 = q_state[3][slot], d12 = q_state[4][slot], d21 = q_state[5][slot], d22 = q_state[6][slot];
-        TC inv = 1, kap_used = kap;
+        TC d1n = d1, d2n = d2, inv = 1, kap_used = kap;
+        int it = py_semantics ? 9 : 10;             // value of the loop variable after a loop that never breaks
 #pragma unroll 1
         for (int k = kPhase1; k < 10; ++k) {
             r = tworay_step<TC>(d11, d12, d21, d22, kap, d1, d2, d1n, d2n, inv, kap_used, tolerance, py_semantics);
             if (r) { if (r > 0) it = k; break; }
         }
-        // the last solve that was evaluated is the result (triangulation.c:130,150)
+        if (r >= 0) {                               // the last solve that was evaluated is the result (triangulation.c:130,150)
+            TC xs[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) xs[k] = tfma(kap_used, q_state[10 + k][slot], q_state[7 + k][slot]) * inv;
+            for (int k = 0; k < 3; ++k) xs[k] = tfma(kap_used, q_state[10 + k][slot], q_state[7 + k][slot]) * inv;
+            x[3 * dst + 0] = static_cast<TO>(xs[0]);
+            x[3 * dst + 1] = static_cast<TO>(xs[1]);
+            x[3 * dst + 2] = static_cast<TO>(xs[2]);
+            const int st = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+            status[dst] = st;
+            fused_eval_point<EVAL, TO, TC>(ev, true, dst, a, b, c, d, xs, st, acc);
+        }
     }
-    if (r < 0) {                                    // the reference's loop as written, from the first solve
-        if constexpr (!EVAL) reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, dst, a, b, c, d);
-        it = iter_point_general<TC>(cams, a, b, c, d, tolerance, py_semantics, xs, d1n, d2n);
-    }
-    x[3 * dst + 0] = static_cast<TO>(xs[0]);
-    x[3 * dst + 1] = static_cast<TO>(xs[1]);
-    x[3 * dst + 2] = static_cast<TO>(xs[2]);
-    const int st = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
-    status[dst] = st;
-    fused_eval_point<EVAL, TO, TC>(ev, true, dst, a, b, c, d, xs, st, acc);
+    if (r < 0) defer_point(df, dst);                // weight ratio left its range / exact-zero depth: the follow-up kernel redoes it
 }
 
-// Copy one finished 256-point tile of x / status from local HBM to every mirror (whole CTA, coalesced).
+// Copy one finished 32-point slice of x / status from local HBM to every mirror (one warp, coalesced rows).
 template <typename TO>
-__device__ __forceinline__ void mirror_tile(const TO* __restrict__ x, const int32_t* __restrict__ status, const Mirrors& mir,
-                                            int64_t base, int64_t n) {
-    const int cnt = (n - base) >= kThreads ? kThreads : static_cast<int>(n - base);
-    for (int idx = threadIdx.x; idx < cnt * 3; idx += kThreads) {
+__device__ __forceinline__ void mirror_slice(const TO* __restrict__ x, const int32_t* __restrict__ status, const Mirrors& mir,
+                                             int64_t base, int64_t n) {
+    if (base >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int cnt = (n - base) >= 32 ? 32 : static_cast<int>(n - base);
+    for (int idx = lane; idx < cnt * 3; idx += 32) {
         const TO v = __ldcg(x + base * 3 + idx);
         for (int r = 0; r < mir.count; ++r) static_cast<TO*>(mir.x[r])[base * 3 + idx] = v;
     }
-    if (static_cast<int>(threadIdx.x) < cnt) {
-        const int32_t v = __ldcg(status + base + threadIdx.x);
-        for (int r = 0; r < mir.count; ++r) static_cast<int32_t*>(mir.status[r])[base + threadIdx.x] = v;
+    if (lane < cnt) {
+        const int32_t v = __ldcg(status + base + lane);
+        for (int r = 0; r < mir.count; ++r) static_cast<int32_t*>(mir.status[r])[base + lane] = v;
     }
 }
 
@@ -437,23 +494,23 @@ __global__ void __launch_bounds__(kThreads, TRGL_ITER_MINB)
 k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                const __grid_constant__ RayGeom<TC> geom, TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n,
                const TC tolerance, const int py_semantics, const __grid_constant__ PRE pre_stage,
-               const __grid_constant__ Mirrors mir, const __grid_constant__ EvalArg<EVAL> ev) {
+               const __grid_constant__ Mirrors mir, const __grid_constant__ EvalArg<EVAL> ev,
+               const __grid_constant__ Deferred df) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IterSmem<TI, TC, TO>& sm = *reinterpret_cast<IterSmem<TI, TC, TO>*>(smem_raw);
-    auto& pre = sm.pre; auto& q_state = sm.q_state; auto& q_idx = sm.q_idx; auto& stage = sm.stage;
-    const Mirrors local_only = {0, 0, {nullptr}, {nullptr}};       // this kernel mirrors whole tiles, see above
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto& pre = sm.pre; auto& q_state = sm.q_state[warp]; auto& q_idx = sm.q_idx[warp]; auto& stage = sm.stage[warp];
+    const Mirrors local_only = {0, 0, {nullptr}, {nullptr}};       // this kernel mirrors whole slices, see above
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
     const int64_t first = static_cast<int64_t>(blockIdx.x) * kThreads;
-    if (threadIdx.x == 0) sm.q_tail = 0u;
-    __syncthreads();
-    int64_t tile = first;
-    int64_t mirrored = first;                            // next tile of this CTA to copy to the mirrors
-    unsigned int head = 0u;                              // position of the oldest queued entry  } identical in
-    int count = 0;                                       // queue length                         } every thread
+    // loop-carried state is four 32-bit registers: pass number, mirrored passes, queue tail and length (warp-uniform)
+    int mirrored = 0;                                    // passes of this CTA whose slice this warp has copied to the mirrors
+    unsigned int tail = 0u;                              // queue position of the next push (oldest entry = tail - count)
+    int count = 0;                                       // queue length
     double acc[4] = {0, 0, 0, 0};                        // fused evaluation sums of this thread
-    pre.issue(u1, u2, tile + threadIdx.x, n);
-    for (;; tile += stride) {
+    pre.issue(u1, u2, first + threadIdx.x, n);
+    for (int pass = 0;; ++pass) {
+        const int64_t tile = first + pass * stride;
         const bool have_tile = tile < n;                 // block-uniform; the pass after the last tile only flushes the queue
         if (have_tile) {
             const int64_t i = tile + threadIdx.x;
@@ -465,7 +522,7 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
             TC xs[3] = {0, 0, 0};
             TC kap = 0, d1 = 1, d2 = 1, d1n = 1, d2n = 1, inv = 1, kap_used = 1;
             int it = -1, r = -1;
-            if (geom.ok && tworay_setup<TC>(cams, geom, a, b, c, d, R)) {
+            if (tworay_setup<TC>(cams, geom, a, b, c, d, R)) {
                 kap = R.kap;
 #pragma unroll 1
                 for (int k = 0; k < kPhase1; ++k) {
@@ -477,56 +534,107 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
 #pragma unroll
                 for (int k = 0; k < 3; ++k) xs[k] = tfma(kap_used, R.X2[k], R.X1[k]) * inv;
             }
-            // r == 0: still iterating; r < 0: not certified -> queued with kappa = NaN, the drain runs the general path
-            const bool pending = (r <= 0) && (i < n);
+            // r == 0: still iterating -> queued; r < 0: not certified -> deferred to the follow-up kernel
+            const bool pending = (r == 0) && (i < n);
+            if (r < 0 && i < n) defer_point(df, i);
             const unsigned ball = __ballot_sync(0xffffffffu, pending);
-            if (ball) {
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(&sm.q_tail, static_cast<unsigned int>(__popc(ball)));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pending) {
-                    const int slot = static_cast<int>((base + __popc(ball & ((1u << lane) - 1u))) & (kQueueCap - 1));
-                    q_state[0][slot] = (r == 0) ? kap : kap_nan<TC>();
-                    q_state[1][slot] = d1; q_state[2][slot] = d2;
-                    q_state[3][slot] = R.d11; q_state[4][slot] = R.d12; q_state[5][slot] = R.d21; q_state[6][slot] = R.d22;
+            if (pending) {
+                const int slot = static_cast<int>((tail + __popc(ball & ((1u << lane) - 1u))) & (kWarpQueueCap - 1));
+                q_state[0][slot] = kap;
+                q_state[1][slot] = d1; q_state[2][slot] = d2;
+                q_state[3][slot] = R.d11; q_state[4][slot] = R.d12; q_state[5][slot] = R.d21; q_state[6][slot] = R.d22;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { q_state[7 + k][slot] = R.X1[k]; q_state[10 + k][slot] = R.X2[k]; }
-                    q_idx[slot] = i;
-                }
+                for (int k = 0; k < 3; ++k) { q_state[7 + k][slot] = R.X1[k]; q_state[10 + k][slot] = R.X2[k]; }
+                q_idx[slot] = i;
             }
-            // finished points leave through the coalesced path (pending lanes write a placeholder that phase 2 overwrites)
+            tail += __popc(ball); count += __popc(ball);
+            // finished points leave through the coalesced path (pending lanes write a placeholder that phase 2 overwrites);
+            // the __syncwarp inside also publishes the queue entries to the warp
             store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                             static_cast<TO>(xs[2]), stage[warp], local_only);
-            if (i < n && !pending) {
+                             static_cast<TO>(xs[2]), stage, local_only);
+            if (i < n && r > 0) {
                 const int st = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
                 status[i] = st;
                 fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, st, acc);
             }
-            // every thread learns how many points this tile queued (the barrier also publishes the queue entries and
-            // this tile's stores); head / count live in registers so the drain decision is uniform
-            count += __syncthreads_count(pending);
         }
-        if (count >= kThreads || (!have_tile && count > 0)) {    // count < kQueueCap: <= kThreads-1 left over + kThreads pushed
-            const int take = count < kThreads ? count : kThreads;
-            if (static_cast<int>(threadIdx.x) < take)
+        if (count >= 32 || (!have_tile && count > 0)) {   // count < kWarpQueueCap: <= 31 left over + 32 pushed
+            const int take = count < 32 ? count : 32;
+            __syncwarp();
+            if (lane < take)
                 iter_ls_phase2<TI, TC, TO, PRE, EVAL>(u1, u2, pre_stage, cams, q_state, q_idx,
-                                                      static_cast<int>((head + threadIdx.x) & (kQueueCap - 1)), x, status,
-                                                      tolerance, py_semantics, ev, acc);
-            head += take; count -= take;
-            __syncthreads();                             // the drained slots may be overwritten, the results are visible
+                                                      static_cast<int>((tail - count + lane) & (kWarpQueueCap - 1)), x, status,
+                                                      tolerance, py_semantics, ev, df, acc);
+            count -= take;
+            __syncwarp();                                // the drained slots may be overwritten, the results are visible
         }
         if (mir.count) {
-            // tiles before the one that holds the oldest queued point are final (pushes are in tile order)
-            int64_t safe = have_tile ? tile + stride : n + stride;
-            if (count > 0) {
-                const int64_t oldest = q_idx[head & (kQueueCap - 1)];
-                safe = oldest - ((oldest - first) % stride);
-            }
-            for (; mirrored < safe && mirrored < n; mirrored += stride) mirror_tile<TO>(x, status, mir, mirrored, n);
+            // slices of the passes before the one that holds the oldest queued point are final (pushes are in pass order)
+            int safe = pass + 1;
+            if (count > 0) safe = static_cast<int>((q_idx[(tail - count) & (kWarpQueueCap - 1)] - first) / stride);
+            __syncwarp();
+            for (; mirrored < safe; ++mirrored) mirror_slice<TO>(x, status, mir, first + mirrored * stride + warp * 32, n);
         }
         if (!have_tile) break;
     }
     fused_eval_finish<EVAL>(ev, acc);
+}
+
+// Tail of the follow-up kernels: add this thread's evaluation sums to the sums the hot kernel has already written
+// (warp shuffle + one atomic per warp and sum), then the last block to finish re-arms the list for the next call.
+template <bool EVAL>
+__device__ __forceinline__ void followup_finish(const EvalArg<EVAL>& ev, const Deferred& df, double (&acc)[4], bool any,
+                                                bool rearm) {
+    if constexpr (EVAL) {
+        if (any) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double v = acc[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&ev.e.sums_out[q], v);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && rearm) {
+        __threadfence();
+        if (atomicAdd(&df.ctl[1], 1u) == gridDim.x - 1) { df.ctl[0] = 0u; df.ctl[1] = 0u; __threadfence(); }
+    }
+}
+
+// Follow-up kernel of k_iterative_ls: the reference's loop as written for the deferred points (all == 0: the first
+// ctl[0] entries of the list, or every point if the list overflowed) or for every point (all != 0: cameras without a
+// finite centre / two-ray forms switched off -- then k_iterative_ls is not launched at all).  Results go to x / status
+// and every mirror point by point; evaluation sums are added to the sums the hot kernel has already written.
+template <typename TI, typename TC, typename TO, class PRE = PreNone, bool EVAL = false>
+__global__ void __launch_bounds__(kThreads)
+k_iterative_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
+                    TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n, const TC tolerance,
+                    const int py_semantics, const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
+                    const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df, const int all) {
+    const unsigned int listed = all ? 0u : df.ctl[0];
+    const bool everything = all || listed > df.cap;
+    const int64_t total = everything ? n : static_cast<int64_t>(listed);
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; k < total;
+         k += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const int64_t i = everything ? k : df.idx[k];
+        TC a, b, c, d, xs[3], d1n, d2n;
+        reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, i, a, b, c, d);
+        const int it = iter_point_general<TC>(cams, a, b, c, d, tolerance, py_semantics, xs, d1n, d2n);
+        const int st = iter_ls_status(it, static_cast<double>(d1n), static_cast<double>(d2n));
+#pragma unroll
+        for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
+        status[i] = st;
+        for (int r = 0; r < mir.count; ++r) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) static_cast<TO*>(mir.x[r])[3 * i + q] = static_cast<TO>(xs[q]);
+            static_cast<int32_t*>(mir.status[r])[i] = st;
+        }
+        fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, st, acc);
+    }
+    followup_finish<EVAL>(ev, df, acc, total > 0, !all);
 }
 
 // ---- linear_eigen_triangulation (triangulation.py:6-25) --------------------------------------------------------
@@ -604,7 +712,11 @@ __device__ __forceinline__ int ldl4(const T S[10], const T b[4], T y[4]) {
 // lam + gap*tr(G) (inertia of the shifted matrix).  (i)+(ii) prove X is the eigenvector of the smallest eigenvalue and that
 // it is separated well enough for the G-based computation to be accurate to ~1e-12; otherwise the caller falls back to
 // the Jacobi SVD.  ~450 FP64 instructions instead of ~4800.
-template <typename TC, int ROWS>
+// SYNC: the caller guarantees that all 32 lanes of the warp are here (the hot kernel); the warp is then re-converged
+// right behind the iteration loop, so that the lanes leaving it at different rounds run the certificate and everything
+// the caller does next ONCE -- without it ptxas placed the reconvergence point behind the evaluation epilogue, which
+// then ran 2.3 times per warp (profiles/README.md, r01f).
+template <typename TC, int ROWS, bool SYNC = false>
 __device__ __forceinline__ bool eigen_point_fast(const Cams<TC>& cams, TC u1x, TC u1y, TC u2x, TC u2y, TC X[4]) {
     TC G[10];
     {
@@ -651,18 +763,27 @@ __device__ __forceinline__ bool eigen_point_fast(const Cams<TC>& cams, TC u1x, T
 #pragma unroll
         for (int k = 0; k < 10; ++k) S[k] = G[k];
         S[0] -= lam; S[4] -= lam; S[7] -= lam; S[9] -= lam;
-        if (ldl4<TC, true>(S, X, y) < 0) return false;
+        if (ldl4<TC, true>(S, X, y) < 0) break;            // unusable pivot: not converged, single loop exit
         const TC nrm = trsqrt(tfma(y[0], y[0], tfma(y[1], y[1], tfma(y[2], y[2], y[3] * y[3]))));
 #pragma unroll
         for (int k = 0; k < 4; ++k) X[k] = y[k] * nrm;
     }
-    if (!conv) return false;
+    if constexpr (SYNC) __syncwarp();
     TC S[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) S[k] = G[k];
     const TC shift = lam + (sizeof(TC) == 8 ? TC(2e-5) : TC(2e-3)) * tr;
     S[0] -= shift; S[4] -= shift; S[7] -= shift; S[9] -= shift;
-    return ldl4<TC, false>(S, X, X) == 1;
+    return (ldl4<TC, false>(S, X, X) == 1) && conv;
+}
+
+// Dehomogenise + finite-coordinates mask (triangulation.py:22-23).
+template <typename TC>
+__device__ __forceinline__ void eigen_finish(const TC X[4], TC max_coord, TC xs[3], bool& good) {
+    const TC inv = TC(1) / X[3];
+    xs[0] = X[0] * inv; xs[1] = X[1] * inv; xs[2] = X[2] * inv;        // Inf/NaN when w == 0
+    const TC m = tmax(tmax(tabs(xs[0]), tabs(xs[1])), tabs(xs[2]));
+    good = (xs[0] == xs[0]) && (xs[1] == xs[1]) && (xs[2] == xs[2]) && (m <= max_coord);   // NaN -> False
 }
 
 template <typename TC, int ROWS>
@@ -671,20 +792,23 @@ __device__ __forceinline__ void eigen_point(const Cams<TC>& cams, TC u1x, TC u1y
     TC X[4];
     if (!eigen_point_fast<TC, ROWS>(cams, u1x, u1y, u2x, u2y, X))
         eigen_point_jacobi<TC, ROWS>(cams, u1x, u1y, u2x, u2y, X);
-    const TC inv = TC(1) / X[3];
-    xs[0] = X[0] * inv; xs[1] = X[1] * inv; xs[2] = X[2] * inv;        // triangulation.py:22 (Inf/NaN when w == 0)
-    const TC m = tmax(tmax(tabs(xs[0]), tabs(xs[1])), tabs(xs[2]));
-    good = (xs[0] == xs[0]) && (xs[1] == xs[1]) && (xs[2] == xs[2]) && (m <= max_coord);   // NaN -> False, :23
+    eigen_finish<TC>(X, max_coord, xs, good);
 }
 
-// Persistent CTAs: grid-stride loop over 256-point tiles, the next tile's inputs are prefetched into registers while the
-// current tile is solved (the solve is ~700 instructions per point, so one tile of lookahead hides the HBM latency).
+// Persistent CTAs: grid-stride loop over 256-point tiles, the next tile's inputs prefetched with cp.async while the
+// current tile is solved.  The hot kernel runs the certified Rayleigh-quotient iteration only and has no subroutine call;
+// what it does not certify (breakdown, no convergence in 5 solves, eigenvalue gap below the certificate: points at
+// infinity / on the baseline) is deferred to k_linear_eigen_general, the one-sided Jacobi SVD cv::SVD would run.  With
+// the Jacobi path inside, its ~4800 instructions ran on one or two lanes while the rest of the warp waited: 0.69 ms per
+// 10 M points on the translating rig (0.7 % of the points), 3.1 ms on the forward-motion rig.
+// (A per-warp queue for the lanes that need a third solve, as in k_iterative_ls, was measured and dropped: the compiled
+// resumable iteration cost more per solve than the divergence it removed, profiles/README.md.)
 template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
-__global__ void __launch_bounds__(kThreads, TRGL_EIGEN_MINB)
+__global__ void __launch_bounds__(kThreads, EVAL ? TRGL_EVAL_MINB : TRGL_EIGEN_MINB)
 k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
                TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord,
                const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
-               const __grid_constant__ EvalArg<EVAL> ev) {
+               const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df) {
     double acc[4] = {0, 0, 0, 0};
     __shared__ TO stage[kWarps][96];
     __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
@@ -698,25 +822,70 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         pre.take(i, n, a, b, c, d);
         pre.issue(u1, u2, i + stride, n);
         if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
-        TC xs[3]; bool good;
-        eigen_point<TC, ROWS>(cams, a, b, c, d, max_coord, xs, good);
+        TC X[4], xs[3] = {0, 0, 0};
+        bool good = false;
+        const bool certified = eigen_point_fast<TC, ROWS, true>(cams, a, b, c, d, X);
+        if (certified) eigen_finish<TC>(X, max_coord, xs, good);
+        else if (i < n) defer_point(df, i);
         store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
                          static_cast<TO>(xs[2]), stage[warp], mir);
-        if (i < n) store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
-        fused_eval_point<EVAL, TO, TC>(ev, i < n, i, a, b, c, d, xs, good ? 1 : 0, acc);
+        if (i < n && certified) {
+            store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
+            fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);
+        }
     }
     fused_eval_finish<EVAL>(ev, acc);
 }
 
-// ---- polynomial_triangulation (triangulation.py:198-232) -------------------------------------------------------
-// Hartley-Sturm correction of the match (cv2.correctMatches) followed by the linear-eigen solve, fused.
+// Follow-up kernel of k_linear_eigen: the deferred points (or every point if the list overflowed) through the one-sided
+// Jacobi SVD, the path cv2.triangulatePoints itself takes.
 template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
-__global__ void __launch_bounds__(kThreads, TRGL_POLY_MINB)
-k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams, const __grid_constant__ HSParams hs,
+__global__ void __launch_bounds__(kThreads)
+k_linear_eigen_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
+                       TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord,
+                       const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
+                       const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df) {
+    const unsigned int listed = df.ctl[0];
+    const bool everything = listed > df.cap;
+    const int64_t total = everything ? n : static_cast<int64_t>(listed);
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; k < total;
+         k += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const int64_t i = everything ? k : df.idx[k];
+        TC a, b, c, d, X[4], xs[3];
+        bool good;
+        reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, i, a, b, c, d);
+        eigen_point_jacobi<TC, ROWS>(cams, a, b, c, d, X);
+        eigen_finish<TC>(X, max_coord, xs, good);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
+        for (int m = 0; m < mir.count; ++m) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) static_cast<TO*>(mir.x[m])[3 * i + q] = static_cast<TO>(xs[q]);
+        }
+        store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
+        fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);
+    }
+    followup_finish<EVAL>(ev, df, acc, total > 0, true);
+}
+
+// ---- polynomial_triangulation (triangulation.py:198-232) -------------------------------------------------------
+// Hartley-Sturm correction of the match (cv2.correctMatches) followed by the triangulation of the corrected match, fused.
+// Hot kernel: the certified fast path of the correction, then the certified intersection of the two viewing rays (the
+// corrected match satisfies the epipolar constraint, so the rays meet and the smallest singular vector of the DLT system
+// is their intersection).  Whatever either certificate does not cover -- Durand-Kerner root finding, a correction that is
+// not exact after rounding to float32 storage, ill-conditioned or centre-less cameras -- is deferred to
+// k_polynomial_general, which runs the complete correction and the eigen solver per point; the hot kernel has no
+// subroutine call.  (On the forward-motion rig, where 1 % - 67 % of the points need Durand-Kerner, the slow lanes used to
+// hold their warps for ~100 sweeps: 21 ms per 10 M points before the split.)
+template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
+__global__ void __launch_bounds__(kThreads, EVAL ? TRGL_EVAL_MINB : TRGL_POLY_MINB)
+k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
+             const __grid_constant__ RayGeom<TC> geom, const __grid_constant__ HSParams hs,
              TO* __restrict__ x, uint8_t* __restrict__ status, TI* __restrict__ u1c, TI* __restrict__ u2c,
              unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord,
              const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
-             const __grid_constant__ EvalArg<EVAL> ev) {
+             const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df) {
     double acc[4] = {0, 0, 0, 0};
     __shared__ TO stage[kWarps][96];
     __shared__ __align__(16) PairPrefetch<TI, kThreads> pre;
@@ -733,25 +902,37 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
         if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
         // The correction always runs in double: the degree-6 coefficients span many orders of magnitude.
         double n1x, n1y, n2x, n2y;
-        hs_correct(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c), static_cast<double>(d),
-                   n1x, n1y, n2x, n2y);
+        bool certified = hs_correct<false>(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c),
+                                           static_cast<double>(d), n1x, n1y, n2x, n2y);
         // cv2.correctMatches returns the dtype of its input, so the corrected points are rounded to TI
         // before the triangulation (triangulation.py:224,232).
         const TI r1x = static_cast<TI>(n1x), r1y = static_cast<TI>(n1y), r2x = static_cast<TI>(n2x), r2y = static_cast<TI>(n2y);
-        if (i < n) {
+        TC xs[3] = {0, 0, 0};
+        bool good = false;
+        if (certified) {
+            const bool nan_match = (n1x != n1x) || (n1y != n1y) || (n2x != n2x) || (n2y != n2y);
+            if (nan_match) {
+                // t = inf won / non-finite system: cv2.triangulatePoints of a NaN match is a NaN point, status False
+                xs[0] = xs[1] = xs[2] = static_cast<TC>(n1x + n1y + n2x + n2y);
+            } else {
+                const TC res_tol = sizeof(TI) == 8 ? TC(1e-11) : TC(1e-7);
+                certified = geom.ok && tworay_intersection<TC>(cams, geom, static_cast<TC>(r1x), static_cast<TC>(r1y),
+                                                               static_cast<TC>(r2x), static_cast<TC>(r2y), res_tol, xs);
+                good = tmax(tmax(tabs(xs[0]), tabs(xs[1])), tabs(xs[2])) <= max_coord;     // triangulation.py:23
+            }
+        }
+        if (!certified && i < n) defer_point(df, i);
+        store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
+                         static_cast<TO>(xs[2]), stage[warp], mir);
+        if (i < n && certified) {
             if (u1c) store_uv(u1c, i, r1x, r1y);
             if (u2c) store_uv(u2c, i, r2x, r2y);
             any1 = any1 || !(n1x != n1x) || !(n1y != n1y);
             any2 = any2 || !(n2x != n2x) || !(n2y != n2y);
+            store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
+            // the harness / SLAM evaluate against the ORIGINAL observations, not the corrected ones
+            fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);
         }
-        TC xs[3]; bool good;
-        eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
-                              static_cast<TC>(r2y), max_coord, xs, good);
-        store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
-                         static_cast<TO>(xs[2]), stage[warp], mir);
-        if (i < n) store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
-        // the harness / SLAM evaluate against the ORIGINAL observations, not the corrected ones
-        fused_eval_point<EVAL, TO, TC>(ev, i < n, i, a, b, c, d, xs, good ? 1 : 0, acc);
     }
     // one flag update per CTA (two words shared by the whole grid: per-warp atomics would all hit the same L2 line)
     const int f1 = __syncthreads_or(any1), f2 = __syncthreads_or(any2);
@@ -760,6 +941,54 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
         if (f2) atomicOr(&not_nan_count[1], 1u);
     }
     fused_eval_finish<EVAL>(ev, acc);
+}
+
+// Follow-up kernel of k_polynomial: the complete correction (Durand-Kerner root finding as cv::solvePoly runs it) and the
+// eigen solver (Rayleigh-quotient iteration, Jacobi SVD) for the deferred points, or for every point if the list
+// overflowed / the two-ray forms are switched off (all != 0: k_polynomial is then not launched).
+template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
+__global__ void __launch_bounds__(kThreads)
+k_polynomial_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
+                     const __grid_constant__ HSParams hs, TO* __restrict__ x, uint8_t* __restrict__ status,
+                     TI* __restrict__ u1c, TI* __restrict__ u2c, unsigned int* __restrict__ not_nan_count, const int64_t n,
+                     const TC max_coord, const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
+                     const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df, const int all) {
+    const unsigned int listed = all ? 0u : df.ctl[0];
+    const bool everything = all || listed > df.cap;
+    const int64_t total = everything ? n : static_cast<int64_t>(listed);
+    double acc[4] = {0, 0, 0, 0};
+    bool any1 = false, any2 = false;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; k < total;
+         k += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const int64_t i = everything ? k : df.idx[k];
+        TC a, b, c, d;
+        reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, i, a, b, c, d);
+        double n1x, n1y, n2x, n2y;
+        hs_correct<true>(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c), static_cast<double>(d),
+                         n1x, n1y, n2x, n2y);
+        const TI r1x = static_cast<TI>(n1x), r1y = static_cast<TI>(n1y), r2x = static_cast<TI>(n2x), r2y = static_cast<TI>(n2y);
+        if (u1c) store_uv(u1c, i, r1x, r1y);
+        if (u2c) store_uv(u2c, i, r2x, r2y);
+        any1 = any1 || !(n1x != n1x) || !(n1y != n1y);
+        any2 = any2 || !(n2x != n2x) || !(n2y != n2y);
+        TC xs[3]; bool good;
+        eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
+                              static_cast<TC>(r2y), max_coord, xs, good);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
+        for (int m = 0; m < mir.count; ++m) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) static_cast<TO*>(mir.x[m])[3 * i + q] = static_cast<TO>(xs[q]);
+        }
+        store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
+        fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);
+    }
+    const int f1 = __syncthreads_or(any1), f2 = __syncthreads_or(any2);
+    if (threadIdx.x == 0) {
+        if (f1) atomicOr(&not_nan_count[0], 1u);
+        if (f2) atomicOr(&not_nan_count[1], 1u);
+    }
+    followup_finish<EVAL>(ev, df, acc, total > 0, !all);
 }
 
 // ---- cv2.undistortPoints as a standalone kernel (slam2.py:551-552; output dtype = input dtype) ---------------------

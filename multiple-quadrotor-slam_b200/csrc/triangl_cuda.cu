@@ -3,8 +3,10 @@
 // H2D -> kernel -> D2H pipeline used when the caller hands in host buffers.  No CPU compute path exists.
 #include "../../include/triangl_cuda.h"
 #include "trgl_kernels.cuh"
+#include "trgl_multiview.cuh"
 #include "trgl_reproj.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -116,6 +118,21 @@ RayGeom<T> make_ray_geom(const double* P1, const double* P2) {
 
 inline unsigned grid_for(int64_t n, int per_block) { return static_cast<unsigned>((n + per_block - 1) / per_block); }
 
+// Reduction scratch (per-block partial sums, the polynomial NaN flags, the last-block ticket) is owned per
+// (device, stream): calls enqueued on one stream reuse it in stream order, calls on different streams never share it,
+// so the entry points are re-entrant per stream like the reference's stack-local C code (triangulation.c:67,106).
+struct Scratch {
+    double* partials = nullptr;       // kPartialDoubles
+    unsigned int* flags = nullptr;    // 2 words per pipeline slot + 2 for device-mode calls (polynomial all-NaN test)
+    unsigned int* counter = nullptr;  // ticket of the in-kernel final reduction (self-resetting)
+    int64_t* deferred = nullptr;      // deferred_cap indices: points a hot kernel hands to its follow-up kernel
+    unsigned int deferred_cap = 0;    // grows with the batch size: one slot per point up to kDeferredMax
+    unsigned int* deferred_ctl = nullptr;   // {count, ticket}, re-armed by the follow-up kernel
+};
+constexpr unsigned int kDeferredMin = 1u << 20, kDeferredMax = 1u << 26;
+std::atomic<unsigned int> g_deferred_limit{kDeferredMax};     // trgl_set_deferred_capacity (test knob)
+int scratch_for(cudaStream_t s, Scratch& out, int64_t deferred_points = 0);
+
 // ------------------------------------------------------------------------------------------------------------
 // Device-pointer launchers, one per solver.  MODE_SWITCH instantiates the five precision modes.
 // ------------------------------------------------------------------------------------------------------------
@@ -132,7 +149,7 @@ inline unsigned grid_for(int64_t n, int per_block) { return static_cast<unsigned
 // Launch geometry of the bulk-async variants: persistent grid of SMs x (CTAs that fit in shared memory).
 std::atomic<int> g_variant{-1};         // -1 = auto, 0 = per-thread loads, >= 1 = bulk-async pipeline (trgl_set_stream_variant)
 int g_sm_count = 0;
-std::atomic<int> g_iter_general{0};     // 1 = iterative_LS runs the reference's loop for every point (trgl_set_iterative_path)
+std::atomic<int> g_two_ray{1};          // 0 = no two-ray closed forms in iterative_LS / polynomial (trgl_set_two_ray)
 
 template <typename TI, typename TC, typename TO, int PPT, int STAGES, int MINB>
 int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_t* status, int64_t n, cudaStream_t s,
@@ -285,27 +302,47 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
                         const Mirrors& mir = kNoMirrors, const FusedEval* ev = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
-    int rc = TRGL_OK;
+    Scratch sc;
+    int rc = scratch_for(s, sc, n);
+    if (rc) return rc;
+    const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+    const int py = semantics == TRGL_ITER_PY ? 1 : 0;
+    int nlaunch = 0;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
-        RayGeom<TC> geom = make_ray_geom<TC>(P1, P2);
-        if (g_iter_general) geom.ok = 0;
+        const RayGeom<TC> geom = make_ray_geom<TC>(P1, P2);
+        const bool closed_form = geom.ok && g_two_ray.load();
         constexpr size_t smem = sizeof(IterSmem<TI, TC, TO>);
+        const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
         with_pre(pre, [&](auto prearg) {
             using PRE = decltype(prearg);
             with_eval(ev, [&](auto E, auto evarg) {
                 constexpr bool EV = decltype(E)::value;
                 if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
-                    auto kern = k_iterative_ls<TI, TC, TO, PRE, EV>;
-                    kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
-                        static_cast<const TI*>(u1), static_cast<const TI*>(u2), cams, geom, static_cast<TO*>(x), status, n,
-                        static_cast<TC>(tol), semantics == TRGL_ITER_PY ? 1 : 0, prearg, mir, evarg);
+                    auto general = k_iterative_general<TI, TC, TO, PRE, EV>;
+                    if (closed_form) {
+                        // hot kernel (two-ray closed form) + follow-up over the points it deferred (usually none)
+                        auto kern = k_iterative_ls<TI, TC, TO, PRE, EV>;
+                        kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
+                            a, b, cams, geom, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df);
+                        const int64_t tiles = (n + kThreads - 1) / kThreads;
+                        const int64_t cap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+                        general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
+                            a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df, 0);
+                        nlaunch = 2;
+                    } else {
+                        // no finite camera centre / closed forms switched off: the reference's loop for every point
+                        if constexpr (EV) cudaMemsetAsync(evarg.e.sums_out, 0, 4 * sizeof(double), s);
+                        general<<<persistent_grid(general, n), kThreads, 0, s>>>(
+                            a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df, 1);
+                        nlaunch = 1;
+                    }
                 }
             });
         });
     })
     if (rc) return rc;
-    g_launches++;
+    g_launches += nlaunch;
     CK(cudaGetLastError());
     return TRGL_OK;
 }
@@ -315,28 +352,33 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
                         const Mirrors& mir = kNoMirrors, const FusedEval* ev = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
-    int rc = TRGL_OK;
+    Scratch sc;
+    int rc = scratch_for(s, sc, n);
+    if (rc) return rc;
+    const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
+        const int64_t tiles = (n + kThreads - 1) / kThreads;
         with_pre(pre, [&](auto prearg) {
             using PRE = decltype(prearg);
             with_eval(ev, [&](auto E, auto evarg) {
                 constexpr bool EV = decltype(E)::value;
                 if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
-                    if (rows == 4) {
-                        auto kern = k_linear_eigen<TI, TC, TO, 4, PRE, EV>;
-                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg);
-                    } else {
-                        auto kern = k_linear_eigen<TI, TC, TO, 6, PRE, EV>;
-                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg);
-                    }
+                    // hot kernel (Rayleigh-quotient iteration, certified) + follow-up over the points it deferred (Jacobi SVD)
+                    auto launch = [&](auto kern, auto general) {
+                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
+                        const int64_t cap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+                        general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
+                    };
+                    if (rows == 4) launch(k_linear_eigen<TI, TC, TO, 4, PRE, EV>, k_linear_eigen_general<TI, TC, TO, 4, PRE, EV>);
+                    else launch(k_linear_eigen<TI, TC, TO, 6, PRE, EV>, k_linear_eigen_general<TI, TC, TO, 6, PRE, EV>);
                 }
             });
         });
     })
     if (rc) return rc;
-    g_launches++;
+    g_launches += 2;
     CK(cudaGetLastError());
     return TRGL_OK;
 }
@@ -347,28 +389,44 @@ int launch_polynomial(const void* u1, const void* u2, const double* P1, const do
                       const FusedEval* ev = nullptr) {
     if (n == 0) return TRGL_OK;
     if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers (see header)
-    int rc = TRGL_OK;
+    Scratch sc;
+    int rc = scratch_for(s, sc, n);
+    if (rc) return rc;
+    const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+    int nlaunch = 0;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
+        const RayGeom<TC> geom = make_ray_geom<TC>(P1, P2);
+        const bool closed_form = geom.ok && g_two_ray.load();
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
+        const int64_t tiles = (n + kThreads - 1) / kThreads;
         with_pre(pre, [&](auto prearg) {
             using PRE = decltype(prearg);
             with_eval(ev, [&](auto E, auto evarg) {
                 constexpr bool EV = decltype(E)::value;
                 if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
-                    if (rows == 4) {
-                        auto kern = k_polynomial<TI, TC, TO, 4, PRE, EV>;
-                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg);
-                    } else {
-                        auto kern = k_polynomial<TI, TC, TO, 6, PRE, EV>;
-                        kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg);
-                    }
+                    auto launch = [&](auto kern, auto general) {
+                        if (closed_form) {
+                            // hot kernel (certified correction + ray intersection) + follow-up over the points it deferred
+                            kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, geom, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
+                            const int64_t cap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+                            general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 0);
+                            nlaunch = 2;
+                        } else {
+                            // no finite camera centre / closed forms switched off: the complete per-point path for every point
+                            if constexpr (EV) cudaMemsetAsync(evarg.e.sums_out, 0, 4 * sizeof(double), s);
+                            general<<<persistent_grid(general, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 1);
+                            nlaunch = 1;
+                        }
+                    };
+                    if (rows == 4) launch(k_polynomial<TI, TC, TO, 4, PRE, EV>, k_polynomial_general<TI, TC, TO, 4, PRE, EV>);
+                    else launch(k_polynomial<TI, TC, TO, 6, PRE, EV>, k_polynomial_general<TI, TC, TO, 6, PRE, EV>);
                 }
             });
         });
     })
     if (rc) return rc;
-    g_launches++;
+    g_launches += nlaunch;
     CK(cudaGetLastError());
     return TRGL_OK;
 }
@@ -392,20 +450,12 @@ std::mutex g_pipe_mutex;
 Slot g_slots[kSlots];
 std::mutex g_host_mutex;              // host-mode calls that keep state across host_pipeline (polynomial flags)
 
-// Reduction scratch (per-block partial sums, the polynomial NaN flags, the last-block ticket) is owned per
-// (device, stream): calls enqueued on one stream reuse it in stream order, calls on different streams never share it,
-// so the entry points are re-entrant per stream like the reference's stack-local C code (triangulation.c:67,106).
-struct Scratch {
-    double* partials = nullptr;       // kPartialDoubles
-    unsigned int* flags = nullptr;    // 2 words per pipeline slot + 2 for device-mode calls (polynomial all-NaN test)
-    unsigned int* counter = nullptr;  // ticket of the in-kernel final reduction (self-resetting)
-};
 constexpr size_t kPartialDoubles = static_cast<size_t>(kReduceBlocks) * 48;
 constexpr int kFlagWords = 2 * (kSlots + 1);
 std::mutex g_scratch_mutex;
 std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
 
-int scratch_for(cudaStream_t s, Scratch& out) {
+int scratch_for(cudaStream_t s, Scratch& out, int64_t deferred_points) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_scratch_mutex);
@@ -415,12 +465,26 @@ int scratch_for(cudaStream_t s, Scratch& out) {
             cudaGetLastError();
             return fail(TRGL_E_NOMEM, "cudaMalloc of reduction scratch failed");
         }
-        if (cudaMalloc(&sc.flags, sizeof(unsigned int) * (kFlagWords + 2)) != cudaSuccess) {
+        if (cudaMalloc(&sc.flags, sizeof(unsigned int) * (kFlagWords + 4)) != cudaSuccess) {
             cudaGetLastError(); cudaFree(sc.partials); sc.partials = nullptr;
             return fail(TRGL_E_NOMEM, "cudaMalloc of reduction scratch failed");
         }
-        CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * (kFlagWords + 2)));
+        CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * (kFlagWords + 4)));
         sc.counter = sc.flags + kFlagWords;
+        sc.deferred_ctl = sc.flags + kFlagWords + 2;
+    }
+    if (deferred_points > 0) {
+        // one slot per point of the batch (a rig can defer most of its points, e.g. forward motion under heavy noise)
+        int64_t want = deferred_points < kDeferredMin ? kDeferredMin : deferred_points;
+        if (want > kDeferredMax) want = kDeferredMax;
+        if (sc.deferred_cap < want) {
+            if (sc.deferred) { CK(cudaStreamSynchronize(s)); cudaFree(sc.deferred); sc.deferred = nullptr; sc.deferred_cap = 0; }
+            if (cudaMalloc(&sc.deferred, sizeof(int64_t) * want) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(TRGL_E_NOMEM, "cudaMalloc of the deferred-point list failed");
+            }
+            sc.deferred_cap = static_cast<unsigned int>(want);
+        }
     }
     out = sc;
     return TRGL_OK;
@@ -470,6 +534,7 @@ int ensure_slot(Slot& sl, size_t bytes) {
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 struct HostArray { const void* in; void* out; size_t bytes_per_point; };
+constexpr int kMaxHostArrays = 2 * kMaxViews + 2;     // multi-view: m observation arrays + m masks + x + status
 
 // Small batches (the SLAM keyframe sizes, slam2.py:1080-1082: a few hundred points): latency is all API calls, so the
 // kernel works straight on page-locked, device-mapped host memory (UVA: the cudaHostAlloc pointer is valid on the
@@ -502,7 +567,7 @@ int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
         if (rc) return rc;
         rc = ensure_slot(g_slots[0], 0);
         if (rc) return rc;
-        void* dptr[8];
+        void* dptr[kMaxHostArrays];
         size_t pos = 0;
         for (int a = 0; a < narrays; ++a) {
             dptr[a] = g_zc_buf + pos;
@@ -525,7 +590,7 @@ int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
     for (int64_t off = 0; off < n; off += chunk, ++idx) {
         Slot& sl = g_slots[idx % nslots];
         const int64_t m = (n - off) < chunk ? (n - off) : chunk;
-        void* dptr[8];
+        void* dptr[kMaxHostArrays];
         size_t pos = 0;
         for (int a = 0; a < narrays; ++a) {
             dptr[a] = sl.buf + pos;
@@ -791,9 +856,14 @@ int trgl_set_stream_variant(int variant) {
     if (variant >= -1 && variant <= 12) g_variant.store(variant);
     return old;
 }
-int trgl_set_iterative_path(int general_only) {
-    const int old = g_iter_general.load();
-    g_iter_general.store(general_only ? 1 : 0);
+int64_t trgl_set_deferred_capacity(int64_t max_points) {
+    const int64_t old = g_deferred_limit.load();
+    if (max_points >= 1 && max_points <= static_cast<int64_t>(kDeferredMax)) g_deferred_limit.store(static_cast<unsigned int>(max_points));
+    return old;
+}
+int trgl_set_two_ray(int enabled) {
+    const int old = g_two_ray.load();
+    g_two_ray.store(enabled ? 1 : 0);
     return old;
 }
 int trgl_set_points_per_thread(int ppt) {
@@ -832,6 +902,84 @@ int trgl_linear_ls_px(const void* px1, const void* px2, const double* K1, const 
     Undist2 pre;
     if (!make_undist2(K1, dist1, K2, dist2, pre)) return fail(TRGL_E_BADARG, "camera matrix K is NULL or has a zero focal length");
     return impl_linear_ls(px1, px2, P1, P2, x, status, n, mode, mem, stream, &pre);
+}
+
+// ---- multi-view linear LS -----------------------------------------------------------------------
+static int launch_multiview_ls(void* const* u, void* const* valid, const double* P, int m, int min_views, void* x,
+                               uint8_t* status, int64_t n, int mode, cudaStream_t s) {
+    if (n == 0) return TRGL_OK;
+    if (mode == TRGL_F32) mode = TRGL_F32IO;     // float32 storage, float64 registers
+    Scratch sc;
+    int rc = scratch_for(s, sc, n);
+    if (rc) return rc;
+    const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+    MODE_SWITCH(mode, {
+        if constexpr (sizeof(TC) == 8) {
+            MultiViewArgs<TI, TC> args;
+            std::memset(&args, 0, sizeof(args));
+            for (int v = 0; v < m; ++v) {
+                args.u[v] = static_cast<const TI*>(u[v]);
+                args.valid[v] = valid ? static_cast<const uint8_t*>(valid[v]) : nullptr;
+                for (int k = 0; k < 12; ++k) args.P[v][k] = P[12 * v + k];
+            }
+            args.m = m; args.min_views = min_views;
+            if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); }
+            const int64_t cap = static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148) * 16;
+            if (m <= 4) {
+                const int64_t tiles = (n + 2 * kThreads - 1) / (2 * kThreads);
+                k_multiview_ls<TI, TC, TO, 2, 4><<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
+                    args, static_cast<TO*>(x), status, n, df);
+            } else {
+                const int64_t tiles = (n + kThreads - 1) / kThreads;
+                k_multiview_ls<TI, TC, TO, 1, 8><<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
+                    args, static_cast<TO*>(x), status, n, df);
+            }
+            const int64_t ftiles = (n + kThreads - 1) / kThreads;
+            const int64_t fcap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+            k_multiview_general<TI, TC, TO><<<static_cast<unsigned>(ftiles < fcap ? ftiles : fcap), kThreads, 0, s>>>(
+                args, static_cast<TO*>(x), n, df);
+        } else {
+            rc = fail(TRGL_E_BADARG, "multi-view triangulation computes in float64");
+        }
+    })
+    if (rc) return rc;
+    g_launches += 2;
+    CK(cudaGetLastError());
+    return TRGL_OK;
+}
+
+int trgl_multiview_ls(const void* u, const uint8_t* valid, const double* P, int m, void* x, uint8_t* status, int64_t n,
+                      int min_views, int mode, int mem, void* stream) {
+    ModeInfo mi;
+    if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
+    if (!mode_info(mode, mi)) return fail(TRGL_E_BADARG, "unknown precision mode");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (m < 1 || m > kMaxViews) return fail(TRGL_E_BADARG, "number of views must be 1..16");
+    if (!P) return fail(TRGL_E_BADARG, "camera matrix pointer is NULL");
+    if (n > 0 && (!u || !x || !status)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
+    if (mem == TRGL_MEM_DEVICE && n > 0 && (reinterpret_cast<uintptr_t>(u) & static_cast<uintptr_t>(2 * mi.in_bytes - 1)))
+        return fail(TRGL_E_BADARG, "device u must be aligned to one (x,y) pair (16 bytes float64, 8 bytes float32)");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    if (n == 0) return TRGL_OK;
+    const size_t view_bytes = static_cast<size_t>(n) * 2 * mi.in_bytes;
+    if (mem == TRGL_MEM_DEVICE) {
+        void* up[kMaxViews]; void* vp[kMaxViews];
+        for (int v = 0; v < m; ++v) {
+            up[v] = const_cast<char*>(static_cast<const char*>(u)) + v * view_bytes;
+            vp[v] = valid ? const_cast<uint8_t*>(valid) + static_cast<size_t>(v) * n : nullptr;
+        }
+        return launch_multiview_ls(up, valid ? vp : nullptr, P, m, min_views, x, status, n, mode, static_cast<cudaStream_t>(stream));
+    }
+    HostArray arr[kMaxHostArrays];
+    int na = 0;
+    for (int v = 0; v < m; ++v) arr[na++] = {static_cast<const char*>(u) + v * view_bytes, nullptr, size_t(2 * mi.in_bytes)};
+    if (valid) for (int v = 0; v < m; ++v) arr[na++] = {valid + static_cast<size_t>(v) * n, nullptr, 1};
+    const int ix = na;
+    arr[na++] = {nullptr, x, size_t(3 * mi.out_bytes)};
+    arr[na++] = {nullptr, status, 1};
+    return host_pipeline(arr, na, n, [&](void** d, int64_t cnt, cudaStream_t s, int) {
+        return launch_multiview_ls(d, valid ? d + m : nullptr, P, m, min_views, d[ix], static_cast<uint8_t*>(d[ix + 1]), cnt, mode, s);
+    });
 }
 
 static int impl_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,

@@ -182,3 +182,25 @@ def circle_cameras(num_cams=8, offset=40., max_angle=asin(1.0) * 0.5):
         cam.camera_pose(offset, offset * sin(a), offset * (1 - cos(a)), a)
         Ps.append(cam.P.copy())
     return Ps
+
+
+def make_multiview(n, num_cams=8, sigma=0.8, seed=RSEED, r=4., dtype=np.float64, p_visible=1.0):
+    """
+    Multi-quadrotor scene for the m-view solver: the cloud seen by `num_cams` cameras on the trajectory-4/5 circle.
+    Returns us (m,n,2) normalised observations (pixel noise sigma / f), Ps (list of m 3x4), X (n,3), valid (m,n) bool
+    (each view observes a point with probability p_visible; all True for p_visible >= 1).
+    RNG order: cloud, then per camera its noise, then the visibility draws.
+    """
+    rng = np.random.RandomState(seed)
+    X = ball_3D_points(n, r, rng)
+    Ps = circle_cameras(num_cams)
+    us = np.empty((num_cams, n, 2), dtype=dtype)
+    for v, P in enumerate(Ps):
+        cam = Camera()
+        cam.P = P
+        cam.camera_intrinsics((640, 480))
+        cam.project_points(X)
+        cam.apply_noise(sigma, False, rng)
+        us[v] = cam.normalized_points().astype(dtype)
+    valid = np.ones((num_cams, n), dtype=bool) if p_visible >= 1.0 else rng.uniform(size=(num_cams, n)) < p_visible
+    return us, Ps, np.ascontiguousarray(X[:, 0:3]), valid

@@ -31,7 +31,7 @@ EXPORTS = [
     "trgl_event_create", "trgl_event_destroy", "trgl_event_record", "trgl_event_elapsed_ms",
     "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
-    "trgl_set_points_per_thread", "trgl_set_stream_variant", "trgl_set_iterative_path",
+    "trgl_set_points_per_thread", "trgl_set_stream_variant", "trgl_set_two_ray", "trgl_multiview_ls", "trgl_set_deferred_capacity",
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
     "trgl_set_fused_eval", "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
@@ -76,6 +76,9 @@ def lib():
     L.trgl_event_elapsed_ms.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_float)]
     L.trgl_linear_ls.argtypes = [vp, vp, dp, dp, vp, vp, i64, cint, cint, vp]
     L.trgl_iterative_ls.argtypes = [vp, vp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
+    L.trgl_set_deferred_capacity.argtypes = [i64]
+    L.trgl_set_deferred_capacity.restype = i64
+    L.trgl_multiview_ls.argtypes = [vp, vp, dp, cint, vp, vp, i64, cint, cint, cint, vp]
     L.trgl_linear_eigen.argtypes = [vp, vp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
     L.trgl_polynomial.argtypes = [vp, vp, dp, dp, vp, vp, vp, vp, ctypes.POINTER(cint), i64, dbl, cint, cint, cint, vp]
     L.trgl_polynomial_F.argtypes = [vp, vp, dp, dp, dp, vp, vp, vp, vp, ctypes.POINTER(cint), i64, dbl, cint, cint,
@@ -384,6 +387,35 @@ def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=
     return x, status
 
 
+def multiview_ls(us, Ps, valid=None, min_views=2, out_dtype=np.float64, x=None, status=None, stream=None):
+    """us (m,n,2) host array or DeviceArray, Ps (m,3|4,4), valid (m,n) bool / uint8 or None -> x (n,3), status (n,) bool."""
+    dev = _is_device(us)
+    if not dev:
+        us = np.asarray(us)
+        if us.dtype != np.float32:
+            us = us.astype(np.float64, copy=False)
+        us = np.ascontiguousarray(us)
+    if len(us.shape) != 3 or us.shape[2] != 2:
+        raise ValueError("us must have shape (m, n, 2)")
+    m, n = int(us.shape[0]), int(us.shape[1])
+    in_dtype = np.dtype(str(us.dtype).replace("torch.", ""))
+    Pm = np.ascontiguousarray(np.stack([_P12(P) for P in Ps]).reshape(-1))
+    if len(Pm) != 12 * m:
+        raise ValueError("need one camera matrix per view")
+    if valid is not None:
+        if dev != _is_device(valid):
+            raise ValueError("us and valid must both be host arrays or both be device buffers")
+        if not dev:
+            valid = np.ascontiguousarray(np.asarray(valid).astype(np.uint8, copy=False))
+        if tuple(valid.shape) != (m, n):
+            raise ValueError("valid must have shape (m, n)")
+    x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
+    check(lib().trgl_multiview_ls(_ptr(us), _ptr(valid) if valid is not None else None, _dp(Pm), m, _ptr(x), _ptr(status),
+                                  n, int(min_views), mode_for(in_dtype, np.float64, out_dtype),
+                                  MEM_DEVICE if dev else MEM_HOST, stream))
+    return x, status
+
+
 def iterative_ls(u1, P1, u2, P2, tolerance=3.e-5, semantics=ITER_C, out_dtype=np.float64, compute_dtype=np.float64,
                  x=None, status=None, stream=None, pixel=None, evaluate=None):
     u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
@@ -642,9 +674,15 @@ def set_stream_variant(v):
     return lib().trgl_set_stream_variant(int(v))
 
 
-def set_iterative_path(general_only):
-    """0 = two-ray closed form where certified (default), 1 = the reference's loop for every point; returns the old value."""
-    return lib().trgl_set_iterative_path(int(general_only))
+def set_deferred_capacity(max_points):
+    """Test knob: limit of the deferred-point list of the hot kernels (default 2**26); returns the old limit."""
+    return lib().trgl_set_deferred_capacity(int(max_points))
+
+
+def set_two_ray(enabled):
+    """1 = two-ray closed forms where certified (iterative_LS, polynomial; default), 0 = the reference's arithmetic for
+    every point; returns the old value."""
+    return lib().trgl_set_two_ray(int(enabled))
 
 
 def synchronize():

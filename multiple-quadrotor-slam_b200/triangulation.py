@@ -177,6 +177,17 @@ def linear_eigen_triangulation_px(imgp1, P1, imgp2, P2, cameraMatrix, distCoeffs
     return _finish(x, status)
 
 
+def multiview_LS_triangulation(us, Ps, valid=None, min_views=2):
+    """
+    Linear Least Squares triangulation from m >= 2 views (not in the reference, whose calls are all two-view; same
+    conventions): "us" (m, N, 2) normalised observations, "Ps" m camera matrices (3x4 or 4x4), "valid" (m, N) which
+    view observes which point (default: all).  Returns x (N, 3) of the output dtype and a bool status-vector that is True
+    where at least "min_views" views observe the point.  With two views and no mask: linear_LS_triangulation.
+    """
+    x, status = _tc.multiview_ls(us, Ps, valid, min_views, _kernel_out_dtype())
+    return _finish(x, status)
+
+
 def linear_LS_triangulation_px(imgp1, P1, imgp2, P2, cameraMatrix, distCoeffs=None, cameraMatrix2=None,
                                distCoeffs2=None):
     """linear_LS_triangulation on pixel coordinates (undistortion fused in front of the solve)."""

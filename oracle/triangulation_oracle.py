@@ -84,6 +84,28 @@ def linear_LS_triangulation(u1, P1, u2, P2):
     return x.astype(output_dtype), np.ones(len(x), dtype=bool)
 
 
+def multiview_LS_triangulation(us, Ps, valid=None, min_views=2):
+    """
+    m-view generalisation of linear_LS_triangulation (no reference statement -- the definition is
+    the stacked system of triangulation.c:30-40 for every observing view, solved like cvSolve(DECOMP_SVD) at :81).
+    us (m,N,2), Ps m matrices, valid (m,N) or None.  Rows of non-observing views are zero rows: they change neither the
+    singular values nor the minimum-norm solution.
+    """
+    us = np.asarray(us, dtype=np.float64)
+    m, n = us.shape[0], us.shape[1]
+    A = np.zeros((n, 2 * m, 3)); b = np.zeros((n, 2 * m))
+    seen = np.ones((m, n), dtype=bool) if valid is None else np.asarray(valid).astype(bool)
+    for v in range(m):
+        P = np.asarray(Ps[v], dtype=np.float64)
+        r0 = us[v][:, 0:1] * P[2, :] - P[0, :]
+        r1 = us[v][:, 1:2] * P[2, :] - P[1, :]
+        sel = seen[v]
+        A[sel, 2 * v, :] = r0[sel, 0:3];     b[sel, 2 * v] = -r0[sel, 3]
+        A[sel, 2 * v + 1, :] = r1[sel, 0:3]; b[sel, 2 * v + 1] = -r1[sel, 3]
+    x = lstsq_minnorm(A, b)
+    return x.astype(output_dtype), seen.sum(axis=0) >= min_views
+
+
 def iterative_LS_core(u1, P1, u2, P2, tolerance=3.e-5, semantics='c'):
     """
     Returns x (N,3) f64, status (N,) int, n_solves (N,) and the convergence margin

@@ -109,17 +109,17 @@ def test_iterative_ls_vs_oracle(tri, rig_name, sigma, semantics):
 @pytest.mark.parametrize("rig_name", RIG_NAMES)
 @pytest.mark.parametrize("sigma", [0.8, 20.0])
 def test_iterative_ls_closed_form_equals_reference_loop(tri, rig_name, sigma):
-    """The two-ray closed form (default) and the reference's loop as written (trgl_set_iterative_path(1)) are the same
+    """The two-ray closed form (default) and the reference's loop as written (trgl_set_two_ray(0)) are the same
     function: identical status vector away from knife-edge convergence tests, points within 1e-9."""
     import triangl_cuda as tc
     u1, P1, u2, P2, X = rig.make_correspondences(50021, rig_name, sigma)
     x, st = tri.iterative_LS_triangulation(u1, P1, u2, P2)
-    old = tc.set_iterative_path(1)
+    old = tc.set_two_ray(0)
     try:
         xg, stg = tri.iterative_LS_triangulation(u1, P1, u2, P2)
     finally:
-        tc.set_iterative_path(old)
-    assert old == 0
+        tc.set_two_ray(old)
+    assert old == 1
     knife = iterative_margin(u1, P1, u2, P2) < 1e-9
     ok = ls_well_posed(u1, P1, u2, P2) & ~knife
     assert ok.mean() > 0.9
@@ -130,6 +130,52 @@ def test_iterative_ls_closed_form_equals_reference_loop(tri, rig_name, sigma):
     s = np.linalg.svd(A, compute_uv=False)
     same = st == stg
     assert np.all(rel_err(x, xg)[same & ~knife] < np.maximum(TOL64, (s[:, 0] / s[:, 2])[same & ~knife] ** 2 * 1e-13))
+
+
+def test_deferred_list_overflow_redoes_every_point(tri):
+    """More uncertified points than the deferred list holds: the follow-up kernels fall back to redoing every point.
+    The list is limited to 1000 slots; identical cameras make every system rank 2, i.e. every point uncertified, and the
+    forward-motion rig under 20 px noise defers most of its points in polynomial (Durand-Kerner) and some in linear_eigen."""
+    import triangl_cuda as tc
+    old = tc.set_deferred_capacity(1000)
+    try:
+        n = 40013
+        u1, P1, u2, P2, X = rig.make_correspondences(n, "translating", 0.5)
+        xi, sti = tri.iterative_LS_triangulation(u1, P1, u1, P1)
+        xo, so, _, margin = orc.iterative_LS_core(u1, P1, u1, P1)
+        keep = margin > 1e-9
+        assert np.isfinite(xi).all()
+        assert np.array_equal(sti[keep], so[keep]) and rel_err(xi, xo)[keep].max() < 1e-8
+        xe, ste = tri.linear_eigen_triangulation(u1, P1, u1, P1)          # two-dimensional null space: well-formedness only
+        assert xe.shape == (n, 3) and ste.shape == (n,)
+        us = np.stack([u1, u1, u1])
+        xm, stm = tri.multiview_LS_triangulation(us, [P1, P1, P1])
+        xmo, _ = orc.multiview_LS_triangulation(us, [P1, P1, P1])
+        assert stm.all() and rel_err(xm, xmo).max() < 1e-8
+        u1, P1, u2, P2, X = rig.make_correspondences(n, "forward", 20.0)
+        for name in ("polynomial", "linear_eigen"):
+            x, st = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)
+            tc.set_deferred_capacity(old)
+            x_full, st_full = getattr(tri, name + "_triangulation")(u1, P1, u2, P2)      # same points through the list
+            tc.set_deferred_capacity(1000)
+            xo, so = orc.SOLVERS[name](u1, P1, u2, P2)
+            if name == "polynomial":
+                n1, n2 = orc.correct_matches(orc.fundamental_from_P(P1, P2), u1, u2)
+                ok = eigen_well_posed(n1, P1, n2, P2)
+            else:
+                ok = eigen_well_posed(u1, P1, u2, P2)
+            ok &= np.isfinite(xo).all(axis=1)
+            assert ok.mean() > 0.5, name
+            assert np.array_equal(st[ok], so[ok]) and np.array_equal(st_full[ok], so[ok]), name
+            assert rel_err(x, xo)[ok].max() < TOL64 and rel_err(x_full, xo)[ok].max() < TOL64, name
+    finally:
+        tc.set_deferred_capacity(old)
+    # the list is re-armed: a normal call right after it is unaffected
+    u1, P1, u2, P2, X = rig.make_correspondences(30011, "rotating", 0.8)
+    x, st = tri.iterative_LS_triangulation(u1, P1, u2, P2)
+    xo, so, _, margin = orc.iterative_LS_core(u1, P1, u2, P2)
+    keep = margin > 1e-9
+    assert np.array_equal(st[keep], so[keep]) and rel_err(x, xo)[keep].max() < TOL64
 
 
 def test_iterative_ls_uncertified_points_take_the_reference_loop(tri):
@@ -190,6 +236,26 @@ def test_polynomial_vs_oracle(tri, rig_name, sigma):
     assert ok.mean() > (0.5 if rig_name == "forward" else 0.99)
     assert np.array_equal(st[ok], so[ok])
     assert rel_err(x, xo)[ok].max() < TOL64
+
+
+@pytest.mark.parametrize("rig_name", RIG_NAMES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_polynomial_ray_intersection_equals_eigen_solver(tri, rig_name, dtype):
+    """After the Hartley-Sturm correction the two viewing rays meet: the certified closed-form intersection (default)
+    and cv2.triangulatePoints' smallest singular vector (trgl_set_two_ray(0)) are the same point, same mask."""
+    import triangl_cuda as tc
+    u1, P1, u2, P2, X = rig.make_correspondences(50021, rig_name, 4.0, dtype=dtype)
+    x, st = tri.polynomial_triangulation(u1, P1, u2, P2)
+    old = tc.set_two_ray(0)
+    try:
+        xg, stg = tri.polynomial_triangulation(u1, P1, u2, P2)
+    finally:
+        tc.set_two_ray(old)
+    assert np.array_equal(st, stg)
+    n1, n2 = orc.correct_matches(orc.fundamental_from_P(P1, P2), np.asarray(u1, np.float64), np.asarray(u2, np.float64))
+    ok = eigen_well_posed(n1, P1, n2, P2) & st
+    assert ok.mean() > 0.9
+    assert rel_err(x, xg)[ok].max() < (TOL64 if dtype == np.float64 else TOL32)
 
 
 @pytest.mark.parametrize("rig_name", RIG_NAMES)
@@ -779,3 +845,81 @@ def test_per_call_requests_do_not_outlive_a_failed_call(tri):
     tc.synchronize()
     assert np.isnan(gx.to_host()).all() and np.isnan(fe.sums.to_host()).all()
     assert np.isfinite(x.to_host()).all()
+
+
+# ---- multi-view linear LS -----------------------------------------------------------------------
+def multiview_well_posed(us, Ps, valid, tol=1e-9):
+    m, n = us.shape[0], us.shape[1]
+    A = np.zeros((n, 2 * m, 3))
+    for v in range(m):
+        P = np.asarray(Ps[v])
+        A[:, 2 * v] = (us[v][:, 0:1] * P[2] - P[0])[:, 0:3] * valid[v][:, None]
+        A[:, 2 * v + 1] = (us[v][:, 1:2] * P[2] - P[1])[:, 0:3] * valid[v][:, None]
+    s = np.linalg.svd(A, compute_uv=False)
+    with np.errstate(all='ignore'):
+        return (s[:, 0] / s[:, 2]) * 2.2e-16 * 50 < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("num_cams", [2, 3, 8, 16])
+@pytest.mark.parametrize("p_visible", [1.0, 0.6])
+def test_multiview_ls_vs_oracle(tri, num_cams, p_visible):
+    us, Ps, X, valid = rig.make_multiview(20011, num_cams, 0.8, p_visible=p_visible)
+    mask = None if p_visible >= 1.0 else valid
+    x, st = tri.multiview_LS_triangulation(us, Ps, mask)
+    xo, so = orc.multiview_LS_triangulation(us, Ps, mask)
+    assert x.shape == (20011, 3) and x.dtype == np.float64 and st.dtype == np.bool_
+    assert np.array_equal(st, so)
+    ok = multiview_well_posed(us, Ps, valid) & so
+    assert ok.mean() > 0.95 * so.mean() > 0.3
+    assert rel_err(x, xo)[ok].max() < TOL64
+    # points seen by 0 or 1 view: minimum-norm solutions of rank <= 2 systems, like the oracle
+    few = valid.sum(axis=0) < 2
+    if few.any():
+        assert np.isfinite(x[few]).all()
+        assert np.abs(x[few] - xo[few]).max() < 1e-8 * max(1.0, np.abs(xo[few]).max())
+    if num_cams >= 8 and p_visible >= 1.0:           # more views -> closer to the ground truth than any pair
+        x2, _ = tri.linear_LS_triangulation(us[0], Ps[0], us[-1], Ps[-1])
+        assert np.linalg.norm(x - X, axis=1).mean() < np.linalg.norm(x2 - X, axis=1).mean()
+
+
+@pytest.mark.gpu
+def test_multiview_two_views_is_linear_ls(tri):
+    import triangl_cuda as tc
+    for dtype in (np.float64, np.float32):
+        u1, P1, u2, P2, X = rig.make_correspondences(30011, "rotating", 0.8, dtype=dtype)
+        x2, s2 = tri.linear_LS_triangulation(u1, P1, u2, P2)
+        xm, sm = tri.multiview_LS_triangulation(np.stack([u1, u2]), [P1, P2])
+        assert np.array_equal(sm, s2)
+        assert rel_err(xm, x2).max() < (1e-12 if dtype == np.float64 else 1e-6)
+    # device-resident call, float32 output, 4x4 matrices, ragged size
+    us, Ps, X, valid = rig.make_multiview(1000 + 37, 5, 0.8, p_visible=0.8)
+    P4 = [np.vstack([P, [0, 0, 0, 1]]) for P in Ps]
+    xd, sd = tc.multiview_ls(tc.to_device(us), P4, tc.to_device(valid.astype(np.uint8)), out_dtype=np.float32)
+    xh, sh = tc.multiview_ls(us, Ps, valid, out_dtype=np.float32)
+    assert np.array_equal(xd.to_host(), xh) and np.array_equal(sd.to_host().astype(bool), sh.astype(bool))
+    for n in (0, 1, 33):
+        x, st = tri.multiview_LS_triangulation(us[:, :n], Ps, valid[:, :n])
+        assert x.shape == (n, 3) and st.shape == (n,)
+
+
+@pytest.mark.gpu
+def test_multiview_degenerate_and_nan(tri):
+    us, Ps, X, valid = rig.make_multiview(600, 4, 0.5)
+    # all four "cameras" identical: every system has rank 2 -> minimum-norm solution, as cvSolve(DECOMP_SVD)
+    same = np.stack([us[0]] * 4)
+    x, st = tri.multiview_LS_triangulation(same, [Ps[0]] * 4)
+    xo, so = orc.multiview_LS_triangulation(same, [Ps[0]] * 4)
+    assert np.isfinite(x).all() and st.all()
+    assert rel_err(x, xo).max() < 1e-8
+    # NaN / Inf observations poison their point only -- unless the view is masked out
+    bad = us.copy(); bad[1, 5, 0] = np.nan; bad[2, 9, 1] = np.inf
+    x, st = tri.multiview_LS_triangulation(bad, Ps)
+    assert not np.isfinite(x[5]).all() and not np.isfinite(x[9]).all()
+    keep = np.ones(600, bool); keep[[5, 9]] = False
+    xo, _ = orc.multiview_LS_triangulation(us, Ps)
+    assert rel_err(x, xo)[keep].max() < TOL64
+    valid2 = np.ones((4, 600), bool); valid2[1, 5] = False; valid2[2, 9] = False
+    x, st = tri.multiview_LS_triangulation(bad, Ps, valid2)
+    xo, so = orc.multiview_LS_triangulation(us, Ps, valid2)
+    assert np.isfinite(x).all() and rel_err(x, xo).max() < TOL64 and np.array_equal(st, so)

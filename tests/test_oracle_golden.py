@@ -95,3 +95,21 @@ def test_scene_cells(cells, ci):
     got = replay_cell(SOLVERS, _pose(g["trajectories"], cell["traj"], cell["pose"]), num_trials=g["num_trials"],
                       rseed=g["rseed"], points_3D=np.array(g["points_3D"]))
     _check(got, cell, (1, 2), ALL_KEYS)
+
+
+def test_multiview_oracle_reduces_to_linear_ls_and_ignores_masked_views():
+    """The m-view oracle is the stacked system of the two-view one: identical for m = 2; masked
+    views change nothing; more views of the same noise level move the estimate towards the ground truth."""
+    import synthetic_rig as rig
+    u1, P1, u2, P2, X = rig.make_correspondences(2000, "rotating", 0.8)
+    x2, _ = orc.linear_LS_triangulation(u1, P1, u2, P2)
+    xm, st = orc.multiview_LS_triangulation(np.stack([u1, u2]), [P1, P2])
+    assert np.array_equal(x2, xm) and st.all()
+    us, Ps, Xm, valid = rig.make_multiview(2000, 6, 0.8, p_visible=0.7)
+    xa, sa = orc.multiview_LS_triangulation(us, Ps, valid)
+    junk = us.copy(); junk[~valid] = 1e6
+    xb, sb = orc.multiview_LS_triangulation(junk, Ps, valid)
+    assert np.array_equal(xa, xb) and np.array_equal(sa, valid.sum(axis=0) >= 2)
+    full, _ = orc.multiview_LS_triangulation(us, Ps)
+    pair, _ = orc.linear_LS_triangulation(us[0], Ps[0], us[-1], Ps[-1])
+    assert np.linalg.norm(full - Xm, axis=1).mean() < np.linalg.norm(pair - Xm, axis=1).mean()

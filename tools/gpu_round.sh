@@ -15,6 +15,8 @@ echo "== bench 10M"; timeout 600 python bench.py > $OUT/bench_10M.json 2> $OUT/b
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cut -c1-400 $OUT/bench_reference.json
 echo "== bench 100M"; timeout 600 python bench.py --points 100000000 --steps 5 --no-cpu-baseline > $OUT/bench_100M.json 2> $OUT/bench_100M.err; cut -c1-400 $OUT/bench_100M.json
 echo "== sweep 100M"; timeout 600 python tools/sweep_kernels.py --points 100000000 --solvers linear_LS,iterative_LS,linear_eigen,polynomial --modes f64,f32 --variants 0,8 --ppts 4 > $OUT/sweep_100M.jsonl 2> $OUT/sweep_100M.err; cat $OUT/sweep_100M.jsonl
+echo "== sweep 10M per rig"; for R in rotating translating forward general; do timeout 300 python tools/sweep_kernels.py --points 10000000 --solvers linear_LS,iterative_LS,linear_eigen,polynomial --modes f64 --variants 0 --ppts 4 --rig $R | sed "s/^{/{\"rig\": \"$R\", /" >> $OUT/sweep_rigs_10M.jsonl; done; cut -c1-150 $OUT/sweep_rigs_10M.jsonl
+echo "== multi-view"; timeout 300 python tools/sweep_multiview.py --views 2,4,8,16 > $OUT/sweep_multiview.jsonl 2> $OUT/sweep_multiview.err; timeout 300 python tools/sweep_multiview.py --views 8 --visible 0.7 >> $OUT/sweep_multiview.jsonl; cut -c1-200 $OUT/sweep_multiview.jsonl
 
 echo "== ncu launch list (bench --steps 2 --warmup 1)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
@@ -29,13 +31,14 @@ export_rep() {
 }
 echo "== ncu --set full, the four solver kernels at 10 M points (one launch each, after warm-up)"
 for K in k_linear_ls k_iterative_ls k_linear_eigen k_polynomial; do
-    timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -f -o $OUT/full_$K \
+    # anchored: k_linear_eigen must not match its follow-up kernel k_linear_eigen_general, k_linear_ls not its ring / tma variants
+    timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^$K\$" -s 1 -c 1 -f -o $OUT/full_$K \
         python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/full_$K.log 2>&1
     echo "$K rc=$?"
     export_rep $OUT/full_$K
 done
 echo "== ncu --set full, linear_LS at 100 M points"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_linear_ls -s 1 -c 1 -f -o $OUT/full_k_linear_ls_100M \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^k_linear_ls\$" -s 1 -c 1 -f -o $OUT/full_k_linear_ls_100M \
     python tools/sweep_kernels.py --points 100000000 --solvers linear_LS --modes f64 --variants 0 --ppts 4 --iters 2 > $OUT/full_k_linear_ls_100M.log 2>&1
 echo "100M rc=$?"
 export_rep $OUT/full_k_linear_ls_100M
