@@ -13,6 +13,8 @@ echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q > $OUT/
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -6 $OUT/smoke.log
 echo "== bench 10M"; timeout 600 python bench.py > $OUT/bench_10M.json 2> $OUT/bench_10M.err; echo "bench rc=$?"; cut -c1-600 $OUT/bench_10M.json
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cut -c1-400 $OUT/bench_reference.json
+echo "== bench 10M, evaluation of linear_LS fused as well"; timeout 300 python bench.py --no-cpu-baseline --fuse-ls-eval > $OUT/bench_10M_fuse_ls.json 2>> $OUT/bench_10M.err; cut -c1-200 $OUT/bench_10M_fuse_ls.json
+for V in variants/*.so; do [ -f $V ] || continue; echo "== bench 10M with $V"; TRGL_CUDA_LIB=$PWD/$V timeout 300 python bench.py --no-cpu-baseline > $OUT/bench_10M_$(basename $V .so).json 2>> $OUT/bench_10M.err; done
 echo "== bench 100M"; timeout 600 python bench.py --points 100000000 --steps 5 --no-cpu-baseline > $OUT/bench_100M.json 2> $OUT/bench_100M.err; cut -c1-400 $OUT/bench_100M.json
 echo "== sweep 100M"; timeout 600 python tools/sweep_kernels.py --points 100000000 --solvers linear_LS,iterative_LS,linear_eigen,polynomial --modes f64,f32 --variants 0,8 --ppts 4 > $OUT/sweep_100M.jsonl 2> $OUT/sweep_100M.err; cat $OUT/sweep_100M.jsonl
 echo "== sweep 10M per rig"; for R in rotating translating forward general; do timeout 300 python tools/sweep_kernels.py --points 10000000 --solvers linear_LS,iterative_LS,linear_eigen,polynomial --modes f64 --variants 0 --ppts 4 --rig $R | sed "s/^{/{\"rig\": \"$R\", /" >> $OUT/sweep_rigs_10M.jsonl; done; cut -c1-150 $OUT/sweep_rigs_10M.jsonl
