@@ -316,11 +316,13 @@ __device__ __forceinline__ double fast_rcp(double x) {
 __device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
 
 // Conditioning tiers of the normal-equation solve.  kappa^2(A) <= tr(M)^3 / (4 det(M)); tier 1: plain
-// adjugate solve (error ~ kappa^2 eps); tier 2: + one refinement step on the residual (error ~ kappa eps);
+// adjugate solve (error ~ kappa^2 eps in theory; measured against the SVD solve on the forward-motion and small-baseline
+// rigs: <= 1.1e-11 for bounds up to 1e6, which is the limit -- at the old limit 2e4 the forward-motion rig sent 31 % of its
+// points to tier 2, at 1e6 it sends 0.6 %); tier 2: + one refinement step on the residual (error ~ kappa eps);
 // tier 3: Jacobi SVD with the reference's rank rule.
 template <typename T> struct Tiers;
 template <> struct Tiers<double> {
-    static __device__ __forceinline__ double t1() { return 4.0 * 2.0e4; }
+    static __device__ __forceinline__ double t1() { return 4.0 * 1.0e6; }
     static __device__ __forceinline__ double t2() { return 4.0 * 1.0e10; }
 };
 template <> struct Tiers<float> {
@@ -338,8 +340,10 @@ __device__ __forceinline__ void weighted_rows(const Cams<T>& cams, T a, T b, T c
     for (int k = 0; k < 4; ++k) { rows[0][k] *= w1; rows[1][k] *= w1; rows[2][k] *= w2; rows[3][k] *= w2; }
 }
 
-// Tiers 2 and 3 in double precision on an explicit system (out of line: rare path).
-__device__ __noinline__ void solve4x3_careful_f64(const double rows[4][4], double x[3]) {
+// Tier 2 in double precision on an explicit system: normal equations + one refinement step on the residual.  Returns
+// false (x untouched) when the system is beyond tier 2 -- the caller then takes the SVD.  Inline: shared by the
+// out-of-line careful path below and by the follow-up kernel of linear_LS, so both produce the same bits.
+__device__ __forceinline__ bool solve4x3_tier2_f64(const double rows[4][4], double x[3]) {
     double M[6], v[3], M2[6], v2[3], C[6];
     normal_acc2<double>(rows[0], rows[1], M, v);
     normal_acc2<double>(rows[2], rows[3], M2, v2);
@@ -349,25 +353,28 @@ __device__ __noinline__ void solve4x3_careful_f64(const double rows[4][4], doubl
     for (int k = 0; k < 3; ++k) v[k] += v2[k];
     const double det = sym3_cofactors(M, C);
     const double tr = M[0] + M[3] + M[5];
-    if (tr * tr * tr < Tiers<double>::t2() * det) {
-        const double inv = 1.0 / det;
-        sym3_apply(C, v, inv, x);
-        double g[3] = {0, 0, 0};                       // g = A^T (b - A x), x += M^-1 g
+    if (!(tr * tr * tr < Tiers<double>::t2() * det)) return false;
+    const double inv = 1.0 / det;
+    sym3_apply(C, v, inv, x);
+    double g[3] = {0, 0, 0};                       // g = A^T (b - A x), x += M^-1 g
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            double res = -rows[r][3];
+    for (int r = 0; r < 4; ++r) {
+        double res = -rows[r][3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) res = fma(-rows[r][k], x[k], res);
+        for (int k = 0; k < 3; ++k) res = fma(-rows[r][k], x[k], res);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) g[k] = fma(rows[r][k], res, g[k]);
-        }
-        double dx[3];
-        sym3_apply(C, g, inv, dx);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) x[k] += dx[k];
-    } else {
-        solve4x3_svd<double>(rows, x);
+        for (int k = 0; k < 3; ++k) g[k] = fma(rows[r][k], res, g[k]);
     }
+    double dx[3];
+    sym3_apply(C, g, inv, dx);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[k] += dx[k];
+    return true;
+}
+
+// Tiers 2 and 3 in double precision on an explicit system (out of line: rare path).
+__device__ __noinline__ void solve4x3_careful_f64(const double rows[4][4], double x[3]) {
+    if (!solve4x3_tier2_f64(rows, x)) solve4x3_svd<double>(rows, x);
 }
 
 template <typename T>

@@ -15,6 +15,9 @@
 #ifndef TRGL_POLY_MINB
 #define TRGL_POLY_MINB 3
 #endif
+#ifndef TRGL_LS_MINB
+#define TRGL_LS_MINB 3             // linear_LS hot kernel without the in-line SVD tier: 3 CTAs/SM of loads in flight
+#endif
 #ifndef TRGL_ITER_MINB
 #define TRGL_ITER_MINB 3          // 80 registers with the evaluation epilogue, no spills
 #endif
@@ -156,16 +159,32 @@ __device__ __forceinline__ void defer_point(const Deferred& df, int64_t i) {
     const unsigned int k = atomicAdd(&df.ctl[0], 1u);
     if (k < df.cap) df.idx[k] = i;            // on overflow the follow-up kernel redoes every point instead
 }
+// Warp-aggregated append (callable from divergent code): one atomic for the lanes that are here together.  Which of the
+// two forms a kernel uses was decided by measurement: linear_LS runs at 0.93 of the copy peak with this one and at 0.84
+// with the plain atomic (same registers, same occupancy -- the plain read-modify-write sits between the four
+// interleaved points of a thread), the FP64-bound kernels are 2-3 % slower with it.
+__device__ __forceinline__ void defer_point_warp(const Deferred& df, int64_t i) {
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&df.ctl[0], static_cast<unsigned int>(__popc(mask)));
+    base = __shfl_sync(mask, base, leader);
+    const unsigned int k = base + __popc(mask & ((1u << lane) - 1u));
+    if (k < df.cap) df.idx[k] = i;
+}
 
 
 // ---- linear_LS_triangulation (triangulation.c:65-83) -----------------------------------------------------------
 // Per point: straight-line fast solve, (rare) careful redo, immediate coalesced store.  Measured on B200: storing each
 // point as soon as it is solved beats "solve all PPT points, then store" by 0.81 vs 0.65 of the HBM peak, and keeping
 // the 4x4 row block alive for an inline refinement path costs 2x (0.39).
-template <typename TI, typename TC, typename TO, int PPT, class PRE, bool EVAL, class MIR>
+// DEFER: a point beyond tier 1 is not redone in line (an out-of-line call in the hot kernel, run by one or two lanes of
+// the warp) but appended to the deferred list; k_linear_ls_general redoes it with the same solve_point_careful.
+template <typename TI, typename TC, typename TO, int PPT, class PRE, bool EVAL, class MIR, bool DEFER>
 __device__ __forceinline__ void ls_tile(const TI* __restrict__ u1, const TI* __restrict__ u2, const Cams<TC>& cams,
                                         TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const PRE& pre,
-                                        const MIR& mir, const EvalArg<EVAL>& ev, const int64_t block_base,
+                                        const MIR& mir, const EvalArg<EVAL>& ev, const Deferred& df, const int64_t block_base,
                                         TO* __restrict__ stage_warp, double (&acc)[4]) {
     const int warp = threadIdx.x >> 5;
     TC in[PPT][4];
@@ -184,32 +203,36 @@ __device__ __forceinline__ void ls_tile(const TI* __restrict__ u1, const TI* __r
         const int64_t i = block_base + p * kThreads + threadIdx.x;
         TC xs[3];
         if constexpr (PRE::kActive) pre.template apply<TI, TC>(in[p][0], in[p][1], in[p][2], in[p][3]);
-        if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs))
-            solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
+        bool done = true;
+        if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs)) {
+            if constexpr (DEFER) { done = false; if (i < n) defer_point_warp(df, i); }
+            else solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
+        }
         store_x_warp(x, block_base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]),
                          static_cast<TO>(xs[1]), static_cast<TO>(xs[2]), stage_warp, mir);
         if (i < n) store_status(status, mir, i, static_cast<uint8_t>(1));
-        fused_eval_point<EVAL, TO, TC>(ev, i < n, i, in[p][0], in[p][1], in[p][2], in[p][3], xs, 1, acc);
+        fused_eval_point<EVAL, TO, TC>(ev, (i < n) && done, i, in[p][0], in[p][1], in[p][2], in[p][3], xs, 1, acc);
     }
 }
 
-template <typename TI, typename TC, typename TO, int PPT, class PRE = PreNone, bool EVAL = false, class MIR = Mirrors>
-__global__ void __launch_bounds__(kThreads)
+template <typename TI, typename TC, typename TO, int PPT, class PRE = PreNone, bool EVAL = false, class MIR = Mirrors,
+          bool DEFER = false>
+__global__ void __launch_bounds__(kThreads, DEFER ? TRGL_LS_MINB : 1)
 k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
             TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ PRE pre,
-            const __grid_constant__ MIR mir, const __grid_constant__ EvalArg<EVAL> ev) {
+            const __grid_constant__ MIR mir, const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df) {
     __shared__ TO stage[kWarps][96];
     double acc[4] = {0, 0, 0, 0};
     if constexpr (EVAL) {
         // grid-stride loop over tiles (capped grid): the evaluation sums are reduced per CTA at the end of the kernel
         const int64_t stride = static_cast<int64_t>(gridDim.x) * (kThreads * PPT);
         for (int64_t base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT); base < n; base += stride)
-            ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR>(u1, u2, cams, x, status, n, pre, mir, ev, base, stage[threadIdx.x >> 5], acc);
+            ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR, DEFER>(u1, u2, cams, x, status, n, pre, mir, ev, df, base, stage[threadIdx.x >> 5], acc);
         fused_eval_finish<EVAL>(ev, acc);
     } else {
         // one tile per CTA
-        ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR>(u1, u2, cams, x, status, n, pre, mir, ev,
-                                            static_cast<int64_t>(blockIdx.x) * (kThreads * PPT), stage[threadIdx.x >> 5], acc);
+        ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR, DEFER>(u1, u2, cams, x, status, n, pre, mir, ev, df,
+                                                        static_cast<int64_t>(blockIdx.x) * (kThreads * PPT), stage[threadIdx.x >> 5], acc);
     }
 }
 
@@ -635,6 +658,64 @@ k_iterative_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const 
         fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, st, acc);
     }
     followup_finish<EVAL>(ev, df, acc, total > 0, !all);
+}
+
+// Follow-up kernel of k_linear_ls<..., DEFER>: the deferred points (or every point if the list overflowed) through the
+// conditioning tiers of solve_point_careful -- refinement step, Jacobi SVD with OpenCV's rank rule (triangulation.c:81).
+template <typename TI, typename TC, typename TO, class PRE = PreNone, bool EVAL = false>
+__global__ void __launch_bounds__(kThreads)
+k_linear_ls_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
+                    TO* __restrict__ x, const int64_t n, const __grid_constant__ PRE pre_stage,
+                    const __grid_constant__ Mirrors mir, const __grid_constant__ EvalArg<EVAL> ev,
+                    const __grid_constant__ Deferred df) {
+    const unsigned int listed = df.ctl[0];
+    const bool everything = listed > df.cap;
+    const int64_t total = everything ? n : static_cast<int64_t>(listed);
+    double acc[4] = {0, 0, 0, 0};
+    // 4 points per thread and pass: the list entries, then the 8 input loads, are issued together -- a rig can defer
+    // millions of points (forward motion: 40 % are beyond tier 1), and the gathers are what this kernel waits for
+    constexpr int kBatch = 4;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+    for (int64_t k0 = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; k0 < total; k0 += kBatch * stride) {
+        int64_t idx[kBatch];
+        TC in[kBatch][4];
+#pragma unroll
+        for (int p = 0; p < kBatch; ++p) {
+            const int64_t k = k0 + p * stride;
+            idx[p] = k < total ? (everything ? k : df.idx[k]) : -1;
+        }
+#pragma unroll
+        for (int p = 0; p < kBatch; ++p) {
+            in[p][0] = in[p][1] = in[p][2] = in[p][3] = TC(0);
+            if (idx[p] >= 0) reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, idx[p], in[p][0], in[p][1], in[p][2], in[p][3]);
+        }
+#pragma unroll 1
+        for (int p = 0; p < kBatch; ++p) {
+            const int64_t i = idx[p];
+            if (i < 0) continue;
+            TC xs[3];
+            // same two-step as the in-line path: points within tier 1 keep the adjugate solve (only reached on overflow)
+            if (!ls_point_fast<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], xs)) {
+                // tier 2 in line (the bulk of what a low-parallax rig defers), the SVD tier out of line -- the same
+                // arithmetic as solve_point_careful, which the non-deferring variants call
+                bool done = false;
+                if constexpr (sizeof(TC) == 8) {
+                    double rows[4][4];
+                    weighted_rows<double>(cams, in[p][0], in[p][1], in[p][2], in[p][3], 1.0, 1.0, rows);
+                    done = solve4x3_tier2_f64(rows, xs);
+                }
+                if (!done) solve_point_careful<TC>(cams, in[p][0], in[p][1], in[p][2], in[p][3], TC(1), TC(1), xs);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
+            for (int r = 0; r < mir.count; ++r) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) static_cast<TO*>(mir.x[r])[3 * i + q] = static_cast<TO>(xs[q]);
+            }
+            fused_eval_point<EVAL, TO, TC>(ev, true, i, in[p][0], in[p][1], in[p][2], in[p][3], xs, 1, acc);
+        }
+    }
+    followup_finish<EVAL>(ev, df, acc, total > 0, true);
 }
 
 // ---- linear_eigen_triangulation (triangulation.py:6-25) --------------------------------------------------------

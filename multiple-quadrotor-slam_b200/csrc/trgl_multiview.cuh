@@ -138,8 +138,22 @@ k_multiview_ls(const __grid_constant__ MultiViewArgs<TI, TC> args, TO* __restric
             const TC det = sym3_cofactors(M[p], C);
             const TC tr = M[p][0] + M[p][3] + M[p][5];
             sym3_apply(C, v3[p], fast_rcp(det), xs);
-            // not tier 1 (ill-conditioned, rank-deficient, fewer than two views, NaN): x comes from the follow-up kernel
-            if (i < n && !(tr * tr * tr < Tiers<TC>::t1() * det)) defer_point(df, i);
+            if (nviews[p] <= 1) {
+                // one view: M = A^T A has rank 2 and v = A^T b lies in its range, so the minimum-norm solution is
+                // M^+ v = (tr(M) v - M v) / (sum of the principal 2x2 minors)   (Cayley-Hamilton on the range);
+                // no view: x = 0.  Both are what the SVD rule returns; neither needs the follow-up kernel.
+                const TC e2 = C[0] + C[3] + C[5];
+                const TC inv = nviews[p] == 1 ? fast_rcp(e2) : TC(0);
+                const TC Mv0 = tfma(M[p][0], v3[p][0], tfma(M[p][1], v3[p][1], M[p][2] * v3[p][2]));
+                const TC Mv1 = tfma(M[p][1], v3[p][0], tfma(M[p][3], v3[p][1], M[p][4] * v3[p][2]));
+                const TC Mv2 = tfma(M[p][2], v3[p][0], tfma(M[p][4], v3[p][1], M[p][5] * v3[p][2]));
+                xs[0] = nviews[p] == 1 ? tfma(tr, v3[p][0], -Mv0) * inv : TC(0);
+                xs[1] = nviews[p] == 1 ? tfma(tr, v3[p][1], -Mv1) * inv : TC(0);
+                xs[2] = nviews[p] == 1 ? tfma(tr, v3[p][2], -Mv2) * inv : TC(0);
+            } else if (i < n && !(tr * tr * tr < Tiers<TC>::t1() * det)) {
+                // not tier 1 (ill-conditioned, rank-deficient, NaN): x comes from the follow-up kernel
+                defer_point(df, i);
+            }
             store_x_warp(x, base + p * kThreads + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
                          static_cast<TO>(xs[2]), stage[warp], nomir);
             if (i < n) status[i] = static_cast<uint8_t>(nviews[p] >= args.min_views ? 1 : 0);

@@ -269,26 +269,49 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
             case 10: rc = launch_ls_ring<TI, TC, TO, 4, 3, 2>(a, b, cams, xo, status, n, s, mir); break;
             case 11: rc = launch_ls_ring<TI, TC, TO, 2, 4, 3>(a, b, cams, xo, status, n, s, mir); break;
             case 12: rc = launch_ls_ring<TI, TC, TO, 2, 6, 2>(a, b, cams, xo, status, n, s, mir); break;
-            default:
+            default: {
+                // float64 arithmetic with 4 points per thread (or pixel inputs): the hot kernel defers what is beyond tier 1
+                // to a follow-up kernel instead of redoing it in line (no subroutine call in the hot kernel)
+                const bool defer = sizeof(TC) == 8 && g_two_ray.load() && (pre || ev || ppt == 4);
+                Deferred df = {nullptr, nullptr, 0u};
+                if (defer) {
+                    Scratch sc;
+                    rc = scratch_for(s, sc, n);
+                    if (rc) break;
+                    df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+                }
                 with_eval(ev, [&](auto E, auto evarg) {
                     constexpr bool EV = decltype(E)::value;
                     if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
                         if (pre) {      // pixel inputs: the undistortion makes the kernel FP64-bound, one point per thread
                             const unsigned grid = EV ? ls_eval_grid(n, kThreads) : grid_for(n, kThreads);
-                            k_linear_ls<TI, TC, TO, 1, PreUndistort, EV><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreUndistort{*pre}, mir, evarg);
+                            if (defer) k_linear_ls<TI, TC, TO, 1, PreUndistort, EV, Mirrors, true><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreUndistort{*pre}, mir, evarg, df);
+                            else k_linear_ls<TI, TC, TO, 1, PreUndistort, EV><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreUndistort{*pre}, mir, evarg, df);
                         } else if (!EV && ppt == 4 && mir.count == 0) {
                             // THE hot path: no pre-stage, no epilogue, no mirrors compiled in
-                            k_linear_ls<TI, TC, TO, 4, PreNone, false, NoMirrors><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, NoMirrors{}, EvalArg<false>{});
+                            if (defer) k_linear_ls<TI, TC, TO, 4, PreNone, false, NoMirrors, true><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, NoMirrors{}, EvalArg<false>{}, df);
+                            else k_linear_ls<TI, TC, TO, 4, PreNone, false, NoMirrors><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, NoMirrors{}, EvalArg<false>{}, df);
                         } else if (EV || ppt == 4) {
                             const unsigned grid = EV ? ls_eval_grid(n, kThreads * 4) : grid_for(n, kThreads * 4);
-                            k_linear_ls<TI, TC, TO, 4, PreNone, EV><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, evarg);
+                            if (defer) k_linear_ls<TI, TC, TO, 4, PreNone, EV, Mirrors, true><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, evarg, df);
+                            else k_linear_ls<TI, TC, TO, 4, PreNone, EV><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, evarg, df);
                         } else if (ppt == 2) {
-                            k_linear_ls<TI, TC, TO, 2, PreNone, false><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, EvalArg<false>{});
+                            k_linear_ls<TI, TC, TO, 2, PreNone, false><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, EvalArg<false>{}, df);
                         } else {
-                            k_linear_ls<TI, TC, TO, 1, PreNone, false><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, EvalArg<false>{});
+                            k_linear_ls<TI, TC, TO, 1, PreNone, false><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, EvalArg<false>{}, df);
+                        }
+                        if (defer) {
+                            const int64_t tiles = (n + kThreads - 1) / kThreads;
+                            if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); }
+                            const int64_t cap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+                            const unsigned fgrid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+                            if (pre) k_linear_ls_general<TI, TC, TO, PreUndistort, EV><<<fgrid, kThreads, 0, s>>>(a, b, cams, xo, n, PreUndistort{*pre}, mir, evarg, df);
+                            else k_linear_ls_general<TI, TC, TO, PreNone, EV><<<fgrid, kThreads, 0, s>>>(a, b, cams, xo, n, PreNone{}, mir, evarg, df);
+                            g_launches++;
                         }
                     }
                 });
+            }
         }
     })
     if (rc) return rc;
