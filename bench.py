@@ -371,8 +371,10 @@ def run_ours(args, rank, world, local_rank):
                      "unit": "GB/s", "frac": ls["hbm_frac"],
                      "traffic": (traffic.get("linear_LS") * n) if traffic.get("linear_LS") else None,
                      "peak_source": peak_src, "alg_bytes_per_launch": ALG_BYTES["linear_LS"] * n,
-                     "note": "HBM-bound solver named by the north-star target; per_solver lists all four kernels "
-                             "(iterative_LS / linear_eigen / polynomial are FP64-pipe bound)"},
+                     "note": "HBM-bound solver named by the north-star target (k_linear_ls + its ~4 us follow-up kernel, "
+                             "timed together); per_solver lists all four kernels (iterative_LS / linear_eigen / polynomial "
+                             "are FP64-pipe bound).  peak is the measured 1:1 COPY bandwidth; this kernel reads 32 and "
+                             "writes 25 bytes per point, so frac can reach ~1.03 at 100 M points (DESIGN.md section 6)"},
         "per_solver": per_solver,
         "e2e": {"value": 4.0 * n * world * e2e_steps / e2e_s, "unit": UNIT, "steps": e2e_steps,
                 "h2d_bytes_per_step": 4 * 32 * n, "d2h_bytes_per_step": (25 + 25 + 28 + 25) * n,
