@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define TRGL_VERSION 104
+#define TRGL_VERSION 105
 
 enum { TRGL_F64 = 0, TRGL_F32IO = 1, TRGL_F32 = 2, TRGL_F64_OUT32 = 3, TRGL_F32_OUT64 = 4 };
 enum { TRGL_MEM_HOST = 0, TRGL_MEM_DEVICE = 1 };

@@ -74,8 +74,18 @@ def test_bad_arguments_rejected_before_any_device_work():
         tc.linear_ls(u, np.eye(3), u, np.eye(4))              # not 3x4 / 4x4
     with pytest.raises(ValueError):
         tc.linear_ls(u, np.eye(4), np.zeros((5, 2)), np.eye(4))
+    us = np.zeros((3, 4, 2))
+    with pytest.raises(ValueError):
+        tc.multiview_ls(us[:, :, 0], [np.eye(4)] * 3)                 # not (m, n, 2)
+    with pytest.raises(ValueError):
+        tc.multiview_ls(us, [np.eye(4)] * 2)                          # one camera matrix per view
+    with pytest.raises(ValueError):
+        tc.multiview_ls(us, [np.eye(4)] * 3, valid=np.ones((3, 5)))   # mask must be (m, n)
     L = tc.lib()
     P = (ctypes.c_double * 12)()
+    assert L.trgl_multiview_ls(None, None, P, 17, None, None, 0, 2, 0, 0, None) == -1   # more than 16 views
+    assert L.trgl_multiview_ls(None, None, P, 2, None, None, 4, 2, 0, 0, None) == -1    # NULL arrays, n > 0
+    assert L.trgl_set_two_ray(1) == 1 and L.trgl_set_deferred_capacity(1 << 26) == 1 << 26     # knobs return the old value
     assert L.trgl_linear_ls(None, None, P, P, None, None, 4, 0, 0, None) == -1      # NULL arrays, n > 0
     assert L.trgl_linear_ls(None, None, P, P, None, None, 4, 99, 0, None) == -1     # unknown mode
     assert b"mode" in L.trgl_last_error_string()
