@@ -175,3 +175,24 @@ def triangulate_pairs_sharded(solve_fn, u_by_cam, cams, segs, gather=True, devic
     if not gather:
         return x, st, (lo, hi)
     return gather_shards(x, total, device), gather_shards(st, total, device)
+
+
+def triangulate_multiview_sharded(solve_fn, us, Ps, valid=None, gather=True, device=None, **kwargs):
+    """
+    m-view scene: shard the POINT axis of `us` (m, N, 2) / `valid` (m, N) over the ranks; every
+    rank receives all m camera matrices from rank 0.  `solve_fn` has the signature of
+    triangulation.multiview_LS_triangulation(us, Ps, valid, ...).  Returns (x, status) assembled on every rank when
+    `gather` is true, else this rank's shard and its (lo, hi).  No data-path collective besides the optional gather.
+    """
+    dist = _dist()
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if on else 0
+    world = dist.get_world_size() if on else 1
+    n = us.shape[1]
+    cams = broadcast_cameras(np.stack([np.asarray(P, dtype=np.float64)[0:3] for P in Ps]), 0, device)
+    lo, hi = shard_range(n, rank, world)
+    x, status = solve_fn(us[:, lo:hi], list(cams), None if valid is None else valid[:, lo:hi], **kwargs)
+    if not gather:
+        return x, status, (lo, hi)
+    return gather_shards(x, n, device), gather_shards(status, n, device)
+

@@ -209,7 +209,10 @@ def _gloo_worker(rank, world, port, tmp):
     u_by = {(i, j): (rng.normal(0, 0.05, (c, 2)), rng.normal(0, 0.05, (c, 2))) for (i, j, o, c) in segs}
     xp, sp = sharding.triangulate_pairs_sharded(orc.linear_LS_triangulation, u_by, cams if rank == 0 else
                                                 [np.zeros((3, 4))] * 4, segs)
-    np.savez(os.path.join(tmp, "r%d.npz" % rank), x=x, st=st, xp=xp, sp=sp)
+    us, Ps, Xm, valid = rig.make_multiview(1003, 5, 0.8, p_visible=0.7)
+    xm, sm = sharding.triangulate_multiview_sharded(orc.multiview_LS_triangulation, us,
+                                                    Ps if rank == 0 else [np.zeros((3, 4))] * 5, valid)
+    np.savez(os.path.join(tmp, "r%d.npz" % rank), x=x, st=st, xp=xp, sp=sp, xm=xm, sm=sm)
     dist.destroy_process_group()
 
 
@@ -231,6 +234,12 @@ def test_sharded_path_world_size_2_gloo(tmp_path):
         d = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
         assert np.array_equal(d["st"], so) and np.allclose(d["x"], xo, rtol=1e-12, atol=1e-12)
         assert d["xp"].shape == (999, 3) and np.allclose(d["xp"], xp, rtol=1e-12, atol=1e-12) and d["sp"].all()
+    # m-view scene: points sharded, all cameras broadcast
+    us, Ps, Xm, valid = rig.make_multiview(1003, 5, 0.8, p_visible=0.7)
+    xmo, smo = orc.multiview_LS_triangulation(us, Ps, valid)
+    for r in range(2):
+        d = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        assert np.array_equal(d["sm"], smo) and np.allclose(d["xm"], xmo, rtol=1e-12, atol=1e-12)
 
 
 # ---- input normalisation: oracle pinned to cv2 ------------------------------------------------
