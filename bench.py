@@ -31,7 +31,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "multiple-quadrotor-slam_b200")
-for p in (ROOT, PKG):
+for p in (ROOT, PKG, os.path.join(ROOT, "harness")):
     if p not in sys.path:
         sys.path.insert(0, p)
 

@@ -34,9 +34,14 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __re
 // Same, followed by the grid-level sum inside the kernel when `final_out` is given: the last CTA to arrive (ticket on
 // `counter`, which it resets for the next launch) adds the per-block partials in block order -- the order the host uses --
 // and writes NV doubles to device memory, so the caller needs no synchronisation to own the result in stream order.
+// `deferred_ctl` / `deferred_cap` (hot solver kernels only): when more points were deferred than the list holds, the
+// follow-up kernel redoes EVERY point and accumulates every point's evaluation, so the hot kernel's own sums must not
+// be counted a second time -- the last CTA then writes zeros.  (Every CTA's list appends precede its ticket, so the
+// last CTA sees the final count.)
 template <int NV>
 __device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], double* __restrict__ partials,
-                                                      unsigned int* __restrict__ counter, double* __restrict__ final_out) {
+                                                      unsigned int* __restrict__ counter, double* __restrict__ final_out,
+                                                      const unsigned int* deferred_ctl = nullptr, unsigned int deferred_cap = 0u) {
     block_reduce_store<NV>(v, partials);
     if (final_out == nullptr) return;
     __shared__ bool is_last;
@@ -48,6 +53,7 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], double* _
         if (threadIdx.x < NV) {
             double s = 0.0;
             for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[b * NV + threadIdx.x]);
+            if (deferred_ctl != nullptr && __ldcg(deferred_ctl) > deferred_cap) s = 0.0;
             final_out[threadIdx.x] = s;
         }
         if (threadIdx.x == 0) *counter = 0u;
@@ -118,8 +124,9 @@ __device__ __forceinline__ void fused_eval_point(const EvalArg<EVAL>& ev, bool v
     }
 }
 template <bool EVAL>
-__device__ __forceinline__ void fused_eval_finish(const EvalArg<EVAL>& ev, double (&acc)[4]) {
-    if constexpr (EVAL) block_reduce_finalize<4>(acc, ev.e.partials, ev.e.counter, ev.e.sums_out);
+__device__ __forceinline__ void fused_eval_finish(const EvalArg<EVAL>& ev, double (&acc)[4],
+                                                  const unsigned int* deferred_ctl = nullptr, unsigned int deferred_cap = 0u) {
+    if constexpr (EVAL) block_reduce_finalize<4>(acc, ev.e.partials, ev.e.counter, ev.e.sums_out, deferred_ctl, deferred_cap);
 }
 
 }  // namespace trgl

@@ -228,7 +228,7 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
         const int64_t stride = static_cast<int64_t>(gridDim.x) * (kThreads * PPT);
         for (int64_t base = static_cast<int64_t>(blockIdx.x) * (kThreads * PPT); base < n; base += stride)
             ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR, DEFER>(u1, u2, cams, x, status, n, pre, mir, ev, df, base, stage[threadIdx.x >> 5], acc);
-        fused_eval_finish<EVAL>(ev, acc);
+        fused_eval_finish<EVAL>(ev, acc, DEFER ? df.ctl : nullptr, df.cap);
     } else {
         // one tile per CTA
         ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR, DEFER>(u1, u2, cams, x, status, n, pre, mir, ev, df,
@@ -600,7 +600,7 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         }
         if (!have_tile) break;
     }
-    fused_eval_finish<EVAL>(ev, acc);
+    fused_eval_finish<EVAL>(ev, acc, df.ctl, df.cap);
 }
 
 // Tail of the follow-up kernels: add this thread's evaluation sums to the sums the hot kernel has already written
@@ -915,7 +915,7 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
             fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);
         }
     }
-    fused_eval_finish<EVAL>(ev, acc);
+    fused_eval_finish<EVAL>(ev, acc, df.ctl, df.cap);
 }
 
 // Follow-up kernel of k_linear_eigen: the deferred points (or every point if the list overflowed) through the one-sided
@@ -1021,7 +1021,7 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
         if (f1) atomicOr(&not_nan_count[0], 1u);
         if (f2) atomicOr(&not_nan_count[1], 1u);
     }
-    fused_eval_finish<EVAL>(ev, acc);
+    fused_eval_finish<EVAL>(ev, acc, df.ctl, df.cap);
 }
 
 // Follow-up kernel of k_polynomial: the complete correction (Durand-Kerner root finding as cv::solvePoly runs it) and the

@@ -6,7 +6,7 @@
 //
 // One thread per point (two for m <= 4).  The 2m x 3 system is never materialised: views are streamed through registers
 // in groups (8 vector loads in flight per thread) and folded into the 3x3 normal equations; well-conditioned points
-// (kappa^2 bound < 2e4, as in the two-view solver) finish with the adjugate solve.  The rest is deferred to a follow-up
+// (kappa^2 bound < 1e6, Tiers<double>::t1, as in the two-view solver) finish with the adjugate solve.  The rest is deferred to a follow-up
 // kernel (as in k_iterative_ls: no subroutine call in the hot kernel) that runs a streaming Givens QR -- each row is rotated into a 3x4 triangular factor [R | Q^T b], whose singular values are those
 // of the full system -- followed by the 3x3 Jacobi SVD with OpenCV's rank rule, so rank-deficient and ill-conditioned
 // points behave like the two-view careful path.

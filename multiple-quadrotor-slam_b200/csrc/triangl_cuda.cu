@@ -148,7 +148,42 @@ int scratch_for(cudaStream_t s, Scratch& out, int64_t deferred_points = 0);
 
 // Launch geometry of the bulk-async variants: persistent grid of SMs x (CTAs that fit in shared memory).
 std::atomic<int> g_variant{-1};         // -1 = auto, 0 = per-thread loads, >= 1 = bulk-async pipeline (trgl_set_stream_variant)
-int g_sm_count = 0;
+
+// Launch geometry is cached per (device, kernel instantiation): cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the
+// occupancy query apply to the CURRENT device only, and one host thread may drive several devices (trgl_set_device).
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_sm_by_device[kMaxDevices];
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev;
+}
+int sm_count() {
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) return 148;
+    int n = g_sm_by_device[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        g_sm_by_device[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+// Resident CTAs per SM of `kern` at kThreads threads and `dyn_smem` bytes of dynamic shared memory on the current device
+// (raises the kernel's dynamic shared-memory limit there first when it exceeds the 48 KB default).
+template <typename K>
+int blocks_per_sm(K kern, size_t dyn_smem) {
+    static thread_local std::map<std::pair<int, const void*>, int> cache;
+    int& per_sm = cache[std::make_pair(current_device(), reinterpret_cast<const void*>(kern))];
+    if (per_sm == 0) {
+        if (dyn_smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, dyn_smem) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+    }
+    return per_sm;
+}
 std::atomic<int> g_two_ray{1};          // 0 = no two-ray closed forms in iterative_LS / polynomial (trgl_set_two_ray)
 
 template <typename TI, typename TC, typename TO, int PPT, int STAGES, int MINB>
@@ -157,20 +192,9 @@ int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_
     constexpr int TILE = kThreads * PPT;
     const size_t smem = size_t(STAGES) * 2 * TILE * 2 * sizeof(TI) + kWarps * 96 * sizeof(TO) + STAGES * sizeof(uint64_t);
     auto kern = k_linear_ls_tma<TI, TC, TO, PPT, STAGES, MINB>;
-    static thread_local bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
-    if (g_sm_count == 0) {
-        int dev = 0; CK(cudaGetDevice(&dev));
-        CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
+    const int64_t full = static_cast<int64_t>(sm_count()) * blocks_per_sm(kern, smem);
     const int64_t ntiles = (n + TILE - 1) / TILE;
-    const int64_t grid = ntiles < int64_t(g_sm_count) * per_sm ? ntiles : int64_t(g_sm_count) * per_sm;
+    const int64_t grid = ntiles < full ? ntiles : full;
     kern<<<static_cast<unsigned>(grid), kThreads, smem, s>>>(a, b, cams, xo, status, n, mir);
     return TRGL_OK;
 }
@@ -179,19 +203,8 @@ int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_
 // the batch has fewer 256-point tiles than that.
 template <typename K>
 unsigned persistent_grid(K kern, int64_t n, size_t dyn_smem = 0) {
-    static thread_local std::unordered_map<const void*, int> cache;     // keyed by the instantiation's address
-    if (g_sm_count == 0) {
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    int& per_sm = cache[reinterpret_cast<const void*>(kern)];
-    if (per_sm == 0) {
-        if (dyn_smem > 48 * 1024)
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    }
     const int64_t tiles = (n + kThreads - 1) / kThreads;
-    const int64_t full = static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148) * per_sm;
+    const int64_t full = static_cast<int64_t>(sm_count()) * blocks_per_sm(kern, dyn_smem);
     return static_cast<unsigned>(tiles < full ? tiles : full);
 }
 
@@ -200,15 +213,8 @@ int launch_ls_ring(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8
                    const Mirrors& mir) {
     const size_t smem = size_t(DEPTH) * 2 * kThreads * PPT * 2 * sizeof(TI) + kWarps * 96 * sizeof(TO);
     auto kern = k_linear_ls_ring<TI, TC, TO, PPT, DEPTH, MINB>;
-    static thread_local std::unordered_map<const void*, int> per_sm_cache;
-    int& per_sm = per_sm_cache[reinterpret_cast<const void*>(kern)];
-    if (per_sm == 0) {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        if (g_sm_count == 0) { int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)); }
-    }
     const int64_t tiles = (n + kThreads * PPT - 1) / (kThreads * PPT);
-    const int64_t full = static_cast<int64_t>(g_sm_count) * per_sm;
+    const int64_t full = static_cast<int64_t>(sm_count()) * blocks_per_sm(kern, smem);
     kern<<<static_cast<unsigned>(tiles < full ? tiles : full), kThreads, smem, s>>>(a, b, cams, xo, status, n, mir);
     return TRGL_OK;
 }
@@ -230,9 +236,8 @@ int eval_unsupported() { return fail(TRGL_E_BADARG, "the fused evaluation needs 
 
 // Persistent grid of the evaluation-fused linear_LS kernel (its block partials must fit the reduction scratch).
 unsigned ls_eval_grid(int64_t n, int per_block) {
-    if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); }
     const int64_t tiles = (n + per_block - 1) / per_block;
-    const int64_t cap = static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148) * 8;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
     return static_cast<unsigned>(tiles < cap ? tiles : cap);
 }
 
@@ -302,8 +307,7 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
                         }
                         if (defer) {
                             const int64_t tiles = (n + kThreads - 1) / kThreads;
-                            if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); }
-                            const int64_t cap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+                            const int64_t cap = 2 * static_cast<int64_t>(sm_count());
                             const unsigned fgrid = static_cast<unsigned>(tiles < cap ? tiles : cap);
                             if (pre) k_linear_ls_general<TI, TC, TO, PreUndistort, EV><<<fgrid, kThreads, 0, s>>>(a, b, cams, xo, n, PreUndistort{*pre}, mir, evarg, df);
                             else k_linear_ls_general<TI, TC, TO, PreNone, EV><<<fgrid, kThreads, 0, s>>>(a, b, cams, xo, n, PreNone{}, mir, evarg, df);
@@ -349,7 +353,7 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
                         kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
                             a, b, cams, geom, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df);
                         const int64_t tiles = (n + kThreads - 1) / kThreads;
-                        const int64_t cap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+                        const int64_t cap = 2 * static_cast<int64_t>(sm_count());
                         general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
                             a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df, 0);
                         nlaunch = 2;
@@ -391,7 +395,7 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
                     // hot kernel (Rayleigh-quotient iteration, certified) + follow-up over the points it deferred (Jacobi SVD)
                     auto launch = [&](auto kern, auto general) {
                         kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
-                        const int64_t cap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+                        const int64_t cap = 2 * static_cast<int64_t>(sm_count());
                         general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
                     };
                     if (rows == 4) launch(k_linear_eigen<TI, TC, TO, 4, PRE, EV>, k_linear_eigen_general<TI, TC, TO, 4, PRE, EV>);
@@ -432,7 +436,7 @@ int launch_polynomial(const void* u1, const void* u2, const double* P1, const do
                         if (closed_form) {
                             // hot kernel (certified correction + ray intersection) + follow-up over the points it deferred
                             kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, geom, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
-                            const int64_t cap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+                            const int64_t cap = 2 * static_cast<int64_t>(sm_count());
                             general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 0);
                             nlaunch = 2;
                         } else {
@@ -609,32 +613,41 @@ int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
     for (int a = 0; a < narrays; ++a) per_chunk += align256(arrays[a].bytes_per_point * chunk);
     const int nslots = n > chunk ? kSlots : 1;
     for (int s = 0; s < nslots; ++s) { int rc = ensure_slot(g_slots[s], per_chunk); if (rc) return rc; }
+    // Any failure inside the loop still drains every slot before returning: earlier chunks have asynchronous copies in
+    // flight into the CALLER's buffers, which the caller may free as soon as it sees the error code.
+    int rc = TRGL_OK;
     int idx = 0;
-    for (int64_t off = 0; off < n; off += chunk, ++idx) {
+    for (int64_t off = 0; off < n && rc == TRGL_OK; off += chunk, ++idx) {
         Slot& sl = g_slots[idx % nslots];
         const int64_t m = (n - off) < chunk ? (n - off) : chunk;
         void* dptr[kMaxHostArrays];
         size_t pos = 0;
-        for (int a = 0; a < narrays; ++a) {
+        for (int a = 0; a < narrays && rc == TRGL_OK; ++a) {
             dptr[a] = sl.buf + pos;
             pos += align256(arrays[a].bytes_per_point * chunk);
-            if (arrays[a].in)
-                CK(cudaMemcpyAsync(dptr[a], static_cast<const char*>(arrays[a].in) + off * arrays[a].bytes_per_point,
-                                   arrays[a].bytes_per_point * m, cudaMemcpyHostToDevice, sl.stream));
+            if (arrays[a].in) {
+                const cudaError_t e = cudaMemcpyAsync(dptr[a], static_cast<const char*>(arrays[a].in) + off * arrays[a].bytes_per_point,
+                                                      arrays[a].bytes_per_point * m, cudaMemcpyHostToDevice, sl.stream);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync (host pipeline, H2D)");
+            }
         }
-        int rc = launch(dptr, m, sl.stream, idx % nslots);
-        if (rc) return rc;
-        for (int a = 0; a < narrays; ++a)
-            if (arrays[a].out)
-                CK(cudaMemcpyAsync(static_cast<char*>(arrays[a].out) + off * arrays[a].bytes_per_point, dptr[a],
-                                   arrays[a].bytes_per_point * m, cudaMemcpyDeviceToHost, sl.stream));
+        if (rc == TRGL_OK) rc = launch(dptr, m, sl.stream, idx % nslots);
+        for (int a = 0; a < narrays && rc == TRGL_OK; ++a)
+            if (arrays[a].out) {
+                const cudaError_t e = cudaMemcpyAsync(static_cast<char*>(arrays[a].out) + off * arrays[a].bytes_per_point, dptr[a],
+                                                      arrays[a].bytes_per_point * m, cudaMemcpyDeviceToHost, sl.stream);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync (host pipeline, D2H)");
+            }
     }
-    for (int s = 0; s < nslots; ++s) CK(cudaStreamSynchronize(g_slots[s].stream));
-    return TRGL_OK;
+    for (int s = 0; s < nslots; ++s) {
+        const cudaError_t e = cudaStreamSynchronize(g_slots[s].stream);
+        if (e != cudaSuccess && rc == TRGL_OK) rc = cuda_fail(e, "cudaStreamSynchronize (host pipeline)");
+    }
+    return rc;
 }
 
 int check_common(const void* u1, const void* u2, const double* P1, const double* P2, const void* x, const void* status,
-                 int64_t n, int mode, int mem) {
+                 int64_t n, int mode, int mem, void* stream) {
     ModeInfo mi;
     if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
     if (!mode_info(mode, mi)) return fail(TRGL_E_BADARG, "unknown precision mode");
@@ -654,7 +667,7 @@ int check_common(const void* u1, const void* u2, const double* P1, const double*
         const PendingEval pe = g_next_eval;
         g_next_eval.armed = false;
         if (mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "the fused evaluation needs device buffers (TRGL_MEM_DEVICE)");
-        cudaMemsetAsync(pe.sums, 0, 4 * sizeof(double), nullptr);        // n == 0: all sums are zero
+        cudaMemsetAsync(pe.sums, 0, 4 * sizeof(double), static_cast<cudaStream_t>(stream));   // n == 0: all sums are zero, in the call's stream order
     }
     return TRGL_OK;
 }
@@ -898,7 +911,7 @@ int trgl_set_points_per_thread(int ppt) {
 // ---------------------------------------------------------------------------------------------------------------
 static int impl_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                           int64_t n, int mode, int mem, void* stream, const Undist2* pre) {
-    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
+    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem, stream);
     if (rc || n == 0) return rc;
     if (mem == TRGL_MEM_DEVICE) {
         FusedEval fe; const FusedEval* evp;
@@ -946,8 +959,7 @@ static int launch_multiview_ls(void* const* u, void* const* valid, const double*
                 for (int k = 0; k < 12; ++k) args.P[v][k] = P[12 * v + k];
             }
             args.m = m; args.min_views = min_views;
-            if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); }
-            const int64_t cap = static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148) * 16;
+            const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
             if (m <= 4) {
                 const int64_t tiles = (n + 2 * kThreads - 1) / (2 * kThreads);
                 k_multiview_ls<TI, TC, TO, 2, 4><<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
@@ -958,7 +970,7 @@ static int launch_multiview_ls(void* const* u, void* const* valid, const double*
                     args, static_cast<TO*>(x), status, n, df);
             }
             const int64_t ftiles = (n + kThreads - 1) / kThreads;
-            const int64_t fcap = 2 * static_cast<int64_t>(g_sm_count > 0 ? g_sm_count : 148);
+            const int64_t fcap = 2 * static_cast<int64_t>(sm_count());
             k_multiview_general<TI, TC, TO><<<static_cast<unsigned>(ftiles < fcap ? ftiles : fcap), kThreads, 0, s>>>(
                 args, static_cast<TO*>(x), n, df);
         } else {
@@ -973,6 +985,7 @@ static int launch_multiview_ls(void* const* u, void* const* valid, const double*
 
 int trgl_multiview_ls(const void* u, const uint8_t* valid, const double* P, int m, void* x, uint8_t* status, int64_t n,
                       int min_views, int mode, int mem, void* stream) {
+    PendingClear pending_clear;       // a mirror / evaluation request armed before this call does not leak into the next one
     ModeInfo mi;
     if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
     if (!mode_info(mode, mi)) return fail(TRGL_E_BADARG, "unknown precision mode");
@@ -1007,7 +1020,7 @@ int trgl_multiview_ls(const void* u, const uint8_t* valid, const double* P, int 
 
 static int impl_iterative_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, int32_t* status,
                              int64_t n, double tolerance, int semantics, int mode, int mem, void* stream, const Undist2* pre) {
-    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
+    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem, stream);
     if (rc) return rc;
     if (semantics != TRGL_ITER_C && semantics != TRGL_ITER_PY) return fail(TRGL_E_BADARG, "unknown iterative semantics");
     if (n == 0) return TRGL_OK;
@@ -1042,7 +1055,7 @@ int trgl_iterative_ls_px(const void* px1, const void* px2, const double* K1, con
 static int impl_linear_eigen(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                              int64_t n, double max_coordinate_value, int rows, int mode, int mem, void* stream,
                              const Undist2* pre) {
-    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
+    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem, stream);
     if (rc) return rc;
     if (rows != 4 && rows != 6) return fail(TRGL_E_BADARG, "rows must be 4 or 6");
     if (n == 0) return TRGL_OK;
@@ -1077,7 +1090,7 @@ int trgl_linear_eigen_px(const void* px1, const void* px2, const double* K1, con
 static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, const double* P2, const double* F, void* x,
                              uint8_t* status, void* u1_corr, void* u2_corr, int* all_nan, int64_t n,
                              double max_coordinate_value, int rows, int mode, int mem, void* stream, const Undist2* pre) {
-    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem);
+    int rc = check_common(u1, u2, P1, P2, x, status, n, mode, mem, stream);
     if (rc) return rc;
     if (!F) return fail(TRGL_E_BADARG, "F is NULL");
     if (rows != 4 && rows != 6) return fail(TRGL_E_BADARG, "rows must be 4 or 6");
@@ -1110,7 +1123,10 @@ static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, c
     Scratch sc;
     rc = scratch_for(nullptr, sc);
     if (rc) return rc;
+    // the pipeline slots run on non-blocking streams, which are not ordered behind the legacy default stream: the
+    // clear must have completed before any slot's kernel can set a flag
     CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * 2 * kSlots));
+    CK(cudaStreamSynchronize(nullptr));
     HostArray arr[6] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1},
                         {nullptr, u1_corr, size_t(2 * mi.in_bytes)}, {nullptr, u2_corr, size_t(2 * mi.in_bytes)}};
@@ -1174,7 +1190,8 @@ int trgl_undistort_points(const void* src, void* dst, const double* K, const dou
     const size_t pb = in_is_f32 ? 8 : 16;
     auto run = [&](const void* s_, void* d_, int64_t m, cudaStream_t st) -> int {
         const int64_t tiles = (m + kThreads - 1) / kThreads;
-        const unsigned grid = static_cast<unsigned>(tiles < 148 * 16 ? tiles : 148 * 16);
+        const int64_t gcap = static_cast<int64_t>(sm_count()) * 16;
+        const unsigned grid = static_cast<unsigned>(tiles < gcap ? tiles : gcap);
         if (in_is_f32) k_undistort_points<float><<<grid, kThreads, 0, st>>>(static_cast<const float*>(s_), static_cast<float*>(d_), U, m);
         else k_undistort_points<double><<<grid, kThreads, 0, st>>>(static_cast<const double*>(s_), static_cast<double*>(d_), U, m);
         g_launches++;

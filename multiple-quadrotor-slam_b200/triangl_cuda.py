@@ -246,8 +246,36 @@ def pinned_copy(a):
     return out
 
 
+_FLOAT_DTYPES = (np.dtype(np.float32), np.dtype(np.float64))
+
+
 def _is_device(a):
     return hasattr(a, "data_ptr")
+
+
+def _host_if_cpu_tensor(a):
+    """A CPU torch tensor is a HOST array (its data_ptr() is a host address): hand NumPy its memory instead."""
+    if hasattr(a, "data_ptr") and hasattr(a, "is_cuda") and not a.is_cuda:
+        return a.detach().numpy()
+    return a
+
+
+def _np_dtype(a):
+    return np.dtype(str(a.dtype).replace("torch.", ""))
+
+
+def _check_device_array(a, cols, name, dtypes=_FLOAT_DTYPES):
+    """Device buffers are read as packed row-major (n, cols) arrays: reject anything a kernel would misread."""
+    shape = tuple(int(v) for v in a.shape)
+    if cols:
+        if len(shape) != 2 or shape[1] != cols:
+            raise ValueError("%s: device buffer must have shape (n, %d), got %r" % (name, cols, shape))
+    elif len(shape) != 1:
+        raise ValueError("%s: device buffer must have shape (n,), got %r" % (name, shape))
+    if hasattr(a, "is_contiguous") and not a.is_contiguous():
+        raise ValueError("%s: device tensor must be contiguous (call .contiguous()); a strided view would be read as packed" % name)
+    if dtypes is not None and _np_dtype(a) not in dtypes:
+        raise ValueError("%s: unsupported dtype %s" % (name, a.dtype))
 
 
 def _ptr(a):
@@ -270,7 +298,6 @@ def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
 
-_FLOAT_DTYPES = (np.dtype(np.float32), np.dtype(np.float64))
 _MODE = {(8, 8, 8): F64, (4, 8, 4): F32IO, (4, 4, 4): F32, (8, 8, 4): F64_OUT32, (4, 8, 8): F32_OUT64}
 
 
@@ -292,6 +319,7 @@ def _prep(u1, u2, compute_dtype, out_dtype):
         if np.dtype(compute_dtype) == np.float32 and (in_dtype != np.float32 or np.dtype(out_dtype) != np.float32):
             compute_dtype = np.float64
         return u1, u2, False, len(u1), mode_for(in_dtype, compute_dtype, out_dtype)
+    u1 = _host_if_cpu_tensor(u1); u2 = _host_if_cpu_tensor(u2)
     dev = _is_device(u1)
     if dev != _is_device(u2):
         raise ValueError("u1 and u2 must both be host arrays or both be device buffers")
@@ -300,10 +328,12 @@ def _prep(u1, u2, compute_dtype, out_dtype):
         if u1.dtype != np.float32 or u2.dtype != np.float32:
             u1 = u1.astype(np.float64, copy=False); u2 = u2.astype(np.float64, copy=False)
         u1 = np.ascontiguousarray(u1.reshape(-1, 2)); u2 = np.ascontiguousarray(u2.reshape(-1, 2))
+    else:
+        _check_device_array(u1, 2, "u1"); _check_device_array(u2, 2, "u2")
     if len(u1) != len(u2):
         raise ValueError("u1 and u2 must hold the same number of points")
-    in_dtype = np.dtype(str(u1.dtype).replace("torch.", ""))
-    if in_dtype != np.dtype(str(u2.dtype).replace("torch.", "")):
+    in_dtype = _np_dtype(u1)
+    if in_dtype != _np_dtype(u2):
         raise ValueError("u1 and u2 must have the same dtype")
     if np.dtype(compute_dtype) == np.float32 and (in_dtype != np.float32 or np.dtype(out_dtype) != np.float32):
         compute_dtype = np.float64          # FP32 arithmetic is only defined for float32 in/out
@@ -389,6 +419,7 @@ def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=
 
 def multiview_ls(us, Ps, valid=None, min_views=2, out_dtype=np.float64, x=None, status=None, stream=None):
     """us (m,n,2) host array or DeviceArray, Ps (m,3|4,4), valid (m,n) bool / uint8 or None -> x (n,3), status (n,) bool."""
+    us = _host_if_cpu_tensor(us); valid = _host_if_cpu_tensor(valid)
     dev = _is_device(us)
     if not dev:
         us = np.asarray(us)
@@ -397,6 +428,11 @@ def multiview_ls(us, Ps, valid=None, min_views=2, out_dtype=np.float64, x=None, 
         us = np.ascontiguousarray(us)
     if len(us.shape) != 3 or us.shape[2] != 2:
         raise ValueError("us must have shape (m, n, 2)")
+    if dev:
+        if hasattr(us, "is_contiguous") and not us.is_contiguous():
+            raise ValueError("us: device tensor must be contiguous")
+        if _np_dtype(us) not in _FLOAT_DTYPES:
+            raise ValueError("us: unsupported dtype %s" % us.dtype)
     m, n = int(us.shape[0]), int(us.shape[1])
     in_dtype = np.dtype(str(us.dtype).replace("torch.", ""))
     Pm = np.ascontiguousarray(np.stack([_P12(P) for P in Ps]).reshape(-1))
@@ -409,6 +445,8 @@ def multiview_ls(us, Ps, valid=None, min_views=2, out_dtype=np.float64, x=None, 
             valid = np.ascontiguousarray(np.asarray(valid).astype(np.uint8, copy=False))
         if tuple(valid.shape) != (m, n):
             raise ValueError("valid must have shape (m, n)")
+        if dev and ((hasattr(valid, "is_contiguous") and not valid.is_contiguous()) or _np_dtype(valid).itemsize != 1):
+            raise ValueError("valid: device mask must be a contiguous (m, n) array of 1-byte elements")
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
     check(lib().trgl_multiview_ls(_ptr(us), _ptr(valid) if valid is not None else None, _dp(Pm), m, _ptr(x), _ptr(status),
                                   n, int(min_views), mode_for(in_dtype, np.float64, out_dtype),
@@ -521,7 +559,17 @@ def pair_reproj(x, u1, P1, u2, P2, status, min_status=0, max_sq_err=np.inf, want
     """Two-view reprojection errors + good mask right after a solver call. Returns err1, err2, good, sums(4).
     sums_device (a 4-double device buffer, device inputs only): asynchronous variant -- the sums are finished inside
     the kernel and stay on the device, the call does not synchronise and returns sums_device in place of the host sums."""
+    x, u1, u2, status = (_host_if_cpu_tensor(a) for a in (x, u1, u2, status))
     dev = _is_device(x)
+    if dev:
+        if not (_is_device(u1) and _is_device(u2) and _is_device(status)):
+            raise ValueError("x, u1, u2 and status must all be host arrays or all be device buffers")
+        _check_device_array(x, 3, "x"); _check_device_array(u1, 2, "u1"); _check_device_array(u2, 2, "u2")
+        _check_device_array(status, 0, "status", None)
+        if not (len(x) == len(u1) == len(u2) == len(status)):
+            raise ValueError("x, u1, u2 and status must hold the same number of points")
+        if _np_dtype(status).itemsize not in (1, 4):
+            raise ValueError("status: device buffer must be bool / uint8 or int32")
     if not dev:
         x = np.asarray(x); u1 = np.asarray(u1); u2 = np.asarray(u2); status = np.asarray(status)
         if x.dtype != np.float32:

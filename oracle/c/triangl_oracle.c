@@ -12,7 +12,7 @@
  *                                                solvePoly(100 iterations), cost scan over real parts; then linear_eigen)
  * Used by tests/ (cross-check against the NumPy oracle and cv2) and by bench.py's cpu_baseline / --impl reference.
  * Parity pinning: agrees with oracle/triangulation_oracle.py, which is pinned to the reference's golden .mat cells
- * and exec'd-reference fixtures (tests/test_oracle_c.py).
+ * and exec'd-reference fixtures (tests/test_host_and_abi.py::test_c_oracle_matches_numpy_oracle, tests/test_oracle_golden.py).
  */
 #include <float.h>
 #include <math.h>

@@ -26,6 +26,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "multiple-quadrotor-slam_b200"))
+sys.path.insert(0, os.path.join(ROOT, "harness"))
 
 from oracle.ref_exec import REFERENCE_ROOT, load_reference_triangulation   # noqa: E402
 import synthetic_rig as rig                                                  # noqa: E402

@@ -5,7 +5,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "multiple-quadrotor-slam_b200")
-for p in (ROOT, PKG, os.path.dirname(os.path.abspath(__file__))):
+for p in (ROOT, PKG, os.path.join(ROOT, "harness"), os.path.dirname(os.path.abspath(__file__))):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -17,3 +17,24 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def _have_cuda_device():
+    """GPU tests are skipped on a box without a GPU; on a box WITH one they run -- and fail loudly if the library is
+    missing or broken (the product has no CPU fallback)."""
+    if any(os.path.exists("/dev/nvidia%d" % i) for i in range(16)):
+        return True
+    try:
+        import triangl_cuda
+        return triangl_cuda.device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_cuda_device():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container (run with gpurun / on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

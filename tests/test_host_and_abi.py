@@ -191,7 +191,7 @@ def _gloo_worker(rank, world, port, tmp):
     import sys
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for p in (root, os.path.join(root, "multiple-quadrotor-slam_b200")):
+    for p in (root, os.path.join(root, "multiple-quadrotor-slam_b200"), os.path.join(root, "harness")):
         sys.path.insert(0, p)
     import numpy as np
     import torch.distributed as dist
@@ -303,3 +303,5 @@ def test_bench_reference_arm_under_torchrun_only_rank0_prints():
                           "--warmup", "1", "--cpu-sample", "20000"])
     js = [ln for ln in lines if ln.startswith("{")]
     assert len(js) == 1 and json.loads(js[0])["n_gpus"] == 2
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every core of the box
+    assert json.loads(js[0])["cpu_baseline"]["cores"] == max(1, len(os.sched_getaffinity(0)))

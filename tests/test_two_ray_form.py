@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multiple-quadrotor-slam_b200"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multiple-quadrotor-slam_b200")); sys.path.insert(0, os.path.join(ROOT, "harness"))
 import synthetic_rig as rig                                     # noqa: E402
 from oracle import triangulation_oracle as orc                  # noqa: E402
 from oracle import two_ray_form as trf                           # noqa: E402
