@@ -174,6 +174,24 @@ def make_correspondences(n, rig="translating", sigma=0.8, discretized=False, see
     return out + (cam1, cam2) if return_cameras else out
 
 
+BENCH_BASE_POINTS = 2_000_000
+
+
+def bench_batch(n, rig="rotating", rank=0, sigma=0.8, base_points=BENCH_BASE_POINTS):
+    """
+    The batch bench.py times (and tests/test_gpu_parity.py::test_bench_input_parity checks against the oracle): one seeded
+    batch of min(n, base_points) correspondences (seed RSEED + rank), tiled to n -- values repeat, which does not change
+    the per-point cost, and the arrays (32 B/point) exceed the 126 MB L2 from 4 M points on.
+    Returns u1 (n,2), P1, u2 (n,2), P2 and the number of distinct points.
+    """
+    base_n = min(n, base_points)
+    u1b, P1, u2b, P2, _ = make_correspondences(base_n, rig, sigma=sigma, seed=RSEED + rank)
+    reps = -(-n // base_n) if base_n else 1
+    if reps == 1:
+        return u1b, P1, u2b, P2, base_n
+    return np.tile(u1b, (reps, 1))[:n], P1, np.tile(u2b, (reps, 1))[:n], P2, base_n
+
+
 def circle_cameras(num_cams=8, offset=40., max_angle=asin(1.0) * 0.5):
     """num_cams poses on the trajectory-4/5 circle facing the cloud (multi-quadrotor scene, 3x4 each)."""
     Ps = []

@@ -53,7 +53,7 @@ extern "C" {
 #define TRGL_VERSION 105
 
 enum { TRGL_F64 = 0, TRGL_F32IO = 1, TRGL_F32 = 2, TRGL_F64_OUT32 = 3, TRGL_F32_OUT64 = 4 };
-enum { TRGL_MEM_HOST = 0, TRGL_MEM_DEVICE = 1 };
+enum { TRGL_MEM_HOST = 0, TRGL_MEM_DEVICE = 1, TRGL_MEM_DEVICE_IN = 2 };
 enum { TRGL_ITER_C = 0, TRGL_ITER_PY = 1 };          /* iterative_LS control flow: triangulation.c vs triangulation.py */
 
 enum {
@@ -226,6 +226,19 @@ int trgl_eval_errors_2d(const void* proj, const double* exact, double* errors, d
  * n == 0.  median: host double.  Synchronises the stream. */
 int trgl_median(const double* values, int64_t n, int mem, double* median, void* stream);
 
+/* ---- upload once, solve many (host results from device-resident observations) ---- */
+
+/* The reference's callers run several solvers on the SAME (u1, u2) (the comparison harness:
+ * Work/triangulation_comparison/triangulation_comparison.py:466-469 loops the four methods over one noisy observation set;
+ * slam2.py:553-584 re-triangulates a subset).  In plain host mode every call uploads u1 / u2 again.  Two pieces avoid it:
+ *   trgl_set_input_retention(d_u1, d_u2): the NEXT host-mode solver call of this thread (mem = TRGL_MEM_HOST) uploads its
+ *     u1 / u2 chunk by chunk into these caller-owned device buffers (n x 2 elements of the input dtype each) instead of
+ *     its pipeline scratch -- same overlap of H2D, kernel and D2H -- and leaves them there;
+ *   mem = TRGL_MEM_DEVICE_IN on any solver entry: u1 / u2 are device pointers (e.g. the retained buffers), x / status
+ *     (and the other outputs) are HOST buffers; kernels and D2H copies are pipelined per chunk, nothing is uploaded.
+ * Four solvers on 10 M float64 correspondences then move 0.32 GB host-to-device instead of 1.28 GB. */
+int trgl_set_input_retention(void* u1_device, void* u2_device);
+
 /* ---- multi-GPU: the result gather fused into the solver's stores ---- */
 
 /* One process per GPU.  Every rank allocates the gathered arrays x_all (N_total,3) and status_all (N_total,) with
@@ -234,13 +247,19 @@ int trgl_median(const double* values, int64_t n, int mem, double* median, void* 
  * is enabled by the mapping).  Before a solver call on its shard [lo, lo+n) a rank then passes, for each peer,
  * the addresses of that shard inside the peer's arrays:
  *     x_mirrors[r] = peer_r.x_all + 3*lo (elements of x's dtype),  status_mirrors[r] = peer_r.status_all + lo
- * with trgl_set_result_mirrors (at most 7 peers).  The table applies to the NEXT device-mode solver call of the calling
+ * with trgl_set_result_mirrors (at most 8 entries: 7 peers + optionally a second local copy).  The table applies to the NEXT device-mode solver call of the calling
  * host thread (trgl_linear_ls / iterative_ls / linear_eigen / polynomial and their _px twins) and is cleared by it.
  * That kernel repeats every store of x and status to all mirrors, so when it has finished on every rank (stream
  * synchronise + a barrier of the caller's choice) each rank holds the complete result -- no all-gather pass, no second
  * read of x from HBM, and the NVLink traffic overlaps the solve.  The reference has no multi-process code (SURVEY.md
  * F10); this replaces the ncclAllGather of SURVEY.md 8e. */
 int trgl_set_result_mirrors(void* const* x_mirrors, void* const* status_mirrors, int count);
+/* Same, but the mirrors hold FLOAT32 rows whatever the dtype of the rank's own x (x_mirrors[r] = peer_r.x_all + 3*lo in
+ * float32 elements): the gathered map in the dtype the reference's SLAM keeps it in
+ * (Work/SLAM/application/own/slam2.py:19, set_triangl_output_dtype(np.float32)) at 12 + 1|4 instead of 24 + 1|4 bytes
+ * per point over NVLink -- the gather is link-bound.  Each mirror value is the float64 result
+ * rounded once, i.e. exactly what `.astype(np.float32)` (triangulation.py:242-243) makes of it. */
+int trgl_set_result_mirrors_f32(void* const* x_mirrors, void* const* status_mirrors, int count);
 int trgl_ipc_export(void* device_ptr, void* handle64);            /* device_ptr from trgl_device_alloc */
 int trgl_ipc_import(const void* handle64, void** device_ptr);     /* in ANOTHER process than the exporter */
 int trgl_ipc_close(void* device_ptr);

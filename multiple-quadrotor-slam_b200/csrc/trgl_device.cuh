@@ -126,11 +126,20 @@ struct PreUndistort {
 // slot this rank's shard occupies in that peer's gathered (N_total,3) result / (N_total,) status array.  Every store of
 // x and status is repeated to all mirrors, so when the kernel ends the shard is already in place on every rank: no
 // separate all-gather pass re-reads x from HBM, and the NVLink traffic overlaps the solve tile by tile.
-constexpr int kMaxMirrors = 7;
+constexpr int kMaxMirrors = 8;            // 7 peers + the rank's own narrowed (float32) copy
+// x_f32: the mirrors hold FLOAT32 rows whatever the local output type (the gathered map in the reference's SLAM
+// convention, slam2.py:19 `set_triangl_output_dtype(np.float32)`): 12 instead of 24 bytes per point over NVLink, the
+// rank's own x stays float64.
 struct Mirrors {
     static constexpr bool kActive = true;
-    int count; int pad_; void* x[kMaxMirrors]; void* status[kMaxMirrors];
+    int count; int x_f32; void* x[kMaxMirrors]; void* status[kMaxMirrors];
 };
+// Element `idx` of mirror r's x array (index in elements of the MIRROR's dtype, counted from the shard's slot).
+template <typename TO>
+__device__ __forceinline__ void mirror_put(const Mirrors& mir, int r, int64_t idx, TO v) {
+    if (sizeof(TO) == 8 && mir.x_f32) static_cast<float*>(mir.x[r])[idx] = static_cast<float>(v);
+    else static_cast<TO*>(mir.x[r])[idx] = v;
+}
 // Compile-time "no mirrors" for the HBM-bound linear_LS hot path: even an empty run-time loop in the store path keeps
 // the compiler from interleaving the four points of a thread (measured: 0.85 -> 0.80 of the copy peak).
 struct NoMirrors { static constexpr bool kActive = false; };
@@ -165,11 +174,10 @@ __device__ __forceinline__ void store_x_warp(TO* __restrict__ xout, int64_t warp
     }
     if constexpr (M::kActive) {
         for (int r = 0; r < mir.count; ++r) {       // same three contiguous rows into every peer's gather buffer
-            TO* __restrict__ peer = static_cast<TO*>(mir.x[r]) + warp_base * 3;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int idx = k * 32 + lane;
-                if (idx < cnt) peer[idx] = stage[idx];
+                if (idx < cnt) mirror_put<TO>(mir, r, warp_base * 3 + idx, stage[idx]);
             }
         }
     }

@@ -504,7 +504,7 @@ __device__ __forceinline__ void mirror_slice(const TO* __restrict__ x, const int
     const int cnt = (n - base) >= 32 ? 32 : static_cast<int>(n - base);
     for (int idx = lane; idx < cnt * 3; idx += 32) {
         const TO v = __ldcg(x + base * 3 + idx);
-        for (int r = 0; r < mir.count; ++r) static_cast<TO*>(mir.x[r])[base * 3 + idx] = v;
+        for (int r = 0; r < mir.count; ++r) mirror_put<TO>(mir, r, base * 3 + idx, v);
     }
     if (lane < cnt) {
         const int32_t v = __ldcg(status + base + lane);
@@ -652,7 +652,7 @@ k_iterative_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const 
         status[i] = st;
         for (int r = 0; r < mir.count; ++r) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) static_cast<TO*>(mir.x[r])[3 * i + q] = static_cast<TO>(xs[q]);
+            for (int q = 0; q < 3; ++q) mirror_put<TO>(mir, r, 3 * i + q, static_cast<TO>(xs[q]));
             static_cast<int32_t*>(mir.status[r])[i] = st;
         }
         fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, st, acc);
@@ -710,7 +710,7 @@ k_linear_ls_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const 
             for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
             for (int r = 0; r < mir.count; ++r) {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) static_cast<TO*>(mir.x[r])[3 * i + q] = static_cast<TO>(xs[q]);
+                for (int q = 0; q < 3; ++q) mirror_put<TO>(mir, r, 3 * i + q, static_cast<TO>(xs[q]));
             }
             fused_eval_point<EVAL, TO, TC>(ev, true, i, in[p][0], in[p][1], in[p][2], in[p][3], xs, 1, acc);
         }
@@ -942,7 +942,7 @@ k_linear_eigen_general(const TI* __restrict__ u1, const TI* __restrict__ u2, con
         for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
         for (int m = 0; m < mir.count; ++m) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) static_cast<TO*>(mir.x[m])[3 * i + q] = static_cast<TO>(xs[q]);
+            for (int q = 0; q < 3; ++q) mirror_put<TO>(mir, m, 3 * i + q, static_cast<TO>(xs[q]));
         }
         store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
         fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);
@@ -1059,7 +1059,7 @@ k_polynomial_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const
         for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
         for (int m = 0; m < mir.count; ++m) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) static_cast<TO*>(mir.x[m])[3 * i + q] = static_cast<TO>(xs[q]);
+            for (int q = 0; q < 3; ++q) mirror_put<TO>(mir, m, 3 * i + q, static_cast<TO>(xs[q]));
         }
         store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
         fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);

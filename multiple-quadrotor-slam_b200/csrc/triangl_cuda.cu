@@ -34,6 +34,12 @@ Mirrors take_mirrors() {
 }
 const Mirrors kNoMirrors = {0, 0, {nullptr}, {nullptr}};
 
+// Input retention requested for the NEXT host-mode solver call of this host thread (trgl_set_input_retention): the call
+// uploads u1 / u2 into these device buffers instead of its pipeline scratch, so later calls can read them in place
+// (TRGL_MEM_DEVICE_IN) -- "upload once, solve many".
+struct PendingRetain { void* u1; void* u2; };
+thread_local PendingRetain g_next_retain = {nullptr, nullptr};
+
 // Fused evaluation requested for the NEXT device-mode solver call of this host thread (trgl_set_fused_eval).
 struct PendingEval { bool armed; int min_status; double max_sq_err; void* err1; void* err2; uint8_t* good; double* sums; };
 thread_local PendingEval g_next_eval = {false, 0, 0.0, nullptr, nullptr, nullptr, nullptr};
@@ -520,7 +526,7 @@ int scratch_for(cudaStream_t s, Scratch& out, int64_t deferred_points) {
 // Result mirrors / fused evaluation apply to ONE solver call: whatever that call's outcome (argument error, n == 0,
 // host mode), the request is gone when it returns.
 struct PendingClear {
-    ~PendingClear() { g_next_mirrors.count = 0; g_next_eval.armed = false; }
+    ~PendingClear() { g_next_mirrors.count = 0; g_next_eval.armed = false; g_next_retain = {nullptr, nullptr}; }
 };
 
 // Consume the pending fused-evaluation request: cameras of this call, reduction scratch of this stream.
@@ -560,7 +566,15 @@ int ensure_slot(Slot& sl, size_t bytes) {
 
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
-struct HostArray { const void* in; void* out; size_t bytes_per_point; };
+// One array of a host-mode call: `in` is copied to the device before the launch, `out` is filled from the device after
+// it.  `dev` (optional): the array lives in this caller-owned device buffer instead of the pipeline scratch -- with `in`
+// it is uploaded there (input retention), without `in` it is already resident (TRGL_MEM_DEVICE_IN).
+struct HostArray { const void* in; void* out; size_t bytes_per_point; void* dev = nullptr; };
+// u1 / u2 of a solver call in host mode, input-retention mode or device-in mode.
+inline HostArray input_array(const void* u, size_t bytes_per_point, int mem, void* retain) {
+    if (mem == TRGL_MEM_DEVICE_IN) return HostArray{nullptr, nullptr, bytes_per_point, const_cast<void*>(u)};
+    return HostArray{u, nullptr, bytes_per_point, retain};
+}
 constexpr int kMaxHostArrays = 2 * kMaxViews + 2;     // multi-view: m observation arrays + m masks + x + status
 
 // Small batches (the SLAM keyframe sizes, slam2.py:1080-1082: a few hundred points): latency is all API calls, so the
@@ -587,7 +601,9 @@ int ensure_zero_copy(size_t bytes) {
 template <typename Launch>
 int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
     std::lock_guard<std::mutex> lock(g_pipe_mutex);
-    if (n <= kZeroCopyMax) {
+    bool caller_device_arrays = false;
+    for (int a = 0; a < narrays; ++a) caller_device_arrays = caller_device_arrays || arrays[a].dev != nullptr;
+    if (n <= kZeroCopyMax && !caller_device_arrays) {
         size_t total = 0;
         for (int a = 0; a < narrays; ++a) total += align256(arrays[a].bytes_per_point * n);
         int rc = ensure_zero_copy(total);
@@ -623,7 +639,7 @@ int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
         void* dptr[kMaxHostArrays];
         size_t pos = 0;
         for (int a = 0; a < narrays && rc == TRGL_OK; ++a) {
-            dptr[a] = sl.buf + pos;
+            dptr[a] = arrays[a].dev ? static_cast<char*>(arrays[a].dev) + off * arrays[a].bytes_per_point : sl.buf + pos;
             pos += align256(arrays[a].bytes_per_point * chunk);
             if (arrays[a].in) {
                 const cudaError_t e = cudaMemcpyAsync(dptr[a], static_cast<const char*>(arrays[a].in) + off * arrays[a].bytes_per_point,
@@ -651,11 +667,20 @@ int check_common(const void* u1, const void* u2, const double* P1, const double*
     ModeInfo mi;
     if (n < 0) return fail(TRGL_E_BADARG, "negative point count");
     if (!mode_info(mode, mi)) return fail(TRGL_E_BADARG, "unknown precision mode");
-    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE && mem != TRGL_MEM_DEVICE_IN) return fail(TRGL_E_BADARG, "unknown memory space");
     if (!P1 || !P2) return fail(TRGL_E_BADARG, "camera matrix pointer is NULL");
     if (n > 0 && (!u1 || !u2 || !x || !status)) return fail(TRGL_E_BADARG, "NULL array pointer with n > 0");
+    if (g_next_retain.u1 && mem != TRGL_MEM_HOST) {
+        g_next_retain = {nullptr, nullptr};
+        return fail(TRGL_E_BADARG, "input retention applies to host-mode calls (TRGL_MEM_HOST)");
+    }
+    if (g_next_retain.u1 && n > 0 &&
+        ((reinterpret_cast<uintptr_t>(g_next_retain.u1) | reinterpret_cast<uintptr_t>(g_next_retain.u2)) & static_cast<uintptr_t>(2 * mi.in_bytes - 1))) {
+        g_next_retain = {nullptr, nullptr};
+        return fail(TRGL_E_BADARG, "retention buffers must be aligned to one (x,y) pair");
+    }
     // the kernels read one (x,y) pair per vector load / cp.async: device buffers must be aligned to a pair
-    if (mem == TRGL_MEM_DEVICE && n > 0 &&
+    if (mem != TRGL_MEM_HOST && n > 0 &&
         ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & static_cast<uintptr_t>(2 * mi.in_bytes - 1)))
         return fail(TRGL_E_BADARG, "device u1/u2 must be aligned to one (x,y) pair (16 bytes float64, 8 bytes float32)");
     if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
@@ -849,21 +874,33 @@ int trgl_event_elapsed_ms(void* start, void* stop, float* ms) {
 }
 
 // ---- result mirrors / CUDA IPC (multi-GPU gather fused into the solver stores) ----------------------------------------
-int trgl_set_result_mirrors(void* const* x_mirrors, void* const* status_mirrors, int count) {
-    if (count < 0 || count > kMaxMirrors) return fail(TRGL_E_BADARG, "at most 7 result mirrors");
+static int set_mirrors(void* const* x_mirrors, void* const* status_mirrors, int count, int x_f32) {
+    if (count < 0 || count > kMaxMirrors) return fail(TRGL_E_BADARG, "at most 8 result mirrors");
     if (count > 0 && (!x_mirrors || !status_mirrors)) return fail(TRGL_E_BADARG, "NULL mirror table");
     g_next_mirrors.count = count;
+    g_next_mirrors.x_f32 = x_f32 ? 1 : 0;
     for (int r = 0; r < count; ++r) {
         if (!x_mirrors[r] || !status_mirrors[r]) { g_next_mirrors.count = 0; return fail(TRGL_E_BADARG, "NULL mirror pointer"); }
         g_next_mirrors.x[r] = x_mirrors[r]; g_next_mirrors.status[r] = status_mirrors[r];
     }
     return TRGL_OK;
 }
+int trgl_set_result_mirrors(void* const* x_mirrors, void* const* status_mirrors, int count) {
+    return set_mirrors(x_mirrors, status_mirrors, count, 0);
+}
+int trgl_set_result_mirrors_f32(void* const* x_mirrors, void* const* status_mirrors, int count) {
+    return set_mirrors(x_mirrors, status_mirrors, count, 1);
+}
 int trgl_set_fused_eval(int min_status, double max_sq_err, void* err1, void* err2, uint8_t* good, double* sums_device) {
     if (!sums_device) return fail(TRGL_E_BADARG, "sums_device is NULL");
     g_next_eval.armed = true;
     g_next_eval.min_status = min_status; g_next_eval.max_sq_err = max_sq_err;
     g_next_eval.err1 = err1; g_next_eval.err2 = err2; g_next_eval.good = good; g_next_eval.sums = sums_device;
+    return TRGL_OK;
+}
+int trgl_set_input_retention(void* u1_device, void* u2_device) {
+    if (!u1_device || !u2_device) { g_next_retain = {nullptr, nullptr}; return fail(TRGL_E_BADARG, "NULL retention buffer"); }
+    g_next_retain = {u1_device, u2_device};
     return TRGL_OK;
 }
 int trgl_ipc_export(void* device_ptr, void* handle64) {
@@ -920,7 +957,8 @@ static int impl_linear_ls(const void* u1, const void* u2, const double* P1, cons
         return launch_linear_ls(u1, u2, P1, P2, x, status, n, mode, static_cast<cudaStream_t>(stream), pre, take_mirrors(), evp);
     }
     ModeInfo mi; mode_info(mode, mi);
-    HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
+    HostArray arr[4] = {input_array(u1, size_t(2 * mi.in_bytes), mem, g_next_retain.u1),
+                        input_array(u2, size_t(2 * mi.in_bytes), mem, g_next_retain.u2),
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
     return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
         return launch_linear_ls(d[0], d[1], P1, P2, d[2], static_cast<uint8_t*>(d[3]), m, mode, s, pre);
@@ -1032,7 +1070,8 @@ static int impl_iterative_ls(const void* u1, const void* u2, const double* P1, c
                                    take_mirrors(), evp);
     }
     ModeInfo mi; mode_info(mode, mi);
-    HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
+    HostArray arr[4] = {input_array(u1, size_t(2 * mi.in_bytes), mem, g_next_retain.u1),
+                        input_array(u2, size_t(2 * mi.in_bytes), mem, g_next_retain.u2),
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 4}};
     return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
         return launch_iterative_ls(d[0], d[1], P1, P2, d[2], static_cast<int32_t*>(d[3]), m, tolerance, semantics, mode, s, pre);
@@ -1067,7 +1106,8 @@ static int impl_linear_eigen(const void* u1, const void* u2, const double* P1, c
                                    take_mirrors(), evp);
     }
     ModeInfo mi; mode_info(mode, mi);
-    HostArray arr[4] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
+    HostArray arr[4] = {input_array(u1, size_t(2 * mi.in_bytes), mem, g_next_retain.u1),
+                        input_array(u2, size_t(2 * mi.in_bytes), mem, g_next_retain.u2),
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1}};
     return host_pipeline(arr, 4, n, [&](void** d, int64_t m, cudaStream_t s, int) {
         return launch_linear_eigen(d[0], d[1], P1, P2, d[2], static_cast<uint8_t*>(d[3]), m, max_coordinate_value, rows, mode, s, pre);
@@ -1127,7 +1167,8 @@ static int impl_polynomial_F(const void* u1, const void* u2, const double* P1, c
     // clear must have completed before any slot's kernel can set a flag
     CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * 2 * kSlots));
     CK(cudaStreamSynchronize(nullptr));
-    HostArray arr[6] = {{u1, nullptr, size_t(2 * mi.in_bytes)}, {u2, nullptr, size_t(2 * mi.in_bytes)},
+    HostArray arr[6] = {input_array(u1, size_t(2 * mi.in_bytes), mem, g_next_retain.u1),
+                        input_array(u2, size_t(2 * mi.in_bytes), mem, g_next_retain.u2),
                         {nullptr, x, size_t(3 * mi.out_bytes)}, {nullptr, status, 1},
                         {nullptr, u1_corr, size_t(2 * mi.in_bytes)}, {nullptr, u2_corr, size_t(2 * mi.in_bytes)}};
     rc = host_pipeline(arr, 6, n, [&](void** d, int64_t m, cudaStream_t s, int slot) {

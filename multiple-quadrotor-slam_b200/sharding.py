@@ -83,41 +83,74 @@ def gather_shards(x_shard, n_total, device=None):
 
 class PeerGather:
     """
-    The result gather fused into the solver kernels (include/triangl_cuda.h "result mirrors"): every rank owns full-size
-    `x_all (n_total,3)` / `status_all (n_total,)` device arrays, maps its peers' copies through CUDA IPC (handles are
-    exchanged with `all_gather_object` of the default process group -- NCCL or gloo, plumbing only), and each solver call
-    on the local shard stores straight into all of them over NVLink.  After `finish()` every rank holds the full result.
+    The result gather fused into the solver kernels (include/triangl_cuda.h "result mirrors"): the ranks that need the
+    map own full-size `x_all (n_total,3)` / `status_all (n_total,)` device arrays, the others map them through CUDA IPC
+    (handles are exchanged with `all_gather_object` of the default process group -- NCCL or gloo, plumbing only), and each
+    solver call on the local shard stores straight into all of them over NVLink.  After `finish()` the gathered arrays are
+    complete.
+
+    gather_dtype : dtype of the gathered x rows.  None = x_dtype.  np.float32 with x_dtype float64 = the map in the
+                   reference's SLAM convention (slam2.py:19 sets the output dtype to float32): the rank's own shard stays
+                   float64 in `x_local`, the gathered rows travel and are stored as float32 (12 instead of 24 B/point over
+                   the links, which bound the gather).
+    root         : None = every rank receives the map (all-gather); r = only rank r does (gather): the other ranks
+                   allocate no gathered arrays and ship their shard once instead of world-1 times.
     """
 
-    def __init__(self, n_total, x_dtype=np.float64, status_dtype=np.uint8):
+    def __init__(self, n_total, x_dtype=np.float64, status_dtype=np.uint8, gather_dtype=None, root=None):
         import triangl_cuda as tc
         dist = _dist()
         self.tc = tc
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        if self.world - 1 > 7:
-            raise ValueError("at most 8 ranks (7 peers)")
-        self.n_total = n_total
+        if self.world > 8:
+            raise ValueError("at most 8 ranks")
+        self.n_total, self.root = n_total, root
         self.lo, self.hi = shard_range(n_total, self.rank, self.world)
-        self.x_all = tc.DeviceArray((n_total, 3), x_dtype)
-        self.status_all = tc.DeviceArray((n_total,), status_dtype)
-        mine = (tc.ipc_export(self.x_all), tc.ipc_export(self.status_all))
+        self.x_dtype = np.dtype(x_dtype)
+        self.gather_dtype = np.dtype(gather_dtype) if gather_dtype is not None else self.x_dtype
+        if self.gather_dtype != self.x_dtype and not (self.gather_dtype == np.float32 and self.x_dtype == np.float64):
+            raise ValueError("gather_dtype must equal x_dtype, or be float32 for float64 results")
+        self.narrow = self.gather_dtype != self.x_dtype
+        self.owner = root is None or root == self.rank
+        self.x_all = tc.DeviceArray((n_total, 3), self.gather_dtype) if self.owner else None
+        self.status_all = tc.DeviceArray((n_total,), status_dtype) if self.owner else None
+        n = self.hi - self.lo
+        # narrowed gather: the rank's own full-precision result lives apart from the float32 map
+        self.x_local = tc.DeviceArray((n, 3), self.x_dtype) if (self.narrow or not self.owner) else None
+        self.status_local = tc.DeviceArray((n,), status_dtype) if not self.owner else None
+        mine = (tc.ipc_export(self.x_all), tc.ipc_export(self.status_all)) if self.owner else None
         handles = [None] * self.world
         dist.all_gather_object(handles, mine)
         self.peers = []
-        for r, (hx, hs) in enumerate(handles):
-            if r != self.rank:
-                self.peers.append((tc.ipc_import(hx), tc.ipc_import(hs)))
-        self.xb = 3 * np.dtype(x_dtype).itemsize
+        for r, h in enumerate(handles):
+            if r != self.rank and h is not None:
+                self.peers.append((tc.ipc_import(h[0]), tc.ipc_import(h[1])))
+        self.xb = 3 * self.gather_dtype.itemsize
         self.sb = np.dtype(status_dtype).itemsize
 
     def shard_outputs(self):
-        """(x, status) views of this rank's shard inside its own gathered arrays: pass them as x= / status=."""
+        """(x, status) buffers of this rank's shard: pass them as x= / status= of the solver call."""
         n = self.hi - self.lo
-        return self.x_all.view(3 * self.lo, (n, 3)), self.status_all.view(self.lo, (n,))
+        x = self.x_local if self.x_local is not None else self.x_all.view(3 * self.lo, (n, 3))
+        st = self.status_local if self.status_local is not None else self.status_all.view(self.lo, (n,))
+        return x, st
 
-    def arm(self):
-        """Attach the peers' shard addresses to the next device-mode solver call of this thread."""
-        self.tc.set_result_mirrors([(px + self.lo * self.xb, ps + self.lo * self.sb) for (px, ps) in self.peers])
+    def mirror_table(self, sub=0):
+        at = self.lo + sub
+        table = [(px + at * self.xb, ps + at * self.sb) for (px, ps) in self.peers]
+        if self.narrow and self.owner:
+            # this rank's own float32 rows are one more "mirror" (in local HBM); its status already lands in status_all
+            table.append((self.x_all.ptr + at * self.xb, self.status_all.ptr + at * self.sb))
+        return table
+
+    def arm(self, sub=0):
+        """Attach the shard addresses inside the gathered arrays to the next device-mode solver call of this thread.
+        sub: the call solves the piece of the shard that starts `sub` points into it (one call per camera-pair segment)."""
+        self.tc.set_result_mirrors(self.mirror_table(sub), x_f32=self.narrow)
+
+    def egress_bytes_per_point(self):
+        """Bytes this rank ships over NVLink per point of its shard."""
+        return len(self.peers) * (self.xb + self.sb)
 
     def finish(self):
         """All ranks' kernels have completed: the gathered arrays are valid everywhere."""

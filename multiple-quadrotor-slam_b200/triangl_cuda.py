@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRGL_CUDA_LIB") or os.path.join(_HERE, "libtriangl_cuda.so")
 
 F64, F32IO, F32, F64_OUT32, F32_OUT64 = 0, 1, 2, 3, 4
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_DEVICE_IN = 0, 1, 2
 PINNED_OUTPUT_MIN_POINTS = 1 << 16      # host-mode outputs at least this long are allocated page-locked
 ITER_C, ITER_PY = 0, 1
 
@@ -34,6 +34,7 @@ EXPORTS = [
     "trgl_set_points_per_thread", "trgl_set_stream_variant", "trgl_set_two_ray", "trgl_multiview_ls", "trgl_set_deferred_capacity",
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
     "trgl_set_fused_eval", "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
+    "trgl_set_result_mirrors_f32", "trgl_set_input_retention",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -89,6 +90,8 @@ def lib():
     L.trgl_pair_reproj_async.argtypes = [vp, vp, vp, dp, dp, vp, cint, cint, dbl, vp, vp, vp, vp, i64, cint, vp]
     L.trgl_set_fused_eval.argtypes = [cint, dbl, vp, vp, vp, vp]
     L.trgl_set_result_mirrors.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), cint]
+    L.trgl_set_result_mirrors_f32.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), cint]
+    L.trgl_set_input_retention.argtypes = [vp, vp]
     L.trgl_ipc_export.argtypes = [vp, vp]
     L.trgl_ipc_import.argtypes = [vp, ctypes.POINTER(vp)]
     L.trgl_ipc_close.argtypes = [vp]
@@ -286,6 +289,49 @@ def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+class _ResidentPair:
+    def __init__(self, u1, u2):
+        u1 = np.asarray(_host_if_cpu_tensor(u1)); u2 = np.asarray(_host_if_cpu_tensor(u2))
+        if u1.dtype != np.float32 or u2.dtype != np.float32:
+            u1 = u1.astype(np.float64, copy=False); u2 = u2.astype(np.float64, copy=False)
+        self.host = (np.ascontiguousarray(u1.reshape(-1, 2)), np.ascontiguousarray(u2.reshape(-1, 2)))
+        if len(self.host[0]) != len(self.host[1]):
+            raise ValueError("u1 and u2 must hold the same number of points")
+        self.dev = (DeviceArray(self.host[0].shape, self.host[0].dtype), DeviceArray(self.host[1].shape, self.host[1].dtype))
+        self.uploaded = False
+
+
+class ResidentPoints:
+    """
+    One of the two observation arrays of an "upload once, solve many" pair (see `resident`).  Passed as u1 / u2 to any
+    solver, it behaves like the host array it was made from -- results come back as host arrays -- but the first solver
+    call leaves the uploaded observations in HBM (trgl_set_input_retention) and every later call reads them there
+    (TRGL_MEM_DEVICE_IN) instead of uploading them again.
+    """
+
+    def __init__(self, pair, which):
+        self._pair, self._which = pair, which
+        self.shape, self.dtype = pair.host[which].shape, pair.host[which].dtype
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._pair.host[self._which]
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    @property
+    def device(self):
+        """The device-resident copy (valid after the first solver call)."""
+        return self._pair.dev[self._which]
+
+
+def resident(u1, u2):
+    """(u1, u2) host arrays -> a pair of ResidentPoints handles for the four solvers' u1 / u2 arguments."""
+    pair = _ResidentPair(u1, u2)
+    return ResidentPoints(pair, 0), ResidentPoints(pair, 1)
+
+
 def _P12(P):
     """Rows 0..2 of a 3x4 / 4x4 camera matrix as 12 contiguous doubles (triangulation.c:24-25 reads P[4*k+l])."""
     P = np.asarray(P)
@@ -308,9 +354,10 @@ def mode_for(in_dtype, compute_dtype, out_dtype):
     return _MODE[key]
 
 
-def _prep(u1, u2, compute_dtype, out_dtype):
+def _prep(u1, u2, compute_dtype, out_dtype, allow_resident=True):
     """Input coercion of the reference wrapper (triangulation_c/__init__.py:32-39), without the forced up-cast:
-    float32 inputs stay float32 in HBM and are widened in registers."""
+    float32 inputs stay float32 in HBM and are widened in registers.
+    Returns u1, u2, mem (MEM_HOST / MEM_DEVICE / MEM_DEVICE_IN), n, precision mode, resident pair to commit (or None)."""
     if type(u1) is np.ndarray and type(u2) is np.ndarray and u1.dtype == u2.dtype and u1.ndim == 2 and u2.ndim == 2 \
             and u1.shape[1] == 2 and u1.shape == u2.shape and u1.flags.c_contiguous and u2.flags.c_contiguous \
             and u1.dtype in _FLOAT_DTYPES:
@@ -318,18 +365,35 @@ def _prep(u1, u2, compute_dtype, out_dtype):
         in_dtype = u1.dtype
         if np.dtype(compute_dtype) == np.float32 and (in_dtype != np.float32 or np.dtype(out_dtype) != np.float32):
             compute_dtype = np.float64
-        return u1, u2, False, len(u1), mode_for(in_dtype, compute_dtype, out_dtype)
-    u1 = _host_if_cpu_tensor(u1); u2 = _host_if_cpu_tensor(u2)
-    dev = _is_device(u1)
-    if dev != _is_device(u2):
-        raise ValueError("u1 and u2 must both be host arrays or both be device buffers")
-    if not dev:
-        u1 = np.asarray(u1); u2 = np.asarray(u2)
-        if u1.dtype != np.float32 or u2.dtype != np.float32:
-            u1 = u1.astype(np.float64, copy=False); u2 = u2.astype(np.float64, copy=False)
-        u1 = np.ascontiguousarray(u1.reshape(-1, 2)); u2 = np.ascontiguousarray(u2.reshape(-1, 2))
+        return u1, u2, MEM_HOST, len(u1), mode_for(in_dtype, compute_dtype, out_dtype), None
+    commit = None
+    mem = None
+    if isinstance(u1, ResidentPoints) or isinstance(u2, ResidentPoints):
+        if not (isinstance(u1, ResidentPoints) and isinstance(u2, ResidentPoints) and u1._pair is u2._pair
+                and (u1._which, u2._which) == (0, 1)):
+            raise ValueError("resident handles must be passed as the (u1, u2) pair `resident` returned")
+        pair = u1._pair
+        if pair.uploaded:
+            u1, u2 = pair.dev
+            mem = MEM_DEVICE_IN if allow_resident else MEM_DEVICE
+        else:
+            u1, u2 = pair.host
+            mem = MEM_HOST
+            if allow_resident:
+                commit = pair               # the caller arms the retention right before its library call (_retain)
     else:
-        _check_device_array(u1, 2, "u1"); _check_device_array(u2, 2, "u2")
+        u1 = _host_if_cpu_tensor(u1); u2 = _host_if_cpu_tensor(u2)
+        dev = _is_device(u1)
+        if dev != _is_device(u2):
+            raise ValueError("u1 and u2 must both be host arrays or both be device buffers")
+        mem = MEM_DEVICE if dev else MEM_HOST
+        if not dev:
+            u1 = np.asarray(u1); u2 = np.asarray(u2)
+            if u1.dtype != np.float32 or u2.dtype != np.float32:
+                u1 = u1.astype(np.float64, copy=False); u2 = u2.astype(np.float64, copy=False)
+            u1 = np.ascontiguousarray(u1.reshape(-1, 2)); u2 = np.ascontiguousarray(u2.reshape(-1, 2))
+        else:
+            _check_device_array(u1, 2, "u1"); _check_device_array(u2, 2, "u2")
     if len(u1) != len(u2):
         raise ValueError("u1 and u2 must hold the same number of points")
     in_dtype = _np_dtype(u1)
@@ -337,7 +401,7 @@ def _prep(u1, u2, compute_dtype, out_dtype):
         raise ValueError("u1 and u2 must have the same dtype")
     if np.dtype(compute_dtype) == np.float32 and (in_dtype != np.float32 or np.dtype(out_dtype) != np.float32):
         compute_dtype = np.float64          # FP32 arithmetic is only defined for float32 in/out
-    return u1, u2, dev, len(u1), mode_for(in_dtype, compute_dtype, out_dtype)
+    return u1, u2, mem, len(u1), mode_for(in_dtype, compute_dtype, out_dtype), commit
 
 
 def _out(dev, n, cols, dtype, given):
@@ -404,16 +468,18 @@ def undistort_points(src, K, dist=None, dst=None, stream=None):
 def linear_ls(u1, P1, u2, P2, out_dtype=np.float64, compute_dtype=np.float64, x=None, status=None, stream=None,
               pixel=None, evaluate=None):
     """pixel: an Intrinsics -> u1,u2 are pixel coordinates, undistorted in registers in front of the solve."""
-    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
+    u1, u2, mem, n, mode, commit = _prep(u1, u2, compute_dtype, out_dtype)
+    dev = mem == MEM_DEVICE
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
-    mem = MEM_DEVICE if dev else MEM_HOST
     _arm(evaluate, dev)
+    _retain(commit)
     if pixel is None:
         check(lib().trgl_linear_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, mode, mem, stream))
     else:
         check(lib().trgl_linear_ls_px(_ptr(u1), _ptr(u2), *pixel.args(), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
                                       mode, mem, stream))
+    _commit(commit)
     return x, status
 
 
@@ -456,33 +522,37 @@ def multiview_ls(us, Ps, valid=None, min_views=2, out_dtype=np.float64, x=None, 
 
 def iterative_ls(u1, P1, u2, P2, tolerance=3.e-5, semantics=ITER_C, out_dtype=np.float64, compute_dtype=np.float64,
                  x=None, status=None, stream=None, pixel=None, evaluate=None):
-    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
+    u1, u2, mem, n, mode, commit = _prep(u1, u2, compute_dtype, out_dtype)
+    dev = mem == MEM_DEVICE
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.int32, status)
-    mem = MEM_DEVICE if dev else MEM_HOST
     _arm(evaluate, dev)
+    _retain(commit)
     if pixel is None:
         check(lib().trgl_iterative_ls(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n, float(tolerance),
                                       semantics, mode, mem, stream))
     else:
         check(lib().trgl_iterative_ls_px(_ptr(u1), _ptr(u2), *pixel.args(), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
                                          float(tolerance), semantics, mode, mem, stream))
+    _commit(commit)
     return x, status
 
 
 def linear_eigen(u1, P1, u2, P2, max_coordinate_value=1.e16, rows=4, out_dtype=np.float64, compute_dtype=np.float64,
                  x=None, status=None, stream=None, pixel=None, evaluate=None):
-    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
+    u1, u2, mem, n, mode, commit = _prep(u1, u2, compute_dtype, out_dtype)
+    dev = mem == MEM_DEVICE
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
-    mem = MEM_DEVICE if dev else MEM_HOST
     _arm(evaluate, dev)
+    _retain(commit)
     if pixel is None:
         check(lib().trgl_linear_eigen(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
                                       float(max_coordinate_value), rows, mode, mem, stream))
     else:
         check(lib().trgl_linear_eigen_px(_ptr(u1), _ptr(u2), *pixel.args(), _dp(P1), _dp(P2), _ptr(x), _ptr(status), n,
                                          float(max_coordinate_value), rows, mode, mem, stream))
+    _commit(commit)
     return x, status
 
 
@@ -490,7 +560,8 @@ def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_d
                compute_dtype=np.float64, x=None, status=None, want_corrected=False, check_all_nan=True, stream=None,
                pixel=None, evaluate=None):
     """Returns x, status, all_nan[, u1_corr, u2_corr]."""
-    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, out_dtype)
+    u1, u2, mem, n, mode, commit = _prep(u1, u2, compute_dtype, out_dtype)
+    dev = mem == MEM_DEVICE
     P1 = _P12(P1); P2 = _P12(P2)
     x = _out(dev, n, 3, out_dtype, x); status = _out(dev, n, 0, np.bool_, status)
     in_dtype = np.float32 if mode in (F32IO, F32, F32_OUT64) else np.float64
@@ -498,8 +569,8 @@ def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_d
     c2 = _out(dev, n, 2, in_dtype, None) if want_corrected else None
     flag = ctypes.c_int(0)
     flag_p = ctypes.byref(flag) if check_all_nan else None
-    mem = MEM_DEVICE if dev else MEM_HOST
     _arm(evaluate, dev)
+    _retain(commit)
     if pixel is not None:
         if F is not None:
             raise ValueError("pixel inputs and an explicit F cannot be combined")
@@ -513,16 +584,18 @@ def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_d
         F = np.ascontiguousarray(F, dtype=np.float64).reshape(3, 3)
         check(lib().trgl_polynomial_F(_ptr(u1), _ptr(u2), _dp(P1), _dp(P2), _dp(F), _ptr(x), _ptr(status), _ptr(c1),
                                       _ptr(c2), flag_p, n, float(max_coordinate_value), rows, mode, mem, stream))
+    _commit(commit)
     if want_corrected:
         return x, status, bool(flag.value), c1, c2
     return x, status, bool(flag.value)
 
 
 def fundamental_8point(u1, u2, compute_dtype=np.float64, stream=None):
-    u1, u2, dev, n, mode = _prep(u1, u2, compute_dtype, np.float32 if np.dtype(compute_dtype) == np.float32 else
-                                 (np.float32 if getattr(u1, "dtype", None) == np.float32 else np.float64))
+    u1, u2, mem, n, mode, _ = _prep(u1, u2, compute_dtype, np.float32 if np.dtype(compute_dtype) == np.float32 else
+                                    (np.float32 if getattr(u1, "dtype", None) == np.float32 else np.float64),
+                                    allow_resident=False)
     F = np.zeros((3, 3))
-    check(lib().trgl_fundamental_8point(_ptr(u1), _ptr(u2), n, mode, MEM_DEVICE if dev else MEM_HOST, _dp(F), stream))
+    check(lib().trgl_fundamental_8point(_ptr(u1), _ptr(u2), n, mode, mem, _dp(F), stream))
     return F
 
 
@@ -589,7 +662,9 @@ def pair_reproj(x, u1, P1, u2, P2, status, min_status=0, max_sq_err=np.inf, want
     P1 = _P12(P1); P2 = _P12(P2)
     e1 = _out(dev, n, 0, xdt, None) if want_errors else None
     e2 = _out(dev, n, 0, xdt, None) if want_errors else None
-    good = _out(dev, n, 0, np.bool_, None) if want_good else None
+    # want_good may be a caller-owned (n,) bool / uint8 buffer to fill
+    good = want_good if (want_good is not None and not isinstance(want_good, bool)) else \
+        (_out(dev, n, 0, np.bool_, None) if want_good else None)
     if sums_device is not None:
         if not dev:
             raise ValueError("the asynchronous variant needs device buffers")
@@ -676,6 +751,18 @@ class FusedEval:
                                         _ptr(self.sums)))
 
 
+def _retain(pair):
+    """Ask the next host-mode solver call of this thread to leave its uploaded u1 / u2 in the pair's device buffers."""
+    if pair is not None:
+        check(lib().trgl_set_input_retention(_ptr(pair.dev[0]), _ptr(pair.dev[1])))
+
+
+def _commit(pair):
+    """The host-mode call that was asked to retain its inputs has succeeded: later calls read them in HBM."""
+    if pair is not None:
+        pair.uploaded = True
+
+
 def _arm(evaluate, dev):
     if evaluate is not None:
         if not dev:
@@ -683,13 +770,14 @@ def _arm(evaluate, dev):
         evaluate.arm()
 
 
-def set_result_mirrors(mirrors):
+def set_result_mirrors(mirrors, x_f32=False):
     """mirrors: list of (x_address, status_address) in peer GPUs' memory for the NEXT device-mode solver call of this
-    thread (see include/triangl_cuda.h, "result gather fused into the solver's stores")."""
+    thread (see include/triangl_cuda.h, "result gather fused into the solver's stores").  x_f32: the mirrors hold float32
+    rows whatever the dtype of the call's own x (trgl_set_result_mirrors_f32)."""
     k = len(mirrors)
     xs = (ctypes.c_void_p * max(k, 1))(*[int(m[0]) for m in mirrors])
     ss = (ctypes.c_void_p * max(k, 1))(*[int(m[1]) for m in mirrors])
-    check(lib().trgl_set_result_mirrors(xs, ss, k))
+    check((lib().trgl_set_result_mirrors_f32 if x_f32 else lib().trgl_set_result_mirrors)(xs, ss, k))
 
 
 def ipc_export(dev):

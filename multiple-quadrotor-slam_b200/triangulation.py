@@ -20,6 +20,9 @@ Beyond the reference (all optional, defaults reproduce the reference):
     (C extension vs pure-Python fallback, SURVEY.md F2) and the OpenCV-4 / OpenCV-2.4 DLT system (F4);
   * device-resident inputs (triangl_cuda.DeviceArray or CUDA torch tensors) are accepted and give
     device-resident outputs;
+  * resident(u1, u2) returns handles for the u1 / u2 arguments that upload the observations ONCE: the comparison harness
+    runs all four solvers on the same observation set (triangulation_comparison.py:466-469); with the handles the first
+    call leaves them in HBM and the other three read them there (results are host arrays as always);
   * undistort_points(imgp, cameraMatrix, distCoeffs) is cv2.undistortPoints on the GPU (bit-identical to cv2 4.13), and
     every solver has a `*_px` twin taking PIXEL coordinates plus the intrinsics, i.e. the three reference lines
         imgpnrm0 = cv2.undistortPoints(np.array([imgp0]), cameraMatrix, distCoeffs)[0]          (slam2.py:551)
@@ -67,6 +70,16 @@ def set_triangl_semantics(iterative=None, eigen_rows_=None):
         if eigen_rows_ not in (4, 6):
             raise ValueError("eigen_rows must be 4 or 6")
         eigen_rows = eigen_rows_
+
+
+def resident(u1, u2):
+    """
+    "Upload once, solve many": handles to pass as (u1, u2) to any of the solvers of this module.  The first solver call
+    uploads the observations and keeps them in HBM, every later call on the same handles reads them there; the results
+    are host arrays exactly as with plain arrays.  (Four solvers on one observation set -- the harness' loop,
+    triangulation_comparison.py:466-469 -- upload 32 instead of 128 bytes per correspondence.)
+    """
+    return _tc.resident(u1, u2)
 
 
 def _kernel_out_dtype():

@@ -81,18 +81,40 @@ void orc_linear_ls(const double* u1, const double* u2, const double* P1, const d
     }
 }
 
+/* Diagnostics for the parity tests: conditioning s_max / s_min of the unweighted 4x3 system of every point. */
+void orc_ls_condition(const double* u1, const double* u2, const double* P1, const double* P2, double* cond, int64_t n) {
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double A[12], b[4], V[9], lo = DBL_MAX, hi = 0;
+        build_Ab(u1 + 2*i, u2 + 2*i, P1, P2, A, b);
+        jacobi(A, 4, 3, V);
+        for (int j = 0; j < 3; ++j) {
+            double sq = 0;
+            for (int k = 0; k < 4; ++k) sq += A[k*3+j]*A[k*3+j];
+            sq = sqrt(sq);
+            if (sq < lo) lo = sq;
+            if (sq > hi) hi = sq;
+            if (sq != sq) { lo = 0; hi = 1; }
+        }
+        cond[i] = hi / lo;
+    }
+}
+
+/* margin (may be NULL): min over the evaluated convergence tests of | |d_new - d| - tol | -- a point whose margin is at
+ * rounding level changes its iteration count with the last bit of the solve ("knife edge"). */
 void orc_iterative_ls(const double* u1, const double* u2, const double* P1, const double* P2, double* x, int32_t* status,
-                      int32_t* nsolves, int64_t n, double tol, int py_semantics) {
+                      int32_t* nsolves, double* margin, int64_t n, double tol, int py_semantics) {
     #pragma omp parallel for schedule(dynamic, 1024)
     for (int64_t xi = 0; xi < n; ++xi) {
         double A[12], b[4], *xp = x + 3*xi;
         build_Ab(u1 + 2*xi, u2 + 2*xi, P1, P2, A, b);
-        double d1 = 1, d2 = 1, d1n = 1, d2n = 1;
+        double d1 = 1, d2 = 1, d1n = 1, d2n = 1, mg = INFINITY;
         int i;
         for (i = 0; i < 10; ++i) {
             solve43(A, b, xp);
             d1n = P1[8]*xp[0] + P1[9]*xp[1] + P1[10]*xp[2] + P1[11];
             d2n = P2[8]*xp[0] + P2[9]*xp[1] + P2[10]*xp[2] + P2[11];
+            { double m1 = fabs(fabs(d1n - d1) - tol), m2 = fabs(fabs(d2n - d2) - tol); if (m1 < mg) mg = m1; if (m2 < mg) mg = m2; }
             if ((fabs(d1n - d1) <= tol && fabs(d2n - d2) <= tol) || (!py_semantics && (d1n == 0 || d2n == 0))) break;
             double s1 = 1. / d1n, s2 = 1. / d2n;
             for (int k = 0; k < 6; ++k) { A[k] *= s1; A[6+k] *= s2; }
@@ -100,6 +122,7 @@ void orc_iterative_ls(const double* u1, const double* u2, const double* P1, cons
             d1 = d1n; d2 = d2n;
         }
         if (nsolves) nsolves[xi] = i < 10 ? i + 1 : 10;
+        if (margin) margin[xi] = mg;
         if (py_semantics && i == 10) i = 9;
         int st = (i < 10) && (d1n > 0) && (d2n > 0);
         if (d1n <= 0) st -= 1;
@@ -108,8 +131,10 @@ void orc_iterative_ls(const double* u1, const double* u2, const double* P1, cons
     }
 }
 
+/* amp (may be NULL): s_1 / ((s_3 - s_4) |w|) -- how much a relative perturbation eps of the DLT matrix moves the
+ * dehomogenised point; points where amp * eps approaches the tolerance are ill-posed for ANY implementation. */
 static void eigen_point(const double* u1, const double* u2, const double* P1, const double* P2, int rows, double maxc,
-                        double* x, uint8_t* st) {
+                        double* x, uint8_t* st, double* amp) {
     double B[24], V[16];
     int per = rows / 2;
     const double* u[2] = {u1, u2}; const double* P[2] = {P1, P2};
@@ -127,15 +152,22 @@ static void eigen_point(const double* u1, const double* u2, const double* P1, co
     }
     double X[4];
     for (int k = 0; k < 4; ++k) X[k] = (best == best) ? V[k*4+jb] : best;
+    if (amp) {
+        double sv[4];
+        for (int j = 0; j < 4; ++j) { double sq = 0; for (int r = 0; r < rows; ++r) sq += B[r*4+j]*B[r*4+j]; sv[j] = sqrt(sq); }
+        for (int i = 0; i < 3; ++i) for (int j = i + 1; j < 4; ++j) if (sv[j] > sv[i]) { double t = sv[i]; sv[i] = sv[j]; sv[j] = t; }
+        *amp = sv[0] / (sv[2] - sv[3]) / fabs(X[3]);
+        if (!(*amp == *amp)) *amp = INFINITY;
+    }
     for (int k = 0; k < 3; ++k) x[k] = X[k] / X[3];
     double m = fmax(fmax(fabs(x[0]), fabs(x[1])), fabs(x[2]));
     *st = (x[0] == x[0] && x[1] == x[1] && x[2] == x[2] && m <= maxc) ? 1 : 0;
 }
 
 void orc_linear_eigen(const double* u1, const double* u2, const double* P1, const double* P2, double* x, uint8_t* status,
-                      int64_t n, double maxc, int rows) {
+                      double* amp, int64_t n, double maxc, int rows) {
     #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < n; ++i) eigen_point(u1 + 2*i, u2 + 2*i, P1, P2, rows, maxc, x + 3*i, status + i);
+    for (int64_t i = 0; i < n; ++i) eigen_point(u1 + 2*i, u2 + 2*i, P1, P2, rows, maxc, x + 3*i, status + i, amp ? amp + i : 0);
 }
 
 /* smallest right singular vector of a 3x3 (row-major) */
@@ -216,12 +248,12 @@ void orc_correct_matches(const double* F, const double* u1, const double* u2, do
 }
 
 void orc_polynomial(const double* F, const double* u1, const double* u2, const double* P1, const double* P2, double* x,
-                    uint8_t* status, int64_t n, double maxc, int rows) {
+                    uint8_t* status, double* amp, int64_t n, double maxc, int rows) {
     #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < n; ++i) {
         double c1[2], c2[2];
         correct_point(F, u1 + 2*i, u2 + 2*i, c1, c2);
-        eigen_point(c1, c2, P1, P2, rows, maxc, x + 3*i, status + i);
+        eigen_point(c1, c2, P1, P2, rows, maxc, x + 3*i, status + i, amp ? amp + i : 0);   /* amp of the CORRECTED match */
     }
 }
 

@@ -26,7 +26,7 @@ def lib():
 
 
 def _p(a):
-    return a.ctypes.data_as(ctypes.c_void_p)
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
 def _prep(u1, P1, u2, P2):
@@ -51,20 +51,37 @@ def linear_LS_triangulation(u1, P1, u2, P2):
     return x, st.view(np.bool_)
 
 
-def iterative_LS_triangulation(u1, P1, u2, P2, tolerance=3.e-5, semantics='c', return_nsolves=False):
+def ls_condition(u1, P1, u2, P2):
+    """s_max / s_min of the unweighted 4x3 system of every point (parity-test diagnostics)."""
+    u1, P1, u2, P2, n = _prep(u1, P1, u2, P2)
+    cond = np.empty(n)
+    lib().orc_ls_condition(_p(u1), _p(u2), _p(P1), _p(P2), _p(cond), ctypes.c_int64(n))
+    return cond
+
+
+def iterative_LS_triangulation(u1, P1, u2, P2, tolerance=3.e-5, semantics='c', return_nsolves=False, return_margin=False):
+    """return_margin: also the knife-edge margin of the deciding convergence test (oracle.iterative_LS_core)."""
     u1, P1, u2, P2, n = _prep(u1, P1, u2, P2)
     x = np.empty((n, 3)); st = np.empty(n, dtype=np.int32); ns = np.empty(n, dtype=np.int32)
-    lib().orc_iterative_ls(_p(u1), _p(u2), _p(P1), _p(P2), _p(x), _p(st), _p(ns), ctypes.c_int64(n),
-                           ctypes.c_double(tolerance), ctypes.c_int(1 if semantics == 'py' else 0))
-    return (x, st, ns) if return_nsolves else (x, st)
+    mg = np.empty(n) if return_margin else None
+    lib().orc_iterative_ls(_p(u1), _p(u2), _p(P1), _p(P2), _p(x), _p(st), _p(ns), _p(mg) if return_margin else None,
+                           ctypes.c_int64(n), ctypes.c_double(tolerance), ctypes.c_int(1 if semantics == 'py' else 0))
+    out = (x, st)
+    if return_nsolves:
+        out += (ns,)
+    if return_margin:
+        out += (mg,)
+    return out
 
 
-def linear_eigen_triangulation(u1, P1, u2, P2, max_coordinate_value=1.e16, rows=4):
+def linear_eigen_triangulation(u1, P1, u2, P2, max_coordinate_value=1.e16, rows=4, return_amp=False):
+    """return_amp: also s1 / ((s3 - s4) |w|), the error amplification of the dehomogenised singular vector."""
     u1, P1, u2, P2, n = _prep(u1, P1, u2, P2)
     x = np.empty((n, 3)); st = np.empty(n, dtype=np.uint8)
-    lib().orc_linear_eigen(_p(u1), _p(u2), _p(P1), _p(P2), _p(x), _p(st), ctypes.c_int64(n),
+    amp = np.empty(n) if return_amp else None
+    lib().orc_linear_eigen(_p(u1), _p(u2), _p(P1), _p(P2), _p(x), _p(st), _p(amp) if return_amp else None, ctypes.c_int64(n),
                            ctypes.c_double(max_coordinate_value), ctypes.c_int(rows))
-    return x, st.view(np.bool_)
+    return (x, st.view(np.bool_), amp) if return_amp else (x, st.view(np.bool_))
 
 
 def correct_matches(F, u1, u2):
@@ -75,13 +92,14 @@ def correct_matches(F, u1, u2):
     return n1, n2
 
 
-def polynomial_triangulation(u1, P1, u2, P2, rows=4):
+def polynomial_triangulation(u1, P1, u2, P2, rows=4, return_amp=False):
     u1, P1, u2, P2, n = _prep(u1, P1, u2, P2)
     F = np.ascontiguousarray(orc.fundamental_from_P(P1, P2))
     x = np.empty((n, 3)); st = np.empty(n, dtype=np.uint8)
-    lib().orc_polynomial(_p(F), _p(u1), _p(u2), _p(P1), _p(P2), _p(x), _p(st), ctypes.c_int64(n),
-                         ctypes.c_double(1.e16), ctypes.c_int(rows))
-    return x, st.view(np.bool_)
+    amp = np.empty(n) if return_amp else None
+    lib().orc_polynomial(_p(F), _p(u1), _p(u2), _p(P1), _p(P2), _p(x), _p(st), _p(amp) if return_amp else None,
+                         ctypes.c_int64(n), ctypes.c_double(1.e16), ctypes.c_int(rows))
+    return (x, st.view(np.bool_), amp) if return_amp else (x, st.view(np.bool_))
 
 
 SOLVERS = {

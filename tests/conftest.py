@@ -38,3 +38,22 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# ---- parity reports: counted over ALL points, printed at the end of the run (also with -q) -----------------------------
+PARITY_REPORTS = []
+
+
+def pytest_terminal_summary(terminalreporter):
+    if not PARITY_REPORTS:
+        return
+    terminalreporter.write_sep("-", "parity reports (every point counted; ill-posed / knife-edge points are a separate class)")
+    for line in PARITY_REPORTS:
+        terminalreporter.write_line(line)
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_reports.txt"), "w") as f:
+            f.write("\n".join(PARITY_REPORTS) + "\n")
+    except OSError:
+        pass

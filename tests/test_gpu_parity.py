@@ -77,7 +77,7 @@ def test_linear_ls_vs_oracle(tri, rig_name, sigma):
     assert x.shape == (30011, 3) and x.dtype == np.float64 and st.dtype == np.bool_
     assert st.all() and np.array_equal(st, so)
     ok = ls_well_posed(u1, P1, u2, P2)
-    assert ok.mean() > 0.95
+    assert ok.mean() >= 0.995
     assert rel_err(x, xo)[ok].max() < TOL64
     # ill-conditioned remainder still agrees to its conditioning
     A, _ = orc.build_Ab(u1, P1, u2, P2)
@@ -100,7 +100,7 @@ def test_iterative_ls_vs_oracle(tri, rig_name, sigma, semantics):
     knife = margin < 1e-9
     assert knife.mean() < 1e-3
     ok = ls_well_posed(u1, P1, u2, P2) & ~knife
-    assert ok.mean() > 0.9
+    assert ok.mean() >= 0.995
     assert np.array_equal(st[ok], so[ok])
     assert rel_err(x, xo)[ok].max() < TOL64
     assert set(np.unique(st)).issubset({1, 0, -1, -2, -3})
@@ -122,7 +122,7 @@ def test_iterative_ls_closed_form_equals_reference_loop(tri, rig_name, sigma):
     assert old == 1
     knife = iterative_margin(u1, P1, u2, P2) < 1e-9
     ok = ls_well_posed(u1, P1, u2, P2) & ~knife
-    assert ok.mean() > 0.9
+    assert ok.mean() >= 0.995
     assert np.array_equal(st[ok], stg[ok])
     assert rel_err(x, xg)[ok].max() < TOL64
     # away from the certified set both still agree to the conditioning of the system
@@ -165,7 +165,7 @@ def test_deferred_list_overflow_redoes_every_point(tri):
             else:
                 ok = eigen_well_posed(u1, P1, u2, P2)
             ok &= np.isfinite(xo).all(axis=1)
-            assert ok.mean() > 0.5, name
+            assert ok.mean() >= 0.995, name
             assert np.array_equal(st[ok], so[ok]) and np.array_equal(st_full[ok], so[ok]), name
             assert rel_err(x, xo)[ok].max() < TOL64 and rel_err(x_full, xo)[ok].max() < TOL64, name
     finally:
@@ -178,6 +178,46 @@ def test_deferred_list_overflow_redoes_every_point(tri):
     assert np.array_equal(st[keep], so[keep]) and rel_err(x, xo)[keep].max() < TOL64
 
 
+@pytest.mark.parametrize("name", ["linear_eigen", "linear_LS", "iterative_LS", "polynomial"])
+def test_deferred_list_overflow_with_fused_evaluation(tri, name):
+    """List overflow + evaluation epilogue: the follow-up kernel redoes and re-evaluates EVERY point, so the hot kernel's
+    own sums must not be counted twice.  Fused sums / mask / errors == the stand-alone pass over the stored result."""
+    import triangl_cuda as tc
+    n = 60013
+    # forward motion under heavy noise defers thousands of points in every solver but linear_LS; a 1e-5 baseline does for it
+    if name == "linear_LS":
+        u1, P1, u2, P2, _ = rig.make_correspondences(n, (1e-5, 0., 0.), 0.1)
+    else:
+        u1, P1, u2, P2, _ = rig.make_correspondences(n, "forward", 20.0)
+    d1, d2 = tc.to_device(u1), tc.to_device(u2)
+    fn = {"linear_eigen": tc.linear_eigen, "linear_LS": tc.linear_ls, "iterative_LS": tc.iterative_ls,
+          "polynomial": lambda *a, **k: tc.polynomial(*a, check_all_nan=False, **k)[:2]}[name]
+    thr = (30.0 / 480) ** 2
+    if name == "iterative_LS":                   # identical cameras: every system has rank 2, nothing is certified
+        d2, u2, P2 = d1, u1, P1
+    x_ref, st_ref = fn(d1, P1, d2, P2)
+    old = tc.set_deferred_capacity(100)
+    try:
+        fe = tc.FusedEval(n, np.float64, -5, thr, want_errors=True, want_good=True)
+        x, st = fn(d1, P1, d2, P2, evaluate=fe)
+        e1, e2, good, sums = tc.pair_reproj(x, d1, P1, d2, P2, st, -5, thr)
+        tc.synchronize()
+        fs = fe.sums.to_host()
+    finally:
+        tc.set_deferred_capacity(old)
+    assert np.array_equal(x.to_host(), x_ref.to_host(), equal_nan=True) and np.array_equal(st.to_host(), st_ref.to_host())
+    assert np.array_equal(fe.good.to_host(), good.to_host())
+    assert np.array_equal(fe.err1.to_host(), e1.to_host(), equal_nan=True)
+    assert sums[3] > 0 and fs[2] == sums[2] and fs[3] == sums[3]          # counts exactly once
+    assert fs[0] == pytest.approx(sums[0], rel=1e-10) and fs[1] == pytest.approx(sums[1], rel=1e-10)
+    # and the list is re-armed: the same call without the limit gives the same sums
+    fe2 = tc.FusedEval(n, np.float64, -5, thr, want_errors=False, want_good=False)
+    fn(d1, P1, d2, P2, evaluate=fe2)
+    tc.synchronize()
+    f2 = fe2.sums.to_host()
+    assert f2[2] == sums[2] and f2[3] == sums[3] and f2[0] == pytest.approx(sums[0], rel=1e-10)
+
+
 def test_iterative_ls_uncertified_points_take_the_reference_loop(tri):
     """Cameras without a finite centre (affine P), identical cameras (rank 2) and a 1e-5 baseline: none of them is
     certified by the closed form, all must still match the oracle."""
@@ -188,7 +228,7 @@ def test_iterative_ls_uncertified_points_take_the_reference_loop(tri):
     x, st = tri.iterative_LS_triangulation(u1, Pa1, u2, Pa2)
     xo, so, _, margin = orc.iterative_LS_core(u1, Pa1, u2, Pa2)
     ok = ls_well_posed(u1, Pa1, u2, Pa2) & (margin > 1e-9)
-    assert ok.mean() > 0.9
+    assert ok.mean() >= 0.995
     assert np.array_equal(st[ok], so[ok]) and rel_err(x, xo)[ok].max() < TOL64
     # (b) identical cameras: minimum-norm solutions of rank-2 systems
     x, st = tri.iterative_LS_triangulation(u1, P1, u1, P1)
@@ -219,7 +259,7 @@ def test_linear_eigen_vs_oracle(tri, rig_name, sigma, rows):
         tri.set_triangl_semantics(eigen_rows_=4)
     xo, so = orc.linear_eigen_triangulation(u1, P1, u2, P2, rows=rows)
     ok = eigen_well_posed(u1, P1, u2, P2)
-    assert ok.mean() > (0.5 if rig_name == "forward" else 0.99)
+    assert ok.mean() >= 0.995           # measured: >= 0.9956 on every rig and noise level
     assert np.array_equal(st[ok], so[ok])
     assert rel_err(x, xo)[ok].max() < TOL64
 
@@ -233,7 +273,7 @@ def test_polynomial_vs_oracle(tri, rig_name, sigma):
     F = orc.fundamental_from_P(P1, P2)
     c1, c2 = orc.correct_matches(F, u1, u2)
     ok = eigen_well_posed(c1, P1, c2, P2) & np.isfinite(xo).all(axis=1)
-    assert ok.mean() > (0.5 if rig_name == "forward" else 0.99)
+    assert ok.mean() >= 0.995           # measured: >= 0.9956 on every rig and noise level
     assert np.array_equal(st[ok], so[ok])
     assert rel_err(x, xo)[ok].max() < TOL64
 
@@ -254,7 +294,7 @@ def test_polynomial_ray_intersection_equals_eigen_solver(tri, rig_name, dtype):
     assert np.array_equal(st, stg)
     n1, n2 = orc.correct_matches(orc.fundamental_from_P(P1, P2), np.asarray(u1, np.float64), np.asarray(u2, np.float64))
     ok = eigen_well_posed(n1, P1, n2, P2) & st
-    assert ok.mean() > 0.9
+    assert ok.mean() >= 0.995
     assert rel_err(x, xg)[ok].max() < (TOL64 if dtype == np.float64 else TOL32)
 
 
@@ -290,7 +330,7 @@ def test_reference_python_fixtures(tri, golden_dir):
                     F = orc.fundamental_from_P(P1, P2)
                     c1, c2 = orc.correct_matches(F, u1, u2)
                     ok = eigen_well_posed(c1, P1, c2, P2)
-                assert ok.mean() > 0.9, (f, name)
+                assert ok.mean() >= 0.985, (f, name)      # 400-point fixtures: the forward rig has 5 ill-posed points
                 assert np.array_equal(np.asarray(st)[ok], sr[ok]), (f, name)
                 assert rel_err(x, xr)[ok].max() < TOL64, (f, name, rel_err(x, xr)[ok].max())
     finally:
@@ -336,10 +376,17 @@ def test_golden_cells_on_gpu(tri, golden_dir):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rig_name", RIG_NAMES)
+@pytest.mark.parametrize("sigma", [0.0, 0.8, 8.0])
 @pytest.mark.parametrize("name", ["linear_eigen", "linear_LS", "iterative_LS", "polynomial"])
-def test_fp32_mode(tri, name):
-    """FP32 mode: float32 storage and arithmetic; comparator is the float64 reference on the float32-rounded inputs."""
-    u1, P1, u2, P2, X = rig.make_correspondences(30011, "translating", 0.8, dtype=np.float32)
+def test_fp32_mode(tri, name, rig_name, sigma):
+    """FP32 mode: float32 storage (and float32 arithmetic where it exists: linear_LS); the comparator is the float64
+    reference run on the float32-rounded inputs (the reference is all-float64: triangulation_c/__init__.py:32-33), bar 1e-4.
+    Points whose float64 answer is itself ill-posed at the 1e-4 level (conditioning x float32 output rounding) are a
+    separate, counted class; status vectors are compared on every other point."""
+    from oracle import oracle_c
+    n = 30011
+    u1, P1, u2, P2, X = rig.make_correspondences(n, rig_name, sigma, dtype=np.float32)
     tri.set_triangl_output_dtype(np.float32)
     tri.set_triangl_compute_dtype(np.float32)
     try:
@@ -347,10 +394,32 @@ def test_fp32_mode(tri, name):
     finally:
         tri.set_triangl_output_dtype(float)
         tri.set_triangl_compute_dtype(np.float64)
-    xo, so = orc.SOLVERS[name](u1.astype(np.float64), P1, u2.astype(np.float64), P2)
+    w1, w2 = u1.astype(np.float64), u2.astype(np.float64)
     assert x.dtype == np.float32
-    assert np.array_equal(st, so)
-    assert rel_err(x, xo).max() < TOL32
+    if name == "linear_LS":
+        xo, so = oracle_c.linear_LS_triangulation(w1, P1, w2, P2)
+        # float32 ARITHMETIC: the solve is accurate to cond(A) x 6e-8 at best
+        well = oracle_c.ls_condition(w1, P1, w2, P2) * 6e-8 * 8 < TOL32
+    elif name == "iterative_LS":
+        xo, so, margin = oracle_c.iterative_LS_triangulation(w1, P1, w2, P2, return_margin=True)
+        well = margin > 1e-9
+    elif name == "linear_eigen":
+        xo, so, amp = oracle_c.linear_eigen_triangulation(w1, P1, w2, P2, return_amp=True)
+        well = amp * 2.2e-16 * 50 < 1e-9
+    else:
+        xo, so, amp = oracle_c.polynomial_triangulation(w1, P1, w2, P2, return_amp=True)
+        # the corrected match is rounded to float32 before the triangulation (cv2.correctMatches returns its input dtype):
+        # the oracle here corrects in float64, so the comparison carries amp x 6e-8
+        well = (amp * 6e-8 * 4 < TOL32) & np.isfinite(xo).all(axis=1)
+    rel = rel_err(x, xo)
+    mism = np.asarray(st) != np.asarray(so)
+    from conftest import PARITY_REPORTS
+    PARITY_REPORTS.append("fp32 %-13s %-11s sigma %4.1f: n %d, separate class %d, status mismatches %d (outside the class %d), "
+                          "max rel err outside the class %.2e" % (name, rig_name, sigma, n, int((~well).sum()), int(mism.sum()),
+                                                                  int((mism & well).sum()), rel[well].max()))
+    assert well.mean() >= 0.99
+    assert not (mism & well).any()
+    assert rel[well].max() < TOL32
 
 
 @pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 257, 1000])
@@ -490,6 +559,101 @@ def test_fused_pair_reprojection_and_good_mask(tri):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def _classify(name, w1, P1, w2, P2):
+    """Oracle result + the class of points no two correct implementations agree on, from the C oracle."""
+    from oracle import oracle_c
+    if name == "linear_LS":
+        xo, so = oracle_c.linear_LS_triangulation(w1, P1, w2, P2)
+        special = oracle_c.ls_condition(w1, P1, w2, P2) * 2.2e-16 * 50 >= TOL64
+    elif name == "iterative_LS":
+        xo, so, margin = oracle_c.iterative_LS_triangulation(w1, P1, w2, P2, return_margin=True)
+        special = (margin < 1e-9) | (oracle_c.ls_condition(w1, P1, w2, P2) * 2.2e-16 * 50 >= TOL64)
+    elif name == "linear_eigen":
+        xo, so, amp = oracle_c.linear_eigen_triangulation(w1, P1, w2, P2, return_amp=True)
+        special = ~(amp * 2.2e-16 * 50 < TOL64)
+    else:
+        xo, so, amp = oracle_c.polynomial_triangulation(w1, P1, w2, P2, return_amp=True)
+        special = ~(amp * 2.2e-16 * 50 < TOL64) | ~np.isfinite(xo).all(axis=1)
+    return xo, np.asarray(so), special
+
+
+@pytest.mark.parametrize("rig_name,tiled", [("rotating", True), ("rotating", False), ("forward", False)])
+def test_bench_input_parity(tri, rig_name, tiled):
+    """
+    Parity on what is benchmarked (BASELINE configs[1]): 10 M correspondences, 0.8 px noise, all four solvers, device-resident
+    arrays, the evaluation fused / separate exactly as bench.py's timed step runs it -- against the C oracle
+    (triangulation.c:104-161 / triangulation.py:6-25,198-232 restated; pinned to the NumPy oracle and through it to the
+    reference's golden files) on EVERY point.
+      tiled = True : the very arrays bench.py times (harness/synthetic_rig.bench_batch: 2 M seeded points tiled to 10 M);
+                     the oracle runs on the 2 M distinct points, every tile of the GPU result is compared with it;
+      tiled = False: 10 M distinct points (rotating and forward-motion rigs).
+    Nothing is filtered: status mismatches and the largest relative error are counted over all points and reported with the
+    knife-edge / ill-posed class separated; outside that class mismatches must be 0 and errors <= 1e-9.
+    """
+    import triangl_cuda as tc
+    from conftest import PARITY_REPORTS
+    n = 10_000_000
+    if tiled:
+        u1, P1, u2, P2, base = rig.bench_batch(n, rig_name, rank=0)
+    else:
+        u1, P1, u2, P2, _ = rig.make_correspondences(n, rig_name, sigma=0.8, seed=rig.RSEED + 17)
+        base = n
+    d_u1, d_u2 = tc.to_device(u1), tc.to_device(u2)
+    thr = (2.0 / 480) ** 2
+    for name in ("linear_eigen", "linear_LS", "iterative_LS", "polynomial"):
+        fe = None
+        if name != "linear_LS":                  # bench.py default: epilogue for the three FP64-bound solvers ...
+            fe = tc.FusedEval(n, np.float64, 0, thr, want_errors=False, want_good=True)
+        if name == "linear_eigen":
+            x, st = tc.linear_eigen(d_u1, P1, d_u2, P2, evaluate=fe)
+        elif name == "linear_LS":
+            x, st = tc.linear_ls(d_u1, P1, d_u2, P2)
+        elif name == "iterative_LS":
+            x, st = tc.iterative_ls(d_u1, P1, d_u2, P2, evaluate=fe)
+        else:
+            x, st, all_nan = tc.polynomial(d_u1, P1, d_u2, P2, evaluate=fe)
+            assert not all_nan
+        if fe is None:                           # ... and the stand-alone pass after linear_LS
+            _, _, good, sums = tc.pair_reproj(x, d_u1, P1, d_u2, P2, st, 0, thr, want_errors=False, want_good=True)
+        else:
+            good, sums = fe.good, fe.sums.to_host()
+        tc.synchronize()
+        x, st, good = x.to_host(), st.to_host(), good.to_host()
+        xo, so, special = _classify(name, u1[:base], P1, u2[:base], P2)
+        if base < n:                             # every tile against the oracle on the distinct points
+            reps = -(-n // base)
+            xo = np.tile(xo, (reps, 1))[:n]; so = np.tile(so, reps)[:n]; special = np.tile(special, reps)[:n]
+        rel = rel_err(x, xo)
+        with np.errstate(invalid="ignore"):
+            bad = ~(rel <= TOL64) & ~(np.isnan(x).all(axis=1) & np.isnan(xo).all(axis=1))
+        mism = st.astype(np.int64) != so.astype(np.int64)
+        # good mask of the harness / SLAM step from the ORACLE's x (triangulation_comparison.py:190-217; slam2.py:556,589)
+        xh = np.concatenate([xo, np.ones((n, 1))], axis=1)
+        e = []
+        dep = []
+        with np.errstate(all="ignore"):
+            for u, P in ((u1, P1), (u2, P2)):
+                pr = xh @ P.T
+                e.append(((pr[:, 0:2] / pr[:, 2:3] - u) ** 2).sum(axis=1)); dep.append(pr[:, 2])
+            want = (so > 0) & (e[0] <= thr) & (e[1] <= thr) & (dep[0] > 0) & (dep[1] > 0)
+            edge = (np.minimum(np.abs(e[0] - thr), np.abs(e[1] - thr)) <= 1e-9 * thr) | special
+        gm = good.astype(bool) != want
+        PARITY_REPORTS.append(
+            "bench-input %-13s %-8s %s n %d: separate class %d (%.1e of all), status mismatches %d (outside the class %d), "
+            "points over 1e-9 %d (outside the class %d), max rel err outside the class %.2e, good-mask mismatches %d "
+            "(outside the class / threshold edge %d), good %d" %
+            (name, rig_name, "tiled-2M" if tiled else "distinct", n, int(special.sum()), special.mean(), int(mism.sum()),
+             int((mism & ~special).sum()), int(bad.sum()), int((bad & ~special).sum()), np.nanmax(rel[~special]),
+             int(gm.sum()), int((gm & ~edge).sum()), int(good.sum())))
+        assert special.mean() < 5e-3, name
+        assert not (mism & ~special).any(), name
+        assert not (bad & ~special).any(), name
+        assert not (gm & ~edge).any(), name
+        assert sums[2] == good.sum(), name               # the fused count is the mask's population
+        # the ill-posed class is bounded too: finite where the oracle is finite, status mismatches only inside it
+        assert mism.sum() <= special.sum(), name
+
+
 def test_full_size_properties(tri):
     """BASELINE config-2 size (10 M points): size-independent properties instead of an oracle run.
        (1) exact projections triangulate back to the cloud (round trip) for every solver;
@@ -780,6 +944,71 @@ def test_result_mirrors_across_processes_via_cuda_ipc(tri):
     tc.synchronize()
     assert np.array_equal(gx.to_host()[lo:lo + n], xc, equal_nan=True) and np.array_equal(gs.to_host()[lo:lo + n], stc)
     assert np.isnan(gx.to_host()[:lo]).all()
+
+
+def _peer_gather_rank(rank, world, port, n_total, tmp):
+    """One process per GPU: solve the local shard with the peers' shard addresses as result mirrors (sharding.PeerGather),
+    then compare the gathered arrays with a single-GPU solve of the whole batch done on this rank."""
+    import os
+    import sys
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "multiple-quadrotor-slam_b200"), os.path.join(root, "harness")):
+        sys.path.insert(0, p)
+    import numpy as np
+    import torch.distributed as dist
+    import sharding
+    import synthetic_rig as rig
+    import triangl_cuda as tc
+    tc.check(tc.lib().trgl_set_device(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)          # handle exchange + barrier only (plumbing)
+    result = {}
+    try:
+        u1, P1, u2, P2, _ = rig.make_correspondences(n_total, "rotating", sigma=0.8)
+        d1, d2 = tc.to_device(u1), tc.to_device(u2)
+        lo, hi = sharding.shard_range(n_total, rank, world)
+        s1 = d1.view(2 * lo, (hi - lo, 2)); s2 = d2.view(2 * lo, (hi - lo, 2))
+        for name in ("linear_eigen", "linear_LS", "iterative_LS", "polynomial"):
+            sdt = np.int32 if name == "iterative_LS" else np.uint8
+            fn = {"linear_eigen": tc.linear_eigen, "linear_LS": tc.linear_ls, "iterative_LS": tc.iterative_ls,
+                  "polynomial": lambda *a, **k: tc.polynomial(*a, check_all_nan=False, **k)[:2]}[name]
+            pg = sharding.PeerGather(n_total, np.float64, sdt)
+            tc.check(tc.lib().trgl_memset_d(pg.x_all.ptr, 0xff, pg.x_all.nbytes, None))
+            tc.check(tc.lib().trgl_memset_d(pg.status_all.ptr, 0x7f, pg.status_all.nbytes, None))
+            tc.synchronize(); dist.barrier()                               # nobody stores into a buffer still being cleared
+            xs, ss = pg.shard_outputs()
+            pg.arm()
+            fn(s1, P1, s2, P2, x=xs, status=ss)
+            pg.finish()
+            x_full, st_full = fn(d1, P1, d2, P2)                           # single-GPU result of the whole batch
+            tc.synchronize()
+            result[name] = bool(np.array_equal(pg.x_all.to_host(), x_full.to_host(), equal_nan=True) and
+                                np.array_equal(pg.status_all.to_host(), st_full.to_host()))
+            dist.barrier()
+            pg.close()
+    except Exception as exc:        # noqa: BLE001
+        result["error"] = repr(exc)
+    import json
+    with open(os.path.join(tmp, "peer_%d.json" % rank), "w") as f:
+        json.dump(result, f)
+    dist.destroy_process_group()
+
+
+def test_peer_gather_across_real_gpus(tri, tmp_path):
+    """sharding.PeerGather across DIFFERENT GPUs (>= 2 devices): every rank's solver kernels store their shard into every
+    peer's gathered arrays over NVLink; afterwards x_all / status_all on every rank equal the single-GPU result bit for bit."""
+    import triangl_cuda as tc
+    import torch.multiprocessing as mp
+    world = min(tc.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    port = 29700 + os.getpid() % 1000
+    mp.spawn(_peer_gather_rank, args=(world, port, 300_007, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        with open(os.path.join(str(tmp_path), "peer_%d.json" % r)) as f:
+            res = json.load(f)
+        assert "error" not in res, res
+        assert res == {"linear_eigen": True, "linear_LS": True, "iterative_LS": True, "polynomial": True}, (r, res)
 
 
 # ---- evaluation fused into the solver kernels ---------------------------------------------------------------------------

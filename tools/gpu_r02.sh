@@ -1,0 +1,38 @@
+#!/bin/bash
+# Round-2 GPU call: parity tests, smoke, the default bench line (N = 1), reference arm, SLAM latency.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_r02.sh r02a [phases]'      phases: tests,bench,ref,slam,launches,ncu (default: tests,bench,ref,slam)
+set -u
+TAG=${1:-r02}
+PH=${2:-tests,bench,ref,slam}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw --format=csv > $OUT/nvidia_smi.csv 2>&1
+nvidia-smi topo -m > $OUT/topo.txt 2>&1
+has() { [[ ",$PH," == *",$1,"* ]]; }
+if has tests; then echo "== pytest -m gpu"; timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -60 $OUT/pytest_gpu.log | cut -c1-400; fi
+if has smoke; then echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -8 $OUT/smoke.log; fi
+if has bench; then echo "== bench default"; timeout 900 python bench.py > $OUT/bench_10M.json 2> $OUT/bench_10M.err; echo "bench rc=$?"; tail -5 $OUT/bench_10M.err; python tools/show_bench.py $OUT/bench_10M.json; fi
+if has ref; then echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cut -c1-500 $OUT/bench_reference.json; fi
+if has slam; then echo "== slam"; timeout 600 python bench.py --workload slam --steps 200 --warmup 20 > $OUT/slam_latency.json 2> $OUT/slam.err; echo "slam rc=$?"; tail -3 $OUT/slam.err; python tools/show_bench.py $OUT/slam_latency.json; fi
+if has rigs; then echo "== sweep 10M per rig"; for R in rotating translating forward general; do timeout 300 python tools/sweep_kernels.py --points 10000000 --solvers linear_LS,iterative_LS,linear_eigen,polynomial --modes f64 --variants 0 --ppts 4 --rig $R | sed "s/^{/{\"rig\": \"$R\", /" >> $OUT/sweep_rigs_10M.jsonl; done; cut -c1-160 $OUT/sweep_rigs_10M.jsonl; fi
+if has mv; then echo "== multi-view"; timeout 300 python tools/sweep_multiview.py --views 2,4,8,16 > $OUT/sweep_multiview.jsonl 2> $OUT/sweep_multiview.err; timeout 300 python tools/sweep_multiview.py --views 8 --visible 0.7 >> $OUT/sweep_multiview.jsonl; cut -c1-200 $OUT/sweep_multiview.jsonl; fi
+if has launches; then
+  echo "== ncu launch list (bench --steps 2 --warmup 1)"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-100m > $OUT/launches_bench.log 2>&1
+  echo "launch list rc=$? lines=$(wc -l < $OUT/launches.csv)"
+fi
+export_rep() {
+    ncu -i $1.ncu-rep --page raw --csv > $1.raw.csv 2>/dev/null
+    ncu -i $1.ncu-rep --page source --csv > $1.source.csv 2>/dev/null
+    rm -f $1.ncu-rep
+}
+if has ncu; then
+  for K in ${NCU_KERNELS:-k_linear_ls k_iterative_ls k_linear_eigen k_polynomial}; do
+    timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^$K\$" -s 1 -c 1 -f -o $OUT/full_$K \
+        python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-100m > $OUT/full_$K.log 2>&1
+    echo "$K rc=$?"
+    export_rep $OUT/full_$K
+  done
+fi
+ls -la $OUT | head -40
