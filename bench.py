@@ -76,10 +76,11 @@ def parse():
     ap.add_argument("--separate-eval", action="store_true",
                     help="run the two-view reprojection / good-mask evaluation as its own pass after every solver "
                          "(trgl_pair_reproj_async) instead of in the solver kernels' epilogue (trgl_set_fused_eval)")
-    ap.add_argument("--fuse-ls-eval", action="store_true",
-                    help="also fuse the evaluation into linear_LS.  Default: the three FP64-bound solvers carry it in their "
-                         "epilogue (it hides behind the solve), the HBM-bound linear_LS is followed by the stand-alone "
-                         "pass (fusing it there turns an HBM-bound kernel into an FP64-bound one for an 11 %% gain)")
+    ap.add_argument("--separate-ls-eval", action="store_true",
+                    help="run the evaluation of linear_LS as its own pass (trgl_pair_reproj_async) after the HBM-bound kernel "
+                         "instead of in its epilogue.  Default: all four solvers carry the evaluation in their epilogue "
+                         "(linear_LS + epilogue 0.157 ms vs 0.093 + 0.143 ms as two passes per 10 M points); the roofline "
+                         "entry always times the plain HBM-bound k_linear_ls by itself")
     ap.add_argument("--workload", default="solvers", choices=["solvers", "slam", "scene"],
                     help="solvers: the four solvers at --points per GPU (default, BASELINE configs[1]); "
                          "slam: keyframe map-extension latency at SLAM-sized batches (BASELINE configs[4]); "
@@ -290,7 +291,7 @@ def run_ours(args, rank, world, local_rank):
     # the good mask the north star names is WRITTEN in the timed region (1 B/point), by the solver's epilogue or by the pass
     fused = {s: tc.FusedEval(n, np.float64, 0, thr, want_errors=False, want_good=True, sums=d_sums.view(4 * si, (4,)))
              for si, s in enumerate(SOLVERS)
-             if not args.separate_eval and (s != "linear_LS" or args.fuse_ls_eval)}
+             if not args.separate_eval and (s != "linear_LS" or not args.separate_ls_eval)}
     d_good = {s: tc.DeviceArray((n,), np.bool_) for s in SOLVERS if s not in fused}
 
     def solve(name, u1_, u2_, x, st, evaluate=None, nan_check=False):
@@ -364,10 +365,8 @@ def run_ours(args, rank, world, local_rank):
     launches0 = tc.launch_count()
     elapsed_ms = timed_steps(args.steps, args.warmup, per_kernel)
     launches = tc.launch_count() - launches0
-    # the step times linear_LS together with its evaluation pass; the HBM-bound kernel alone is timed right here, same buffers
-    ls_alone_ms = None
-    if "linear_LS" not in fused:
-        ls_alone_ms, _ = time_launches(tc, lambda: tc.linear_ls(d_u1, P1, d_u2, P2, x=d_x["linear_LS"], status=d_st["linear_LS"]), 3, 20)
+    # the step times linear_LS together with its evaluation; the HBM-bound kernel alone is timed right here, same buffers
+    ls_alone_ms, _ = time_launches(tc, lambda: tc.linear_ls(d_u1, P1, d_u2, P2, x=d_x["linear_LS"], status=d_st["linear_LS"]), 3, 20)
 
     # ---- result gather (N > 1): the only real exchange step of the path ------------------------------
     gather = None
@@ -556,7 +555,7 @@ def run_ours(args, rank, world, local_rank):
                                "reprojection error / good mask (written) %s; polynomial's all-NaN flag read once per step "
                                "(BASELINE.json configs[1])"
                                % (args.rig, n, "as its own pass after each" if args.separate_eval else
-                                  ("in each solver kernel's epilogue" if args.fuse_ls_eval else
+                                  ("in each solver kernel's epilogue" if not args.separate_ls_eval else
                                    "in the epilogue of the three FP64-bound solver kernels, as its own pass after linear_LS")),
                    "points_per_gpu": n, "rig": args.rig,
                    "sharding": "contiguous point ranges; `value` has no data-path collective, the result gather is in `gather`",
@@ -576,11 +575,9 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
     }
     # roofline of the dominant HBM-bound kernel: live CUDA-event time of this run; traffic is the ncu figure of the same kernel
-    ls = per_solver["linear_LS"]
-    if "linear_LS" in fused_names(args):
-        ls_ms, ls_src = ls["kernel_ms"], "k_linear_ls<f64, EVAL> + follow-up, timed together inside the step"
-    else:
-        ls_ms, ls_src = ls_alone_ms, "k_linear_ls<f64> + its ~4 us follow-up kernel, median of 20 launches back to back right after the timed steps (CUDA events)"
+    ls_ms, ls_src = ls_alone_ms, ("k_linear_ls<f64> + its ~4 us follow-up kernel, median of 20 launches back to back right after the "
+                                  "timed steps (CUDA events); inside the step linear_LS runs with the evaluation epilogue "
+                                  "(per_solver.linear_LS)")
     if ls_ms:
         gbs = ALG_BYTES["linear_LS"] * n / (ls_ms * 1e-3) / 1e9
         out["roofline"] = {"kernel": "k_linear_ls<f64>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -614,7 +611,7 @@ def run_ours(args, rank, world, local_rank):
 
 
 def fused_names(args):
-    return [s for s in SOLVERS if not args.separate_eval and (s != "linear_LS" or args.fuse_ls_eval)]
+    return [s for s in SOLVERS if not args.separate_eval and (s != "linear_LS" or not args.separate_ls_eval)]
 
 
 # ---- SLAM keyframe map-extension replay: latency at SLAM-sized batches (BASELINE.json configs[4]) ----------------

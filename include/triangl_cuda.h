@@ -77,6 +77,7 @@ int trgl_host_alloc(void** ptr, size_t bytes);           /* pinned */
 int trgl_host_free(void* ptr);
 int trgl_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
 int trgl_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int trgl_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 int trgl_memset_d(void* dst, int value, size_t bytes, void* stream);
 int trgl_stream_create(void** stream);
 int trgl_stream_destroy(void* stream);
@@ -221,6 +222,15 @@ int trgl_eval_errors_3d(const void* x, const double* exact, int exact_stride, co
  * pixel positions (error_vectors_2D, :190-203).  stats (host, 4 doubles): sum of errors, number of NaN errors, 0, 0. */
 int trgl_eval_errors_2d(const void* proj, const double* exact, double* errors, double* stats, int64_t n, int proj_is_f32,
                         int mem, void* stream);
+/* vector_stat of the comparison harness (Work/triangulation_comparison/triangulation_comparison.py:219-240, used at
+ * :483-487 for the last pose of every trajectory): x_trials is the (trials, n, 3) array of the solver results of all
+ * repetitions (errors_partitioned + exact), exact the (n, exact_stride) cloud; means (n,3) and covars (n,3,3) doubles
+ * receive, per point, the mean of its 3-D error vectors x[t,i,:] - exact[i,0:3] over the trials and their population
+ * covariance (divisor = trials, like the reference).  mem = DEVICE: all five arrays on the device, enqueued on stream,
+ * no synchronisation; mem = HOST: staged through the GPU. */
+int trgl_vector_stat(const void* x_trials, const double* exact, int exact_stride, int trials, double* means, double* covars,
+                     int64_t n, int x_is_f32, int mem, void* stream);
+
 /* np.median of n non-negative doubles (the squared errors above), exact: most-significant-digit radix selection on the
  * IEEE bit patterns (8 histogram passes), mean of the two middle elements for even n, NaN if any element is NaN or
  * n == 0.  median: host double.  Synchronises the stream. */
@@ -286,6 +296,10 @@ int trgl_set_two_ray(int enabled);
  * are deferred than the list holds, the follow-up kernel redoes every point instead.  This limits the list to
  * max_points (1 .. 2^26) so that the overflow path can be exercised on small batches.  Returns the previous limit. */
 int64_t trgl_set_deferred_capacity(int64_t max_points);
+/* Diagnostics: running total of the correspondences the hot kernels have handed to their follow-up kernels on this
+ * (current device, stream) since the library was loaded (bench.py reports the deferred fraction per solver with it).
+ * Synchronises the stream. */
+int trgl_deferred_total(void* stream, int64_t* total);
 
 #ifdef __cplusplus
 }

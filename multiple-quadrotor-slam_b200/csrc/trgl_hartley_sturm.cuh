@@ -119,11 +119,22 @@ __device__ __noinline__ double hs_select_dk(const double k[7], double a, double 
     return t_min;
 }
 
+__device__ __forceinline__ double hs_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = x * -0.5;
+    r = fma(r, fma(h * r, r, 0.5), r);
+    r = fma(r, fma(h * r, r, 0.5), r);
+    return r;
+}
+
 __device__ __forceinline__ void hs_epipole(const double e[3], double x, double y, double& ex, double& ey, double& f) {
     ex = fma(-x, e[2], e[0]);
     ey = fma(-y, e[2], e[1]);
     f = e[2];
-    const double inv = rsqrt(fma(ex, ex, ey * ey));       // 0 -> inf -> NaN epipole -> NaN point, like the reference
+    // MUFU.RSQ64H seed + two Newton steps (full precision for normal arguments, no special-case path);
+    // 0 -> inf -> NaN epipole -> NaN point, like the reference
+    const double inv = hs_rsqrt(fma(ex, ex, ey * ey));
     ex *= inv; ey *= inv; f *= inv;
     if (f < 0.0) { ex = -ex; ey = -ey; f = -f; }
 }
@@ -131,7 +142,6 @@ __device__ __forceinline__ void hs_epipole(const double e[3], double x, double y
 // SLOW = true: the complete correction (follow-up kernel, CPU-like robustness).  SLOW = false: the certified fast path
 // only, for the hot kernel -- returns false, leaving the outputs undefined, when the certificate does not hold or the
 // bracketed Newton iteration needs more than kHsFastIters rounds; the caller then defers the point.
-constexpr int kHsFastIters = 12;
 template <bool SLOW>
 __device__ __forceinline__ bool hs_correct(const HSParams& hs, double x1, double y1, double x2, double y2,
                                            double& n1x, double& n1y, double& n2x, double& n2y) {
@@ -174,40 +184,62 @@ __device__ __forceinline__ bool hs_correct(const HSParams& hs, double x1, double
     bool fast = finite_coeffs && (f1s * s0 < 1.0);
     double T0 = 0.0;
     if (fast) {
-        T0 = sqrt(s0 * fast_rcp(1.0 - f1s * s0));
+        // any upper bound of T0 keeps the certificate valid: x * rsqrt(x), inflated by 1e-9, instead of the IEEE sqrt
+        const double T0s = s0 * fast_rcp(1.0 - f1s * s0);
+        T0 = (T0s > 0.0) ? T0s * hs_rsqrt(T0s) * (1.0 + 1e-9) : T0s;
         const double bound = T0 * fma(T0, fma(T0, fma(T0, fma(T0, 6.0 * fabs(k[6]), 5.0 * fabs(k[5])),
                                                       4.0 * fabs(k[4])), 3.0 * fabs(k[3])), 2.0 * fabs(k[2]));
         fast = k[1] > bound;
     }
-    if (fast) {
-        // Bracketed Newton on g (strictly increasing on [-T0, T0]).  Newton converges quadratically, so once a
-        // NEWTON step is below 1e-8 |t| the iterate it produced is exact to rounding (error ~ step^2); bisection steps
-        // only stop on a 2-ulp bracket.  (Demanding a 2-ulp Newton step made single lanes bisect for ~50 rounds.)
-        double lo = -T0, hi = T0;
-        t = 0.0;
-        bool done = false;
+    if constexpr (SLOW) {
+        if (fast) {
+            // Bracketed Newton on g (strictly increasing on [-T0, T0]).  Newton converges quadratically, so once a
+            // NEWTON step is below 1e-8 |t| the iterate it produced is exact to rounding (error ~ step^2); bisection steps
+            // only stop on a 2-ulp bracket.  (Demanding a 2-ulp Newton step made single lanes bisect for ~50 rounds.)
+            double lo = -T0, hi = T0;
+            t = 0.0;
 #pragma unroll 1
-        for (int it = 0; it < (SLOW ? 64 : kHsFastIters); ++it) {
+            for (int it = 0; it < 64; ++it) {
+                double g = k[6], dg = 0.0;
+#pragma unroll
+                for (int i = 5; i >= 0; --i) { dg = fma(dg, t, g); g = fma(g, t, k[i]); }
+                if (g == 0.0) break;
+                if (g < 0.0) lo = t; else hi = t;
+                double tn = fma(-g, fast_rcp(dg), t);          // g' > 0 on the bracket (certificate)
+                if (tn == t) break;                            // Newton step below half an ulp: converged
+                const bool newton = (tn >= lo && tn <= hi);
+                if (!newton) tn = 0.5 * (lo + hi);
+                const double step = fabs(tn - t);
+                t = tn;
+                if ((newton && step <= 1e-8 * fabs(tn)) || (hi - lo) <= 4e-16 * fabs(tn)) break;
+            }
+        } else if (finite_coeffs) {
+            t = hs_select_dk(k, a, b, c, d, f1, f2);
+        }
+    } else {
+        // Hot kernel (all 32 lanes of the warp are here): plain Newton from t = 0 with a FIXED number of steps and one
+        // acceptance test at the end -- no per-lane exit, no bracket bookkeeping; lanes whose certificate failed run along
+        // on garbage and are discarded.  g(0) = k0, g'(0) = k1, so the first iterate is free; two more (one Horner pass
+        // each) satisfy the test for every point of the translating / rotating rigs and 99 % of the general rig at
+        // 0.8 - 8 px; further ones are taken by the whole warp while any of its certified lanes needs them (warp-uniform
+        // branch).  Accepted: the last Newton step is below 1e-8 |t| (the iterate it produced is then exact to rounding,
+        // error ~ step^2) and the iterate lies in [-T0, T0], where the certificate has shown g to have exactly one root --
+        // whatever path the iteration took to get there.  Everything else is deferred.
+        double tp = -k[0] * fast_rcp(k[1]);
+        bool accepted = false;
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
             double g = k[6], dg = 0.0;
 #pragma unroll
-            for (int i = 5; i >= 0; --i) { dg = fma(dg, t, g); g = fma(g, t, k[i]); }
-            if (g == 0.0) { done = true; break; }
-            if (g < 0.0) lo = t; else hi = t;
-            double tn = fma(-g, fast_rcp(dg), t);          // g' > 0 on the bracket (certificate)
-            if (tn == t) { done = true; break; }           // Newton step below half an ulp: converged
-            const bool newton = (tn >= lo && tn <= hi);
-            if (!newton) tn = 0.5 * (lo + hi);
-            const double step = fabs(tn - t);
-            t = tn;
-            if ((newton && step <= 1e-8 * fabs(tn)) || (hi - lo) <= 4e-16 * fabs(tn)) { done = true; break; }
+            for (int i = 5; i >= 0; --i) { dg = fma(dg, tp, g); g = fma(g, tp, k[i]); }
+            t = fma(-g, fast_rcp(dg), tp);
+            accepted = (fabs(t - tp) <= 1e-8 * fabs(t)) && (fabs(t) <= T0);
+            tp = t;
+            if (it >= 1 && __all_sync(0xffffffffu, accepted || !fast)) break;
         }
-        if constexpr (!SLOW) certified = done;
-    } else if (finite_coeffs) {
-        if constexpr (SLOW) t = hs_select_dk(k, a, b, c, d, f1, f2);
-        else certified = false;
+        certified = fast && accepted;
+        if (!certified) t = 0.0;
     }
-    // hot kernel (all 32 lanes are here): re-converge the lanes that left the Newton loop at different rounds
-    if constexpr (!SLOW) __syncwarp();
     // closest points to the origin on the two epipolar lines, then back through R^T and T^-1.  t == DBL_MAX: t = inf
     // wins (or non-finite system) -- the reference evaluates inf/inf -> NaN for both points.
     const bool at_inf = (t == DBL_MAX);

@@ -152,7 +152,8 @@ __device__ __forceinline__ int tworay_step(const T d11, const T d12, const T d21
 // memory (profiles/r01f).
 struct Deferred {
     int64_t* idx;                 // [cap] indices of the points to redo
-    unsigned int* ctl;            // ctl[0] = number of deferred points (may exceed cap), ctl[1] = ticket of the follow-up kernel
+    unsigned int* ctl;            // ctl[0] = number of deferred points (may exceed cap), ctl[1] = ticket of the follow-up kernel,
+                                  // ctl[2..3] = 64-bit running total of deferred points (diagnostics)
     unsigned int cap;
 };
 __device__ __forceinline__ void defer_point(const Deferred& df, int64_t i) {
@@ -234,6 +235,54 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
         ls_tile<TI, TC, TO, PPT, PRE, EVAL, MIR, DEFER>(u1, u2, cams, x, status, n, pre, mir, ev, df,
                                                         static_cast<int64_t>(blockIdx.x) * (kThreads * PPT), stage[threadIdx.x >> 5], acc);
     }
+}
+
+// ---- linear_LS, FP32 mode: four CONSECUTIVE points per thread, 128-bit loads and stores --------------------------------
+// At 29 bytes per point the FP32 mode is bound by instruction issue, not by HBM, unless the per-point overhead goes: here a
+// thread loads its four (x,y) pairs of each view as two float4, solves them with float32 normal equations (no refinement:
+// tier-1 points only, the rest is deferred to k_linear_ls_general<float>), and writes its 12 result floats as three float4
+// and its four status bytes as one 32-bit word -- no shared-memory transposition, no per-point address arithmetic.
+// Needs 16-byte aligned u1 / u2 / x and 4-byte aligned status (the launcher checks); the last < 4 points take scalar accesses.
+__global__ void __launch_bounds__(kThreads, 4)
+k_linear_ls_f32x4(const float* __restrict__ u1, const float* __restrict__ u2, const __grid_constant__ Cams<float> cams,
+                  float* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ Deferred df) {
+    const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    float in1[8], in2[8], xs[4][3];
+    const bool full = i0 + 4 <= n;
+    if (full) {
+        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(u1 + 2 * i0)), a1 = __ldcs(reinterpret_cast<const float4*>(u1 + 2 * i0) + 1);
+        const float4 b0 = __ldcs(reinterpret_cast<const float4*>(u2 + 2 * i0)), b1 = __ldcs(reinterpret_cast<const float4*>(u2 + 2 * i0) + 1);
+        in1[0] = a0.x; in1[1] = a0.y; in1[2] = a0.z; in1[3] = a0.w; in1[4] = a1.x; in1[5] = a1.y; in1[6] = a1.z; in1[7] = a1.w;
+        in2[0] = b0.x; in2[1] = b0.y; in2[2] = b0.z; in2[3] = b0.w; in2[4] = b1.x; in2[5] = b1.y; in2[6] = b1.z; in2[7] = b1.w;
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const bool in = i0 + p < n;
+            in1[2 * p] = in ? u1[2 * (i0 + p)] : 0.f; in1[2 * p + 1] = in ? u1[2 * (i0 + p) + 1] : 0.f;
+            in2[2 * p] = in ? u2[2 * (i0 + p)] : 0.f; in2[2 * p + 1] = in ? u2[2 * (i0 + p) + 1] : 0.f;
+        }
+    }
+    bool ok[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) ok[p] = ls_point_plain_f32(cams, in1[2 * p], in1[2 * p + 1], in2[2 * p], in2[2 * p + 1], xs[p]);
+    if (full) {
+        float4* dst = reinterpret_cast<float4*>(x + 3 * i0);
+        __stcs(dst + 0, make_float4(xs[0][0], xs[0][1], xs[0][2], xs[1][0]));
+        __stcs(dst + 1, make_float4(xs[1][1], xs[1][2], xs[2][0], xs[2][1]));
+        __stcs(dst + 2, make_float4(xs[2][2], xs[3][0], xs[3][1], xs[3][2]));
+        *reinterpret_cast<uint32_t*>(status + i0) = 0x01010101u;
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (i0 + p < n) {
+                x[3 * (i0 + p)] = xs[p][0]; x[3 * (i0 + p) + 1] = xs[p][1]; x[3 * (i0 + p) + 2] = xs[p][2];
+                status[i0 + p] = 1;
+            }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        if (!ok[p] && i0 + p < n) defer_point(df, i0 + p);
 }
 
 // ---- linear_LS, per-thread cp.async ring ---------------------------------------------------------------------------
@@ -622,7 +671,11 @@ __device__ __forceinline__ void followup_finish(const EvalArg<EVAL>& ev, const D
     __syncthreads();
     if (threadIdx.x == 0 && rearm) {
         __threadfence();
-        if (atomicAdd(&df.ctl[1], 1u) == gridDim.x - 1) { df.ctl[0] = 0u; df.ctl[1] = 0u; __threadfence(); }
+        if (atomicAdd(&df.ctl[1], 1u) == gridDim.x - 1) {
+            // ctl[2..3]: running total of deferred points of this (device, stream), for diagnostics (trgl_deferred_total)
+            *reinterpret_cast<unsigned long long*>(df.ctl + 2) += df.ctl[0];
+            df.ctl[0] = 0u; df.ctl[1] = 0u; __threadfence();
+        }
     }
 }
 
@@ -790,7 +843,7 @@ __device__ __forceinline__ int ldl4(const T S[10], const T b[4], T y[4]) {
 
 // Fast path: Rayleigh-quotient iteration on G = B^T B started from the least-squares point (which is within noise
 // of the answer), with a certificate: (i) ||G X - lam X|| <= 4 eps tr(G) and (ii) exactly one eigenvalue of G lies below
-// lam + gap*tr(G) (inertia of the shifted matrix).  (i)+(ii) prove X is the eigenvector of the smallest eigenvalue and that
+// lam + gap*tr(G) (inertia of the shifted matrix), gap = max(2e-5, 5e-6 / |w|).  (i)+(ii) prove X is the eigenvector of the smallest eigenvalue and that
 // it is separated well enough for the G-based computation to be accurate to ~1e-12; otherwise the caller falls back to
 // the Jacobi SVD.  ~450 FP64 instructions instead of ~4800.
 // SYNC: the caller guarantees that all 32 lanes of the warp are here (the hot kernel); the warp is then re-converged
@@ -853,9 +906,143 @@ __device__ __forceinline__ bool eigen_point_fast(const Cams<TC>& cams, TC u1x, T
     TC S[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) S[k] = G[k];
-    const TC shift = lam + (sizeof(TC) == 8 ? TC(2e-5) : TC(2e-3)) * tr;
+    // Required separation of the two smallest eigenvalues, relative to tr(G).  The entries of G carry ~4 eps tr(G) of
+    // rounding, which moves the eigenvector by 4 eps tr / (lam3 - lam4) and the DEHOMOGENISED point by 1/|w| times that
+    // (w = X[3] of the unit vector): measured on the forward-motion rig, 4 eps / (gap |w|) to within 10 % on the 51 of
+    // 10 M points that exceeded 1e-9 with the fixed gap 2e-5 (|w| 1e-4 .. 0.04: points far behind the scene).  So the gap
+    // scales with 1/|w| beyond |w| = 0.25 (error bound 2e-10); such points go to the Jacobi SVD like the other deferred ones.
+    const TC gap_rel = sizeof(TC) == 8 ? tmax(TC(2e-5), TC(5e-6) * fast_rcp(tabs(X[3]))) : TC(2e-3);
+    const TC shift = tfma(gap_rel, tr, lam);
     S[0] -= shift; S[4] -= shift; S[7] -= shift; S[9] -= shift;
-    return (ldl4<TC, false>(S, X, X) == 1) && conv;
+    return (ldl4<TC, false>(S, X, X) == 1) && conv && (gap_rel == gap_rel);
+}
+
+// ---- warp-uniform variant of the fast path for the hot kernel -----------------------------------------------------------
+// The loop above leaves at a per-lane round and the warp pays for its slowest lane; how many rounds a point needs depends on
+// the rig and the noise (measured, residual <= 4 eps tr(G) after 2 / 3 rounds: rotating 0.8 px 98.7 % / 99.998 %,
+// translating 0.8 px 85 % / 99.3 %, forward motion 48 % / 84 %, any rig at 8 px 30-45 % / 75-90 %).  Here the whole warp
+// runs the same number of rounds and decides together after each one (from the second on): all lanes converged -> done;
+// at most kEigenStragglers lanes left -> those are handed to the follow-up kernel (which runs the loop above, then the
+// Jacobi SVD) and the warp is done; otherwise everybody runs another round (a converged lane just stays converged), up to
+// kEigenMaxRounds.  One more round costs the warp 32 x ~95 instructions, a deferred point ~700: break-even at 4 lanes.
+//   * the solve returns the DIRECTION d3 * (G - rho I)^-1 x: the last pivot d3 -> 0 as rho -> lam4 (that is the point of the
+//     iteration), so nothing is divided by it -- no IEEE division, no special-case path, no overflow;
+//   * normalisation uses MUFU.RSQ64H + one Newton step (1e-12): the iteration is self-correcting, and the Rayleigh
+//     quotient / residual test divide by the exact X.X.
+constexpr int kEigenMaxRounds = 4;
+constexpr int kEigenStragglers = 3;
+
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = (x * r) * -0.5;
+    return fma(r, fma(h, r, 0.5), r);
+}
+__device__ __forceinline__ float fast_rsqrt(float x) { return rsqrtf(x); }
+
+// y = d3 * S^-1 b by LDL^T without pivoting (S order 00 01 02 03 11 12 13 22 23 33); false if a leading pivot is unusable.
+template <typename T>
+__device__ __forceinline__ bool ldl4_direction(const T S[10], const T b[4], T y[4]) {
+    const T d0 = S[0];
+    const T i0 = fast_rcp(d0);
+    const T l10 = S[1] * i0, l20 = S[2] * i0, l30 = S[3] * i0;
+    const T d1 = tfma(-l10, S[1], S[4]);
+    const T i1 = fast_rcp(d1);
+    const T t21 = tfma(-l20, S[1], S[5]), t31 = tfma(-l30, S[1], S[6]);
+    const T l21 = t21 * i1, l31 = t31 * i1;
+    const T d2 = tfma(-l21, t21, tfma(-l20, S[2], S[7]));
+    const T i2 = fast_rcp(d2);
+    const T t32 = tfma(-l31, t21, tfma(-l30, S[2], S[8]));
+    const T l32 = t32 * i2;
+    const T d3 = tfma(-l32, t32, tfma(-l31, t31, tfma(-l30, S[3], S[9])));
+    const T z0 = b[0];
+    const T z1 = tfma(-l10, z0, b[1]);
+    const T z2 = tfma(-l21, z1, tfma(-l20, z0, b[2]));
+    const T z3 = tfma(-l32, z2, tfma(-l31, z1, tfma(-l30, z0, b[3])));
+    y[3] = z3;
+    y[2] = tfma(-l32, z3, (z2 * i2) * d3);
+    y[1] = tfma(-l31, z3, tfma(-l21, y[2], (z1 * i1) * d3));
+    y[0] = tfma(-l30, z3, tfma(-l20, y[2], tfma(-l10, y[1], (z0 * i0) * d3)));
+    return (d0 != T(0)) && (d1 != T(0)) && (d2 != T(0)) && (d3 == d3);
+}
+
+// All 32 lanes of the warp must call this together.  Returns true when X is certified; `straggler` = true when the point
+// has to go to the follow-up kernel (not converged within the warp's rounds, breakdown, NaN, no eigenvalue gap).
+template <typename TC, int ROWS>
+__device__ __forceinline__ bool eigen_point_warp(const Cams<TC>& cams, TC u1x, TC u1y, TC u2x, TC u2y, TC X[4]) {
+    TC G[10];
+    {
+        TC B[ROWS][4];
+        dlt_matrix<TC, ROWS>(cams, u1x, u1y, u2x, u2y, B);
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b < 4; ++b) {
+                TC s = B[0][a] * B[0][b];
+#pragma unroll
+                for (int r = 1; r < ROWS; ++r) s = tfma(B[r][a], B[r][b], s);
+                G[k++] = s;
+            }
+    }
+    const TC tr = G[0] + G[4] + G[7] + G[9];
+    {   // least-squares start: G[0:3,0:3] x = -G[0:3,3]
+        const TC M[6] = {G[0], G[1], G[2], G[4], G[5], G[7]};
+        const TC v[3] = {-G[3], -G[6], -G[8]};
+        TC C[6], x0[3];
+        const TC det = sym3_cofactors(M, C);
+        sym3_apply(C, v, fast_rcp(det), x0);
+        const TC nrm = fast_rsqrt(tfma(x0[0], x0[0], tfma(x0[1], x0[1], tfma(x0[2], x0[2], TC(1)))));
+        X[0] = x0[0] * nrm; X[1] = x0[1] * nrm; X[2] = x0[2] * nrm; X[3] = nrm;
+    }
+    const TC tol = TC(4) * Num<TC>::eps() * tr;
+    TC lam = 0;
+    bool alive = true, conv = false;
+#pragma unroll 1
+    for (int round = 0; round <= kEigenMaxRounds; ++round) {
+        TC y[4];
+        y[0] = tfma(G[0], X[0], tfma(G[1], X[1], tfma(G[2], X[2], G[3] * X[3])));
+        y[1] = tfma(G[1], X[0], tfma(G[4], X[1], tfma(G[5], X[2], G[6] * X[3])));
+        y[2] = tfma(G[2], X[0], tfma(G[5], X[1], tfma(G[7], X[2], G[8] * X[3])));
+        y[3] = tfma(G[3], X[0], tfma(G[6], X[1], tfma(G[8], X[2], G[9] * X[3])));
+        lam = tfma(X[0], y[0], tfma(X[1], y[1], tfma(X[2], y[2], X[3] * y[3])));      // ||X|| = 1 to 1e-12: fine for a shift
+        if (round >= 2) {                                  // the LS start and the first iterate are never converged
+            const TC xx = tfma(X[0], X[0], tfma(X[1], X[1], tfma(X[2], X[2], X[3] * X[3])));
+            lam *= fast_rcp(xx);                           // the exact Rayleigh quotient for the residual test
+            TC rn = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const TC r = tfma(-lam, X[k], y[k]); rn = tfma(r, r, rn); }
+            conv = rn <= tol * tol * xx;
+            const unsigned open = __ballot_sync(0xffffffffu, alive && !conv);
+            if (__popc(open) <= kEigenStragglers || round == kEigenMaxRounds) break;       // warp-uniform
+        }
+        TC S[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) S[k] = G[k];
+        S[0] -= lam; S[4] -= lam; S[7] -= lam; S[9] -= lam;
+        alive = ldl4_direction<TC>(S, X, y) && alive;
+        const TC nrm = fast_rsqrt(tfma(y[0], y[0], tfma(y[1], y[1], tfma(y[2], y[2], y[3] * y[3]))));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) X[k] = y[k] * nrm;
+    }
+    // certificate: exactly one eigenvalue of G below lam + gap tr(G)   (see eigen_point_fast)
+    const TC gap_rel = sizeof(TC) == 8 ? tmax(TC(2e-5), TC(5e-6) * fast_rcp(tabs(X[3]))) : TC(2e-3);
+    const TC shift = tfma(gap_rel, tr, lam);
+    TC S[10], dummy[4];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) S[k] = G[k];
+    S[0] -= shift; S[4] -= shift; S[7] -= shift; S[9] -= shift;
+    return alive && conv && (ldl4<TC, false>(S, X, dummy) == 1) && (gap_rel == gap_rel);
+}
+
+// Dehomogenise a CERTIFIED vector (w is bounded away from 0 by the certificate): 2-ulp reciprocal instead of the IEEE
+// division and its special-case path.
+template <typename TC>
+__device__ __forceinline__ void eigen_finish_fast(const TC X[4], TC max_coord, TC xs[3], bool& good) {
+    const TC inv = fast_rcp(X[3]);
+    xs[0] = X[0] * inv; xs[1] = X[1] * inv; xs[2] = X[2] * inv;
+    const TC m = tmax(tmax(tabs(xs[0]), tabs(xs[1])), tabs(xs[2]));
+    good = (xs[0] == xs[0]) && (xs[1] == xs[1]) && (xs[2] == xs[2]) && (m <= max_coord);
 }
 
 // Dehomogenise + finite-coordinates mask (triangulation.py:22-23).
@@ -905,8 +1092,8 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
         TC X[4], xs[3] = {0, 0, 0};
         bool good = false;
-        const bool certified = eigen_point_fast<TC, ROWS, true>(cams, a, b, c, d, X);
-        if (certified) eigen_finish<TC>(X, max_coord, xs, good);
+        const bool certified = eigen_point_warp<TC, ROWS>(cams, a, b, c, d, X);      // all 32 lanes present (uniform trip count)
+        if (certified) eigen_finish_fast<TC>(X, max_coord, xs, good);
         else if (i < n) defer_point(df, i);
         store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
                          static_cast<TO>(xs[2]), stage[warp], mir);
@@ -936,7 +1123,9 @@ k_linear_eigen_general(const TI* __restrict__ u1, const TI* __restrict__ u2, con
         TC a, b, c, d, X[4], xs[3];
         bool good;
         reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, i, a, b, c, d);
-        eigen_point_jacobi<TC, ROWS>(cams, a, b, c, d, X);
+        // the points the fixed-round hot kernel did not converge on first get the iteration with up to 5 rounds; what that
+        // does not certify either (no gap, breakdown, NaN) takes the one-sided Jacobi SVD, the path cv::SVD itself runs
+        if (!eigen_point_fast<TC, ROWS>(cams, a, b, c, d, X)) eigen_point_jacobi<TC, ROWS>(cams, a, b, c, d, X);
         eigen_finish<TC>(X, max_coord, xs, good);
 #pragma unroll
         for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);

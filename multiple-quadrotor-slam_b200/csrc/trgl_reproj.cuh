@@ -118,6 +118,41 @@ k_sq_errors_3d(const TO* __restrict__ x, const double* __restrict__ exact, const
     block_reduce_store<4>(acc, partials);
 }
 
+// vector_stat of the comparison harness (triangulation_comparison.py:219-240): per point, the mean vector and the
+// (population) covariance matrix of its 3-D error vectors x[t, i, :] - exact[i, 0:3] over the `trials` repetitions.
+// One thread per point, two passes over the trials like the reference (means first, then the deviations from them);
+// consecutive threads read consecutive points of one trial, so every pass is a coalesced stream over x (trials, n, 3).
+// means: (n, 3), covars: (n, 3, 3) row-major doubles.
+template <typename TO>
+__global__ void __launch_bounds__(kThreads)
+k_vector_stat(const TO* __restrict__ x, const double* __restrict__ exact, const int exact_stride, const int trials,
+              double* __restrict__ means, double* __restrict__ covars, const int64_t n) {
+    const double inv = 1.0 / static_cast<double>(trials);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const double ex = exact[exact_stride * i + 0], ey = exact[exact_stride * i + 1], ez = exact[exact_stride * i + 2];
+        double mx = 0, my = 0, mz = 0;
+        for (int t = 0; t < trials; ++t) {
+            const TO* p = x + (static_cast<int64_t>(t) * n + i) * 3;
+            mx += static_cast<double>(p[0]) - ex; my += static_cast<double>(p[1]) - ey; mz += static_cast<double>(p[2]) - ez;
+        }
+        mx *= inv; my *= inv; mz *= inv;
+        double c[6] = {0, 0, 0, 0, 0, 0};              // xx xy xz yy yz zz
+        for (int t = 0; t < trials; ++t) {
+            const TO* p = x + (static_cast<int64_t>(t) * n + i) * 3;
+            const double dx = (static_cast<double>(p[0]) - ex) - mx, dy = (static_cast<double>(p[1]) - ey) - my,
+                         dz = (static_cast<double>(p[2]) - ez) - mz;
+            c[0] = fma(dx, dx, c[0]); c[1] = fma(dx, dy, c[1]); c[2] = fma(dx, dz, c[2]);
+            c[3] = fma(dy, dy, c[3]); c[4] = fma(dy, dz, c[4]); c[5] = fma(dz, dz, c[5]);
+        }
+        means[3 * i + 0] = mx; means[3 * i + 1] = my; means[3 * i + 2] = mz;
+        double* o = covars + 9 * i;
+        o[0] = c[0] * inv; o[1] = c[1] * inv; o[2] = c[2] * inv;
+        o[3] = c[1] * inv; o[4] = c[3] * inv; o[5] = c[4] * inv;
+        o[6] = c[2] * inv; o[7] = c[4] * inv; o[8] = c[5] * inv;
+    }
+}
+
 // Squared norm of (n,2) residual vectors proj - exact (error_rms on error_vectors_2D), same partials[0..1].
 template <typename TP>
 __global__ void __launch_bounds__(kThreads)

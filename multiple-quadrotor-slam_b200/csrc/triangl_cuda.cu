@@ -133,7 +133,7 @@ struct Scratch {
     unsigned int* counter = nullptr;  // ticket of the in-kernel final reduction (self-resetting)
     int64_t* deferred = nullptr;      // deferred_cap indices: points a hot kernel hands to its follow-up kernel
     unsigned int deferred_cap = 0;    // grows with the batch size: one slot per point up to kDeferredMax
-    unsigned int* deferred_ctl = nullptr;   // {count, ticket}, re-armed by the follow-up kernel
+    unsigned int* deferred_ctl = nullptr;   // {count, ticket, 64-bit running total}, re-armed by the follow-up kernel
 };
 constexpr unsigned int kDeferredMin = 1u << 20, kDeferredMax = 1u << 26;
 std::atomic<unsigned int> g_deferred_limit{kDeferredMax};     // trgl_set_deferred_capacity (test knob)
@@ -208,8 +208,8 @@ int launch_ls_tma(const TI* a, const TI* b, const Cams<TC>& cams, TO* xo, uint8_
 // Persistent grid of the FP64-bound solvers: SMs x resident CTAs (occupancy API, cached per kernel), or fewer when
 // the batch has fewer 256-point tiles than that.
 template <typename K>
-unsigned persistent_grid(K kern, int64_t n, size_t dyn_smem = 0) {
-    const int64_t tiles = (n + kThreads - 1) / kThreads;
+unsigned persistent_grid(K kern, int64_t n, size_t dyn_smem = 0, int per_cta = kThreads) {
+    const int64_t tiles = (n + per_cta - 1) / per_cta;
     const int64_t full = static_cast<int64_t>(sm_count()) * blocks_per_sm(kern, dyn_smem);
     return static_cast<unsigned>(tiles < full ? tiles : full);
 }
@@ -240,13 +240,6 @@ template <typename TI, typename TO, bool EV>
 constexpr bool eval_supported() { return !EV || std::is_same<TI, TO>::value; }
 int eval_unsupported() { return fail(TRGL_E_BADARG, "the fused evaluation needs u and x of the same storage type (F64, F32IO, F32)"); }
 
-// Persistent grid of the evaluation-fused linear_LS kernel (its block partials must fit the reduction scratch).
-unsigned ls_eval_grid(int64_t n, int per_block) {
-    const int64_t tiles = (n + per_block - 1) / per_block;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
-    return static_cast<unsigned>(tiles < cap ? tiles : cap);
-}
-
 int launch_linear_ls(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,
                      int64_t n, int mode, cudaStream_t s, const Undist2* pre = nullptr, const Mirrors& mir = kNoMirrors,
                      const FusedEval* ev = nullptr) {
@@ -263,6 +256,26 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
     if ((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2)) & 15) variant = 0;
     if (pre || ev) variant = 0;                    // the pre-stage and the fused evaluation live in the direct kernel
     int rc = TRGL_OK;
+    // FP32 mode on the plain path: four consecutive points per thread with 128-bit accesses, float32 normal equations for
+    // tier-1 points, everything else through the follow-up kernel (refinement step / double)
+    if (mode == TRGL_F32 && g_variant.load() < 0 && !pre && !ev && mir.count == 0 && g_two_ray.load() &&
+        !((reinterpret_cast<uintptr_t>(u1) | reinterpret_cast<uintptr_t>(u2) | reinterpret_cast<uintptr_t>(x)) & 15) &&
+        !(reinterpret_cast<uintptr_t>(status) & 3)) {
+        Scratch sc;
+        rc = scratch_for(s, sc, n);
+        if (rc) return rc;
+        const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+        const Cams<float> cams = make_cams<float>(P1, P2);
+        const float* a = static_cast<const float*>(u1); const float* b = static_cast<const float*>(u2);
+        k_linear_ls_f32x4<<<grid_for((n + 3) / 4, kThreads), kThreads, 0, s>>>(a, b, cams, static_cast<float*>(x), status, n, df);
+        const int64_t tiles = (n + kThreads - 1) / kThreads;
+        const int64_t cap = 2 * static_cast<int64_t>(sm_count());
+        k_linear_ls_general<float, float, float, PreNone, false><<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
+            a, b, cams, static_cast<float*>(x), n, PreNone{}, kNoMirrors, EvalArg<false>{}, df);
+        g_launches += 2;
+        CK(cudaGetLastError());
+        return TRGL_OK;
+    }
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
@@ -294,18 +307,22 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
                 with_eval(ev, [&](auto E, auto evarg) {
                     constexpr bool EV = decltype(E)::value;
                     if constexpr (!eval_supported<TI, TO, EV>()) { rc = eval_unsupported(); } else {
+                        // with the evaluation epilogue the kernel is a persistent grid-stride loop (its block partials are
+                        // reduced at the end): exactly SMs x resident CTAs blocks, so that no SM idles through a partial wave
+                        auto go = [&](auto kern, int per_block, auto prearg, auto mirarg) {
+                            const unsigned grid = EV ? persistent_grid(kern, n, 0, per_block) : grid_for(n, per_block);
+                            kern<<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, prearg, mirarg, evarg, df);
+                        };
                         if (pre) {      // pixel inputs: the undistortion makes the kernel FP64-bound, one point per thread
-                            const unsigned grid = EV ? ls_eval_grid(n, kThreads) : grid_for(n, kThreads);
-                            if (defer) k_linear_ls<TI, TC, TO, 1, PreUndistort, EV, Mirrors, true><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreUndistort{*pre}, mir, evarg, df);
-                            else k_linear_ls<TI, TC, TO, 1, PreUndistort, EV><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreUndistort{*pre}, mir, evarg, df);
-                        } else if (!EV && ppt == 4 && mir.count == 0) {
-                            // THE hot path: no pre-stage, no epilogue, no mirrors compiled in
-                            if (defer) k_linear_ls<TI, TC, TO, 4, PreNone, false, NoMirrors, true><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, NoMirrors{}, EvalArg<false>{}, df);
-                            else k_linear_ls<TI, TC, TO, 4, PreNone, false, NoMirrors><<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, NoMirrors{}, EvalArg<false>{}, df);
+                            if (defer) go(k_linear_ls<TI, TC, TO, 1, PreUndistort, EV, Mirrors, true>, kThreads, PreUndistort{*pre}, mir);
+                            else go(k_linear_ls<TI, TC, TO, 1, PreUndistort, EV>, kThreads, PreUndistort{*pre}, mir);
+                        } else if (ppt == 4 && mir.count == 0) {
+                            // THE hot path: no pre-stage, no mirrors compiled in
+                            if (defer) go(k_linear_ls<TI, TC, TO, 4, PreNone, EV, NoMirrors, true>, kThreads * 4, PreNone{}, NoMirrors{});
+                            else go(k_linear_ls<TI, TC, TO, 4, PreNone, EV, NoMirrors>, kThreads * 4, PreNone{}, NoMirrors{});
                         } else if (EV || ppt == 4) {
-                            const unsigned grid = EV ? ls_eval_grid(n, kThreads * 4) : grid_for(n, kThreads * 4);
-                            if (defer) k_linear_ls<TI, TC, TO, 4, PreNone, EV, Mirrors, true><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, evarg, df);
-                            else k_linear_ls<TI, TC, TO, 4, PreNone, EV><<<grid, kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, evarg, df);
+                            if (defer) go(k_linear_ls<TI, TC, TO, 4, PreNone, EV, Mirrors, true>, kThreads * 4, PreNone{}, mir);
+                            else go(k_linear_ls<TI, TC, TO, 4, PreNone, EV>, kThreads * 4, PreNone{}, mir);
                         } else if (ppt == 2) {
                             k_linear_ls<TI, TC, TO, 2, PreNone, false><<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, EvalArg<false>{}, df);
                         } else {
@@ -498,11 +515,11 @@ int scratch_for(cudaStream_t s, Scratch& out, int64_t deferred_points) {
             cudaGetLastError();
             return fail(TRGL_E_NOMEM, "cudaMalloc of reduction scratch failed");
         }
-        if (cudaMalloc(&sc.flags, sizeof(unsigned int) * (kFlagWords + 4)) != cudaSuccess) {
+        if (cudaMalloc(&sc.flags, sizeof(unsigned int) * (kFlagWords + 8)) != cudaSuccess) {
             cudaGetLastError(); cudaFree(sc.partials); sc.partials = nullptr;
             return fail(TRGL_E_NOMEM, "cudaMalloc of reduction scratch failed");
         }
-        CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * (kFlagWords + 4)));
+        CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * (kFlagWords + 8)));
         sc.counter = sc.flags + kFlagWords;
         sc.deferred_ctl = sc.flags + kFlagWords + 2;
     }
@@ -842,6 +859,10 @@ int trgl_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
     if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
     return TRGL_OK;
 }
+int trgl_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return TRGL_OK;
+}
 int trgl_memset_d(void* dst, int value, size_t bytes, void* stream) {
     if (bytes) CK(cudaMemsetAsync(dst, value, bytes, static_cast<cudaStream_t>(stream)));
     return TRGL_OK;
@@ -933,6 +954,19 @@ int64_t trgl_set_deferred_capacity(int64_t max_points) {
     const int64_t old = g_deferred_limit.load();
     if (max_points >= 1 && max_points <= static_cast<int64_t>(kDeferredMax)) g_deferred_limit.store(static_cast<unsigned int>(max_points));
     return old;
+}
+int trgl_deferred_total(void* stream, int64_t* total) {
+    if (!total) return fail(TRGL_E_BADARG, "total is NULL");
+    *total = 0;
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    Scratch sc;
+    int rc = scratch_for(static_cast<cudaStream_t>(stream), sc);
+    if (rc) return rc;
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, sc.deferred_ctl + 2, sizeof(v), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    *total = static_cast<int64_t>(v);
+    return TRGL_OK;
 }
 int trgl_set_two_ray(int enabled) {
     const int old = g_two_ray.load();
@@ -1557,6 +1591,45 @@ int trgl_eval_errors_3d(const void* x, const double* exact, int exact_stride, co
 int trgl_eval_errors_2d(const void* proj, const double* exact, double* errors, double* stats, int64_t n, int proj_is_f32,
                         int mem, void* stream) {
     return eval_errors_common(false, proj, exact, 2, nullptr, 0, 0.0, 0.0, errors, stats, n, proj_is_f32, mem, stream);
+}
+
+int trgl_vector_stat(const void* x_trials, const double* exact, int exact_stride, int trials, double* means, double* covars,
+                     int64_t n, int x_is_f32, int mem, void* stream) {
+    if (n < 0 || trials < 1) return fail(TRGL_E_BADARG, "need n >= 0 and trials >= 1");
+    if (mem != TRGL_MEM_HOST && mem != TRGL_MEM_DEVICE) return fail(TRGL_E_BADARG, "unknown memory space");
+    if (!means || !covars || (n > 0 && (!x_trials || !exact))) return fail(TRGL_E_BADARG, "NULL pointer");
+    if (exact_stride < 3) return fail(TRGL_E_BADARG, "exact_stride must be >= 3");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    if (n == 0) return TRGL_OK;
+    std::unique_lock<std::mutex> lock(g_pipe_mutex, std::defer_lock);
+    if (mem == TRGL_MEM_HOST) lock.lock();
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t xb = static_cast<size_t>(x_is_f32 ? 4 : 8) * 3 * n * trials, eb = sizeof(double) * exact_stride * n;
+    const void* dx = x_trials; const double* de = exact; double* dm = means; double* dc = covars;
+    if (mem == TRGL_MEM_HOST) {
+        const size_t oe = align256(xb), om = oe + align256(eb), oc = om + align256(24 * n);
+        int rc = ensure_slot(g_slots[0], oc + align256(72 * n));
+        if (rc) return rc;
+        Slot& sl = g_slots[0];
+        s = sl.stream;
+        CK(cudaMemcpyAsync(sl.buf, x_trials, xb, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(sl.buf + oe, exact, eb, cudaMemcpyHostToDevice, s));
+        dx = sl.buf; de = reinterpret_cast<const double*>(sl.buf + oe);
+        dm = reinterpret_cast<double*>(sl.buf + om); dc = reinterpret_cast<double*>(sl.buf + oc);
+    }
+    const int64_t tiles = (n + kThreads - 1) / kThreads;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+    if (x_is_f32) k_vector_stat<float><<<grid, kThreads, 0, s>>>(static_cast<const float*>(dx), de, exact_stride, trials, dm, dc, n);
+    else k_vector_stat<double><<<grid, kThreads, 0, s>>>(static_cast<const double*>(dx), de, exact_stride, trials, dm, dc, n);
+    g_launches++;
+    CK(cudaGetLastError());
+    if (mem == TRGL_MEM_HOST) {
+        CK(cudaMemcpyAsync(means, dm, 24 * n, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(covars, dc, 72 * n, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return TRGL_OK;
 }
 
 int trgl_median(const double* values, int64_t n, int mem, double* median, void* stream) {

@@ -27,14 +27,14 @@ ITER_C, ITER_PY = 0, 1
 EXPORTS = [
     "trgl_version", "trgl_last_error_string", "trgl_device_count", "trgl_set_device", "trgl_device_synchronize",
     "trgl_device_alloc", "trgl_device_free", "trgl_host_alloc", "trgl_host_free", "trgl_memcpy_h2d",
-    "trgl_memcpy_d2h", "trgl_memset_d", "trgl_stream_create", "trgl_stream_destroy", "trgl_stream_synchronize",
+    "trgl_memcpy_d2h", "trgl_memcpy_d2d", "trgl_memset_d", "trgl_stream_create", "trgl_stream_destroy", "trgl_stream_synchronize",
     "trgl_event_create", "trgl_event_destroy", "trgl_event_record", "trgl_event_elapsed_ms",
     "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
     "trgl_set_points_per_thread", "trgl_set_stream_variant", "trgl_set_two_ray", "trgl_multiview_ls", "trgl_set_deferred_capacity",
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
     "trgl_set_fused_eval", "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
-    "trgl_set_result_mirrors_f32", "trgl_set_input_retention",
+    "trgl_set_result_mirrors_f32", "trgl_set_input_retention", "trgl_deferred_total", "trgl_vector_stat",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -67,6 +67,7 @@ def lib():
     L.trgl_host_free.argtypes = [vp]
     L.trgl_memcpy_h2d.argtypes = [vp, vp, ctypes.c_size_t, vp]
     L.trgl_memcpy_d2h.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    L.trgl_memcpy_d2d.argtypes = [vp, vp, ctypes.c_size_t, vp]
     L.trgl_memset_d.argtypes = [vp, cint, ctypes.c_size_t, vp]
     L.trgl_stream_create.argtypes = [ctypes.POINTER(vp)]
     L.trgl_stream_destroy.argtypes = [vp]
@@ -92,12 +93,14 @@ def lib():
     L.trgl_set_result_mirrors.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), cint]
     L.trgl_set_result_mirrors_f32.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), cint]
     L.trgl_set_input_retention.argtypes = [vp, vp]
+    L.trgl_deferred_total.argtypes = [vp, ctypes.POINTER(i64)]
     L.trgl_ipc_export.argtypes = [vp, vp]
     L.trgl_ipc_import.argtypes = [vp, ctypes.POINTER(vp)]
     L.trgl_ipc_close.argtypes = [vp]
     L.trgl_eval_errors_3d.argtypes = [vp, vp, cint, vp, cint, dbl, dbl, vp, dp, i64, cint, cint, vp]
     L.trgl_eval_errors_2d.argtypes = [vp, vp, vp, dp, i64, cint, cint, vp]
     L.trgl_median.argtypes = [vp, i64, cint, dp, vp]
+    L.trgl_vector_stat.argtypes = [vp, vp, cint, cint, vp, vp, i64, cint, cint, vp]
     L.trgl_undistort_points.argtypes = [vp, vp, dp, dp, i64, cint, cint, vp]
     L.trgl_linear_ls_px.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, vp, vp, i64, cint, cint, vp]
     L.trgl_iterative_ls_px.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
@@ -289,6 +292,56 @@ def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+# Device buffers of the resident pairs come from a small size-keyed pool (cudaMalloc + cudaFree of two 160 MB blocks per
+# handle cost 2-4 ms, as much as one solver call on 10 M points).
+_DEV_POOL_LIMIT = 8 << 30
+_dev_pool = {}          # nbytes -> [ptr, ...]
+_dev_pool_bytes = 0
+
+
+class _PooledDeviceArray(DeviceArray):
+    def __init__(self, shape, dtype):
+        global _dev_pool_bytes
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        with _pin_lock:
+            lst = _dev_pool.get(self.nbytes)
+            ptr = lst.pop() if lst else None
+            if ptr is not None:
+                _dev_pool_bytes -= self.nbytes
+        if ptr is None:
+            p = ctypes.c_void_p()
+            check(lib().trgl_device_alloc(ctypes.byref(p), self.nbytes))
+            ptr = p.value or 0
+        self.ptr = ptr
+
+    def __del__(self):
+        global _dev_pool_bytes
+        try:
+            if getattr(self, "ptr", 0):
+                with _pin_lock:
+                    if _dev_pool_bytes + self.nbytes <= _DEV_POOL_LIMIT:
+                        _dev_pool.setdefault(self.nbytes, []).append(self.ptr)
+                        _dev_pool_bytes += self.nbytes
+                        self.ptr = 0
+                        return
+                _lib.trgl_device_free(self.ptr)
+            self.ptr = 0
+        except Exception:
+            pass
+
+
+def device_pool_clear():
+    global _dev_pool_bytes
+    with _pin_lock:
+        for lst in _dev_pool.values():
+            for ptr in lst:
+                _lib.trgl_device_free(ptr)
+        _dev_pool.clear()
+        _dev_pool_bytes = 0
+
+
 class _ResidentPair:
     def __init__(self, u1, u2):
         u1 = np.asarray(_host_if_cpu_tensor(u1)); u2 = np.asarray(_host_if_cpu_tensor(u2))
@@ -297,7 +350,7 @@ class _ResidentPair:
         self.host = (np.ascontiguousarray(u1.reshape(-1, 2)), np.ascontiguousarray(u2.reshape(-1, 2)))
         if len(self.host[0]) != len(self.host[1]):
             raise ValueError("u1 and u2 must hold the same number of points")
-        self.dev = (DeviceArray(self.host[0].shape, self.host[0].dtype), DeviceArray(self.host[1].shape, self.host[1].dtype))
+        self.dev = (_PooledDeviceArray(self.host[0].shape, self.host[0].dtype), _PooledDeviceArray(self.host[1].shape, self.host[1].dtype))
         self.uploaded = False
 
 
@@ -722,6 +775,33 @@ def eval_errors_2d(proj, exact, want_errors=True, stream=None):
     return errors, stats
 
 
+def vector_stat(x_trials, exact, stream=None):
+    """vector_stat (triangulation_comparison.py:219-240) of the error vectors x_trials[t] - exact[:, 0:3]:
+    x_trials (trials, n, 3) host array or device buffer, exact (n, 3|4) in the same memory space.
+    Returns means (n,3), covars (n,3,3) -- host arrays for host input, DeviceArrays for device input."""
+    x_trials = _host_if_cpu_tensor(x_trials); exact = _host_if_cpu_tensor(exact)
+    dev = _is_device(x_trials)
+    if dev != _is_device(exact):
+        raise ValueError("x_trials and exact must both be host arrays or both be device buffers")
+    if not dev:
+        x_trials = np.asarray(x_trials)
+        if x_trials.dtype != np.float32:
+            x_trials = x_trials.astype(np.float64, copy=False)
+        x_trials = np.ascontiguousarray(x_trials)
+        exact = np.ascontiguousarray(exact, dtype=np.float64)
+    shape = tuple(int(v) for v in x_trials.shape)
+    if len(shape) != 3 or shape[2] != 3 or len(exact.shape) != 2 or int(exact.shape[0]) != shape[1] or int(exact.shape[1]) < 3:
+        raise ValueError("x_trials must be (trials, n, 3) and exact (n, >= 3)")
+    if dev and ((hasattr(x_trials, "is_contiguous") and not x_trials.is_contiguous()) or _np_dtype(exact) != np.float64):
+        raise ValueError("device x_trials must be contiguous and exact float64")
+    trials, n = shape[0], shape[1]
+    means = _out(dev, n, 3, np.float64, None)
+    covars = DeviceArray((n, 3, 3), np.float64) if dev else np.empty((n, 3, 3))
+    check(lib().trgl_vector_stat(_ptr(x_trials), _ptr(exact), int(exact.shape[1]), trials, _ptr(means), _ptr(covars), n,
+                                 int(_np_dtype(x_trials) == np.float32), MEM_DEVICE if dev else MEM_HOST, stream))
+    return means, covars
+
+
 def median(values, stream=None):
     """np.median of non-negative float64 values (host array or device buffer), exact."""
     dev = _is_device(values)
@@ -813,6 +893,13 @@ def set_stream_variant(v):
 def set_deferred_capacity(max_points):
     """Test knob: limit of the deferred-point list of the hot kernels (default 2**26); returns the old limit."""
     return lib().trgl_set_deferred_capacity(int(max_points))
+
+
+def deferred_total(stream=None):
+    """Running total of the points the hot kernels have deferred to their follow-up kernels on this device / stream."""
+    v = ctypes.c_int64(0)
+    check(lib().trgl_deferred_total(stream, ctypes.byref(v)))
+    return int(v.value)
 
 
 def set_two_ray(enabled):

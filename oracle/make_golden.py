@@ -5,6 +5,8 @@ Generate the committed parity fixtures under tests/golden/ (run in the build con
 
 1. ref_py_<rig>.npz : per-point inputs and the outputs of the reference's own pure-Python solvers
    (Work/python_libs/triangulation.py:1-233 exec'd unmodified, cv2 4.13) on seeded synthetic batches.
+6. vector_stat_cells.npz : the reference's stored vector_stat results (per-point mean / covariance of the 3-D error vectors
+   over the trials of a trajectory's last pose) from test_1and2.mat.
 2. golden_cells.json : sampled cells of the reference's golden result files
    Work/triangulation_comparison/{test_1and2,test_3}.mat and figures_scene/test_1and2.mat (numbers
    only), with the trajectory tables needed to replay them.
@@ -110,6 +112,22 @@ def golden_cells():
     print("wrote golden_cells.json")
 
 
+def vector_stat_fixture():
+    """6. vector_stat_cells.npz : per-point mean vector / covariance matrix of the 3-D error vectors over the 100 trials of
+    the LAST pose of a trajectory (triangulation_comparison.py:483-487, vector_stat :219-240), as stored by the reference
+    in test_1and2.mat (p_err3Dv_mean_summary, p_err3Dv_covar_summary), for linear_LS and iterative_LS."""
+    m = sio.loadmat(os.path.join(REFERENCE_ROOT, "Work/triangulation_comparison", "test_1and2.mat"))
+    methods = [s.strip() for s in m["triangl_methods"]]
+    out = {"methods": np.array(methods), "trajs": np.array([0, 3, 4])}
+    for t in (0, 3, 4):
+        for name in ("linear_LS_triangulation", "iterative_LS_triangulation"):
+            ti = methods.index(name)
+            out["mean_%d_%s" % (t, name)] = m["p_err3Dv_mean_summary"][t, ti]
+            out["covar_%d_%s" % (t, name)] = m["p_err3Dv_covar_summary"][t, ti]
+    np.savez_compressed(os.path.join(GOLDEN, "vector_stat_cells.npz"), **out)
+    print("wrote vector_stat_cells.npz", methods)
+
+
 def cv2_undistort_fixture():
     """3. cv2_undistort.npz : cv2.undistortPoints (OpenCV 4.13, the executable third-party statement of the call at
     slam2.py:551-552) on seeded pixel points, float64 and float32, for several distortion models."""
@@ -199,7 +217,10 @@ if __name__ == "__main__":
         cv2_undistort_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "slam":
         slam_replay_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "vector_stat":
+        vector_stat_fixture()
     else:
+        vector_stat_fixture()
         per_point_fixtures()
         golden_cells()
         cv2_undistort_fixture()

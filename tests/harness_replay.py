@@ -24,8 +24,17 @@ def robustness_stat(errors, statuses):                          # :242-260
     return np.mean(fp), np.mean(fn)
 
 
+def vector_stat(error_vectors):                                 # :219-240
+    """Mean vector and (population) covariance matrix over the trials, per point.  error_vectors: (num_trials, N, d)."""
+    ev = np.asarray(error_vectors, dtype=np.float64)
+    means = ev.mean(axis=0)
+    dev = ev - means[None]
+    covars = np.einsum('tni,tnj->nij', dev, dev) / ev.shape[0]
+    return means, covars
+
+
 def replay_cell(solvers, pose, points_3D=None, num_trials=100, rseed=rig.RSEED, sigma=0.8, discretized=True,
-                k1=0.3, offset=40.):
+                k1=0.3, offset=40., return_vectors=False, on_trial=None):
     """
     solvers: list of callables (u1, P1, u2, P2) -> (x, status).  pose = (sideways, towards, angle) of cam 2.
     Returns a dict of the six summary statistics, each a list over solvers.
@@ -47,6 +56,8 @@ def replay_cell(solvers, pose, points_3D=None, num_trials=100, rseed=rig.RSEED, 
         u2 = cam2.normalized_points()
         for ti, solver in enumerate(solvers):
             x, status = solver(u1, cam1.P, u2, cam2.P)
+            if on_trial is not None:
+                on_trial(ti, x, status)                                              # e.g. device-side accumulation
             x = np.asarray(x, dtype=np.float64)
             errs3D[ti].append(x - points_3D[:, 0:3])                                 # :179-188
             xh = np.concatenate([x, np.ones((len(x), 1))], axis=1)
@@ -63,4 +74,6 @@ def replay_cell(solvers, pose, points_3D=None, num_trials=100, rseed=rig.RSEED, 
             fp, fn = robustness_stat(errors, statuses[ti])
         for k, v in zip(out, (m3, md3, m2, md2, fp, fn)):
             out[k].append(float(v))
+    if return_vectors:
+        out["error_vectors_3D"] = [np.array(e) for e in errs3D]                     # errors_partitioned, :483
     return out

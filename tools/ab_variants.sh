@@ -10,7 +10,7 @@ mkdir -p $OUT
 for LIB in default variants/*.so; do
   NAME=$(basename $LIB .so)
   if [ "$LIB" = default ]; then unset TRGL_CUDA_LIB; else export TRGL_CUDA_LIB=$PWD/$LIB; fi
-  timeout 300 python tools/sweep_kernels.py --points $N --solvers $SOLVERS --modes f64 --variants 0 --ppts 4 --rig ${RIG:-rotating} \
+  timeout 300 python tools/sweep_kernels.py --points $N --solvers $SOLVERS --modes f64 --variants 0 --ppts 4 --rig ${RIG:-rotating} ${SWEEP_FLAGS:-} \
       > $OUT/sweep_$NAME.jsonl 2> $OUT/sweep_$NAME.err
   echo "== $NAME"; cut -c1-260 $OUT/sweep_$NAME.jsonl; tail -2 $OUT/sweep_$NAME.err
 done

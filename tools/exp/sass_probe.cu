@@ -1,0 +1,17 @@
+// Static inspection TU: instantiates the FP64 hot kernels only, so that ptxas -v and cuobjdump -sass answer in seconds
+// (tools/sass_count.sh).
+#include "../../multiple-quadrotor-slam_b200/csrc/trgl_kernels.cuh"
+using namespace trgl;
+#ifndef PROBE_EVAL
+#define PROBE_EVAL true
+#endif
+const void* probe_table[] = {
+    reinterpret_cast<const void*>(&k_linear_eigen<double, double, double, 4, PreNone, PROBE_EVAL>),
+    reinterpret_cast<const void*>(&k_polynomial<double, double, double, 4, PreNone, PROBE_EVAL>),
+    reinterpret_cast<const void*>(&k_iterative_ls<double, double, double, PreNone, PROBE_EVAL>),
+    reinterpret_cast<const void*>(&k_linear_ls<double, double, double, 4, PreNone, PROBE_EVAL, Mirrors, true>),
+    reinterpret_cast<const void*>(&k_linear_ls<double, double, double, 4, PreNone, false, NoMirrors, true>),
+    reinterpret_cast<const void*>(&k_linear_eigen_general<double, double, double, 4, PreNone, PROBE_EVAL>),
+    reinterpret_cast<const void*>(&k_polynomial_general<double, double, double, 4, PreNone, PROBE_EVAL>),
+    reinterpret_cast<const void*>(&k_linear_ls_f32x4),
+};

@@ -20,6 +20,7 @@ ap.add_argument("--ppts", default="1,2,4")
 ap.add_argument("--variants", default="0")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--rig", default="rotating")
+ap.add_argument("--eval", action="store_true", help="with the fused evaluation epilogue (good mask written), as bench.py runs the solvers")
 args = ap.parse_args()
 
 n = args.points
@@ -44,8 +45,10 @@ for mode in args.modes.split(","):
             if ppt:
                 tc.set_points_per_thread(ppt)
 
+            fe = tc.FusedEval(n, dt, 0, (2.0 / 480) ** 2, want_errors=False, want_good=True) if args.eval else None
+
             def launch():
-                kw = dict(out_dtype=dt, compute_dtype=dt, x=x)
+                kw = dict(out_dtype=dt, compute_dtype=dt, x=x, evaluate=fe)
                 if solver == "linear_LS":
                     tc.linear_ls(d1, P1, d2, P2, status=sb, **kw)
                 elif solver == "iterative_LS":
@@ -54,9 +57,11 @@ for mode in args.modes.split(","):
                     tc.linear_eigen(d1, P1, d2, P2, status=sb, **kw)
                 else:
                     tc.polynomial(d1, P1, d2, P2, status=sb, check_all_nan=False, **kw)
+            d0 = tc.deferred_total()
             for _ in range(3):
                 launch()
             tc.synchronize()
+            deferred = (tc.deferred_total() - d0) / 3.0
             if solver == "linear_LS":       # every input path must give the same bits as the per-thread-load kernel
                 chk = x.to_host()[:: max(1, n // 200000)]
                 if (variant, ppt) == cfgs[0]:
@@ -70,7 +75,7 @@ for mode in args.modes.split(","):
             ms = np.array([e[i].elapsed_ms(e[i + 1]) for i in range(args.iters)])
             bpp = 4 * isz + 3 * isz + (4 if solver == "iterative_LS" else 1)
             gbs = bpp * n / (np.median(ms) * 1e-3) / 1e9
-            print(json.dumps({"solver": solver, "mode": mode, "variant": variant, "ppt": ppt, "n": n, "ms_median": float(np.median(ms)),
+            print(json.dumps({"solver": solver, "eval": bool(args.eval), "mode": mode, "variant": variant, "ppt": ppt, "n": n, "deferred_per_call": deferred, "ms_median": float(np.median(ms)),
                               "ms_min": float(ms.min()), "pts_per_s": n / (np.median(ms) * 1e-3), "alg_GBs": gbs,
                               "frac_of_6543": gbs / peak}))
     del d1, d2, x, sb, si
