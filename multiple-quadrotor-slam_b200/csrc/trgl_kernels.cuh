@@ -150,6 +150,11 @@ __device__ __forceinline__ int tworay_step(const T d11, const T d12, const T d21
 // ~120-register path -- and the subroutine calls of its SVD tier -- out of the hot kernels is what lets them run without
 // a single spill and at 3 CTAs per SM: with the call inside, ptxas kept the loop state of the persistent loop in local
 // memory (profiles/r01f).
+// First instruction of every follow-up kernel: wait until the grid this one depends on (the hot kernel, launched just before
+// on the same stream) has completed and flushed its writes.  A no-op when the kernel was launched without the
+// programmatic-dependent-launch attribute.
+__device__ __forceinline__ void wait_for_hot_kernel() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct Deferred {
     int64_t* idx;                 // [cap] indices of the points to redo
     unsigned int* ctl;            // ctl[0] = number of deferred points (may exceed cap), ctl[1] = ticket of the follow-up kernel,
@@ -240,12 +245,24 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
 // ---- linear_LS, FP32 mode: four CONSECUTIVE points per thread, 128-bit loads and stores --------------------------------
 // At 29 bytes per point the FP32 mode is bound by instruction issue, not by HBM, unless the per-point overhead goes: here a
 // thread loads its four (x,y) pairs of each view as two float4, solves them with float32 normal equations (no refinement:
-// tier-1 points only, the rest is deferred to k_linear_ls_general<float>), and writes its 12 result floats as three float4
+// tier-1 points only), and writes its 12 result floats as three float4
 // and its four status bytes as one 32-bit word -- no shared-memory transposition, no per-point address arithmetic.
 // Needs 16-byte aligned u1 / u2 / x and 4-byte aligned status (the launcher checks); the last < 4 points take scalar accesses.
-__global__ void __launch_bounds__(kThreads, 4)
+// A point beyond float32 tier 1 (kappa^2 bound >= 300: low parallax, e.g. the whole forward-motion rig) is redone right here
+// with float64 normal equations on the float32 inputs -- a rig-uniform branch, out of line so that it costs the common path
+// no registers -- and only what is beyond the float64 tier 1 as well goes to the follow-up kernel.
+__device__ __noinline__ bool ls_point_f32_redo_in_double(const Cams<double>& camsd, float a, float b, float c, float d, float x[3]) {
+    double xd[3];
+    const bool ok = ls_point_fast<double>(camsd, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c),
+                                          static_cast<double>(d), xd);
+    x[0] = static_cast<float>(xd[0]); x[1] = static_cast<float>(xd[1]); x[2] = static_cast<float>(xd[2]);
+    return ok;
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
 k_linear_ls_f32x4(const float* __restrict__ u1, const float* __restrict__ u2, const __grid_constant__ Cams<float> cams,
-                  float* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ Deferred df) {
+                  const __grid_constant__ Cams<double> camsd, float* __restrict__ x, uint8_t* __restrict__ status,
+                  const int64_t n, const __grid_constant__ Deferred df) {
     const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * 4;
     if (i0 >= n) return;
     float in1[8], in2[8], xs[4][3];
@@ -266,6 +283,11 @@ k_linear_ls_f32x4(const float* __restrict__ u1, const float* __restrict__ u2, co
     bool ok[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) ok[p] = ls_point_plain_f32(cams, in1[2 * p], in1[2 * p + 1], in2[2 * p], in2[2 * p + 1], xs[p]);
+    if (!(ok[0] && ok[1] && ok[2] && ok[3])) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (!ok[p]) ok[p] = ls_point_f32_redo_in_double(camsd, in1[2 * p], in1[2 * p + 1], in2[2 * p], in2[2 * p + 1], xs[p]);
+    }
     if (full) {
         float4* dst = reinterpret_cast<float4*>(x + 3 * i0);
         __stcs(dst + 0, make_float4(xs[0][0], xs[0][1], xs[0][2], xs[1][0]));
@@ -689,6 +711,7 @@ k_iterative_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const 
                     TO* __restrict__ x, int32_t* __restrict__ status, const int64_t n, const TC tolerance,
                     const int py_semantics, const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
                     const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df, const int all) {
+    wait_for_hot_kernel();
     const unsigned int listed = all ? 0u : df.ctl[0];
     const bool everything = all || listed > df.cap;
     const int64_t total = everything ? n : static_cast<int64_t>(listed);
@@ -721,6 +744,7 @@ k_linear_ls_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const 
                     TO* __restrict__ x, const int64_t n, const __grid_constant__ PRE pre_stage,
                     const __grid_constant__ Mirrors mir, const __grid_constant__ EvalArg<EVAL> ev,
                     const __grid_constant__ Deferred df) {
+    wait_for_hot_kernel();
     const unsigned int listed = df.ctl[0];
     const bool everything = listed > df.cap;
     const int64_t total = everything ? n : static_cast<int64_t>(listed);
@@ -843,7 +867,7 @@ __device__ __forceinline__ int ldl4(const T S[10], const T b[4], T y[4]) {
 
 // Fast path: Rayleigh-quotient iteration on G = B^T B started from the least-squares point (which is within noise
 // of the answer), with a certificate: (i) ||G X - lam X|| <= 4 eps tr(G) and (ii) exactly one eigenvalue of G lies below
-// lam + gap*tr(G) (inertia of the shifted matrix), gap = max(2e-5, 5e-6 / |w|).  (i)+(ii) prove X is the eigenvector of the smallest eigenvalue and that
+// lam + gap*tr(G) (inertia of the shifted matrix), gap = 5e-6 / |w|.  (i)+(ii) prove X is the eigenvector of the smallest eigenvalue and that
 // it is separated well enough for the G-based computation to be accurate to ~1e-12; otherwise the caller falls back to
 // the Jacobi SVD.  ~450 FP64 instructions instead of ~4800.
 // SYNC: the caller guarantees that all 32 lanes of the warp are here (the hot kernel); the warp is then re-converged
@@ -909,9 +933,9 @@ __device__ __forceinline__ bool eigen_point_fast(const Cams<TC>& cams, TC u1x, T
     // Required separation of the two smallest eigenvalues, relative to tr(G).  The entries of G carry ~4 eps tr(G) of
     // rounding, which moves the eigenvector by 4 eps tr / (lam3 - lam4) and the DEHOMOGENISED point by 1/|w| times that
     // (w = X[3] of the unit vector): measured on the forward-motion rig, 4 eps / (gap |w|) to within 10 % on the 51 of
-    // 10 M points that exceeded 1e-9 with the fixed gap 2e-5 (|w| 1e-4 .. 0.04: points far behind the scene).  So the gap
-    // scales with 1/|w| beyond |w| = 0.25 (error bound 2e-10); such points go to the Jacobi SVD like the other deferred ones.
-    const TC gap_rel = sizeof(TC) == 8 ? tmax(TC(2e-5), TC(5e-6) * fast_rcp(tabs(X[3]))) : TC(2e-3);
+    // 10 M points that exceeded 1e-9 with a fixed gap of 2e-5 (|w| 1e-4 .. 0.04: points far behind the scene).  So the
+    // required gap is 5e-6 / |w| (error bound 4 eps / 5e-6 = 1.8e-10); below it the point takes the Jacobi SVD.
+    const TC gap_rel = sizeof(TC) == 8 ? TC(5e-6) * fast_rcp(tabs(X[3])) : TC(2e-3);
     const TC shift = tfma(gap_rel, tr, lam);
     S[0] -= shift; S[4] -= shift; S[7] -= shift; S[9] -= shift;
     return (ldl4<TC, false>(S, X, X) == 1) && conv && (gap_rel == gap_rel);
@@ -998,35 +1022,43 @@ __device__ __forceinline__ bool eigen_point_warp(const Cams<TC>& cams, TC u1x, T
     const TC tol = TC(4) * Num<TC>::eps() * tr;
     TC lam = 0;
     bool alive = true, conv = false;
-#pragma unroll 1
-    for (int round = 0; round <= kEigenMaxRounds; ++round) {
-        TC y[4];
+    // one round: Rayleigh quotient of the (unit, to 1e-12) iterate, shifted solve, normalisation
+    auto rqi_round = [&](const TC (&y)[4]) {
+        lam = tfma(X[0], y[0], tfma(X[1], y[1], tfma(X[2], y[2], X[3] * y[3])));
+        TC S[10], z[4];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) S[k] = G[k];
+        S[0] -= lam; S[4] -= lam; S[7] -= lam; S[9] -= lam;
+        alive = ldl4_direction<TC>(S, X, z) && alive;
+        const TC nrm = fast_rsqrt(tfma(z[0], z[0], tfma(z[1], z[1], tfma(z[2], z[2], z[3] * z[3]))));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) X[k] = z[k] * nrm;
+    };
+    auto matvec = [&](TC (&y)[4]) {
         y[0] = tfma(G[0], X[0], tfma(G[1], X[1], tfma(G[2], X[2], G[3] * X[3])));
         y[1] = tfma(G[1], X[0], tfma(G[4], X[1], tfma(G[5], X[2], G[6] * X[3])));
         y[2] = tfma(G[2], X[0], tfma(G[5], X[1], tfma(G[7], X[2], G[8] * X[3])));
         y[3] = tfma(G[3], X[0], tfma(G[6], X[1], tfma(G[8], X[2], G[9] * X[3])));
-        lam = tfma(X[0], y[0], tfma(X[1], y[1], tfma(X[2], y[2], X[3] * y[3])));      // ||X|| = 1 to 1e-12: fine for a shift
-        if (round >= 2) {                                  // the LS start and the first iterate are never converged
-            const TC xx = tfma(X[0], X[0], tfma(X[1], X[1], tfma(X[2], X[2], X[3] * X[3])));
-            lam *= fast_rcp(xx);                           // the exact Rayleigh quotient for the residual test
-            TC rn = 0;
+    };
+    TC y[4];
+    // the LS start and the first iterate are never converged: two rounds straight-line, then test / vote / continue
+    matvec(y); rqi_round(y);
+    matvec(y); rqi_round(y);
+#pragma unroll 1
+    for (int round = 2;; ++round) {
+        matvec(y);
+        const TC xx = tfma(X[0], X[0], tfma(X[1], X[1], tfma(X[2], X[2], X[3] * X[3])));
+        lam = tfma(X[0], y[0], tfma(X[1], y[1], tfma(X[2], y[2], X[3] * y[3]))) * fast_rcp(xx);     // exact Rayleigh quotient
+        TC rn = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { const TC r = tfma(-lam, X[k], y[k]); rn = tfma(r, r, rn); }
-            conv = rn <= tol * tol * xx;
-            const unsigned open = __ballot_sync(0xffffffffu, alive && !conv);
-            if (__popc(open) <= kEigenStragglers || round == kEigenMaxRounds) break;       // warp-uniform
-        }
-        TC S[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) S[k] = G[k];
-        S[0] -= lam; S[4] -= lam; S[7] -= lam; S[9] -= lam;
-        alive = ldl4_direction<TC>(S, X, y) && alive;
-        const TC nrm = fast_rsqrt(tfma(y[0], y[0], tfma(y[1], y[1], tfma(y[2], y[2], y[3] * y[3]))));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) X[k] = y[k] * nrm;
+        for (int k = 0; k < 4; ++k) { const TC r = tfma(-lam, X[k], y[k]); rn = tfma(r, r, rn); }
+        conv = rn <= tol * tol * xx;
+        const unsigned open = __ballot_sync(0xffffffffu, alive && !conv);
+        if (__popc(open) <= kEigenStragglers || round == kEigenMaxRounds) break;           // warp-uniform
+        rqi_round(y);
     }
     // certificate: exactly one eigenvalue of G below lam + gap tr(G)   (see eigen_point_fast)
-    const TC gap_rel = sizeof(TC) == 8 ? tmax(TC(2e-5), TC(5e-6) * fast_rcp(tabs(X[3]))) : TC(2e-3);
+    const TC gap_rel = sizeof(TC) == 8 ? TC(5e-6) * fast_rcp(tabs(X[3])) : TC(2e-3);
     const TC shift = tfma(gap_rel, tr, lam);
     TC S[10], dummy[4];
 #pragma unroll
@@ -1113,6 +1145,7 @@ k_linear_eigen_general(const TI* __restrict__ u1, const TI* __restrict__ u2, con
                        TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const TC max_coord,
                        const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
                        const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df) {
+    wait_for_hot_kernel();
     const unsigned int listed = df.ctl[0];
     const bool everything = listed > df.cap;
     const int64_t total = everything ? n : static_cast<int64_t>(listed);
@@ -1223,6 +1256,7 @@ k_polynomial_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const
                      TI* __restrict__ u1c, TI* __restrict__ u2c, unsigned int* __restrict__ not_nan_count, const int64_t n,
                      const TC max_coord, const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
                      const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df, const int all) {
+    wait_for_hot_kernel();
     const unsigned int listed = all ? 0u : df.ctl[0];
     const bool everything = all || listed > df.cap;
     const int64_t total = everything ? n : static_cast<int64_t>(listed);

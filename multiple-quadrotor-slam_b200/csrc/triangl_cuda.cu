@@ -16,6 +16,7 @@
 #include <string>
 #include <type_traits>
 #include <unordered_map>
+#include <utility>
 
 using namespace trgl;
 
@@ -122,6 +123,24 @@ RayGeom<T> make_ray_geom(const double* P1, const double* P2) {
     return g;
 }
 
+// Follow-up kernels are launched with programmatic dependent launch (PDL): the launch itself -- ~4 us of latency, as long as
+// the hot kernel of a SLAM-sized batch runs -- overlaps the hot kernel, and the follow-up kernel waits at its first
+// instruction (griddepcontrol.wait) until the hot kernel has completed and its writes (results, deferred list) are visible.
+template <typename... KArgs, typename... Args>
+void launch_followup(void (*kern)(KArgs...), unsigned grid, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
+// Grid cap of the follow-up kernels, in CTAs per SM: they loop over the deferred list with a grid stride, so a batch that
+// defers nothing pays for ceil(n / 256) (at most this many) empty CTAs, and a rig that defers most of its points (forward
+// motion: 20 % in linear_eigen, everything in FP32-mode linear_LS) still fills the machine.
+constexpr int kFollowupCtasPerSm = 8;
 inline unsigned grid_for(int64_t n, int per_block) { return static_cast<unsigned>((n + per_block - 1) / per_block); }
 
 // Reduction scratch (per-block partial sums, the polynomial NaN flags, the last-block ticket) is owned per
@@ -267,11 +286,11 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
         const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
         const Cams<float> cams = make_cams<float>(P1, P2);
         const float* a = static_cast<const float*>(u1); const float* b = static_cast<const float*>(u2);
-        k_linear_ls_f32x4<<<grid_for((n + 3) / 4, kThreads), kThreads, 0, s>>>(a, b, cams, static_cast<float*>(x), status, n, df);
+        k_linear_ls_f32x4<<<grid_for((n + 3) / 4, kThreads), kThreads, 0, s>>>(a, b, cams, make_cams<double>(P1, P2), static_cast<float*>(x), status, n, df);
         const int64_t tiles = (n + kThreads - 1) / kThreads;
-        const int64_t cap = 2 * static_cast<int64_t>(sm_count());
-        k_linear_ls_general<float, float, float, PreNone, false><<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
-            a, b, cams, static_cast<float*>(x), n, PreNone{}, kNoMirrors, EvalArg<false>{}, df);
+        const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
+        launch_followup(k_linear_ls_general<float, float, float, PreNone, false>, static_cast<unsigned>(tiles < cap ? tiles : cap), s,
+                        a, b, cams, static_cast<float*>(x), n, PreNone{}, kNoMirrors, EvalArg<false>{}, df);
         g_launches += 2;
         CK(cudaGetLastError());
         return TRGL_OK;
@@ -330,10 +349,10 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
                         }
                         if (defer) {
                             const int64_t tiles = (n + kThreads - 1) / kThreads;
-                            const int64_t cap = 2 * static_cast<int64_t>(sm_count());
+                            const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
                             const unsigned fgrid = static_cast<unsigned>(tiles < cap ? tiles : cap);
-                            if (pre) k_linear_ls_general<TI, TC, TO, PreUndistort, EV><<<fgrid, kThreads, 0, s>>>(a, b, cams, xo, n, PreUndistort{*pre}, mir, evarg, df);
-                            else k_linear_ls_general<TI, TC, TO, PreNone, EV><<<fgrid, kThreads, 0, s>>>(a, b, cams, xo, n, PreNone{}, mir, evarg, df);
+                            if (pre) launch_followup(k_linear_ls_general<TI, TC, TO, PreUndistort, EV>, fgrid, s, a, b, cams, xo, n, PreUndistort{*pre}, mir, evarg, df);
+                            else launch_followup(k_linear_ls_general<TI, TC, TO, PreNone, EV>, fgrid, s, a, b, cams, xo, n, PreNone{}, mir, evarg, df);
                             g_launches++;
                         }
                     }
@@ -376,9 +395,9 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
                         kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
                             a, b, cams, geom, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df);
                         const int64_t tiles = (n + kThreads - 1) / kThreads;
-                        const int64_t cap = 2 * static_cast<int64_t>(sm_count());
-                        general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
-                            a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df, 0);
+                        const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
+                        launch_followup(general, static_cast<unsigned>(tiles < cap ? tiles : cap), s,
+                                        a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df, 0);
                         nlaunch = 2;
                     } else {
                         // no finite camera centre / closed forms switched off: the reference's loop for every point
@@ -418,8 +437,8 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
                     // hot kernel (Rayleigh-quotient iteration, certified) + follow-up over the points it deferred (Jacobi SVD)
                     auto launch = [&](auto kern, auto general) {
                         kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
-                        const int64_t cap = 2 * static_cast<int64_t>(sm_count());
-                        general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
+                        const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
+                        launch_followup(general, static_cast<unsigned>(tiles < cap ? tiles : cap), s, a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
                     };
                     if (rows == 4) launch(k_linear_eigen<TI, TC, TO, 4, PRE, EV>, k_linear_eigen_general<TI, TC, TO, 4, PRE, EV>);
                     else launch(k_linear_eigen<TI, TC, TO, 6, PRE, EV>, k_linear_eigen_general<TI, TC, TO, 6, PRE, EV>);
@@ -459,8 +478,8 @@ int launch_polynomial(const void* u1, const void* u2, const double* P1, const do
                         if (closed_form) {
                             // hot kernel (certified correction + ray intersection) + follow-up over the points it deferred
                             kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, geom, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
-                            const int64_t cap = 2 * static_cast<int64_t>(sm_count());
-                            general<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 0);
+                            const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
+                            launch_followup(general, static_cast<unsigned>(tiles < cap ? tiles : cap), s, a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 0);
                             nlaunch = 2;
                         } else {
                             // no finite camera centre / closed forms switched off: the complete per-point path for every point
@@ -1032,19 +1051,25 @@ static int launch_multiview_ls(void* const* u, void* const* valid, const double*
             }
             args.m = m; args.min_views = min_views;
             const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+            auto go = [&](auto kern, int per_block) {
+                const int64_t tiles = (n + per_block - 1) / per_block;
+                kern<<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(args, static_cast<TO*>(x), status, n, df);
+            };
+            const bool masked = valid != nullptr;
             if (m <= 4) {
-                const int64_t tiles = (n + 2 * kThreads - 1) / (2 * kThreads);
-                k_multiview_ls<TI, TC, TO, 2, 4><<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
-                    args, static_cast<TO*>(x), status, n, df);
+                if (masked) go(k_multiview_ls<TI, TC, TO, 2, 4, 1, true>, 2 * kThreads);
+                else go(k_multiview_ls<TI, TC, TO, 2, 4, 1, false>, 2 * kThreads);
+            } else if (m <= 8) {
+                if (masked) go(k_multiview_ls<TI, TC, TO, 1, 8, 1, true>, kThreads);
+                else go(k_multiview_ls<TI, TC, TO, 1, 8, 1, false>, kThreads);
             } else {
-                const int64_t tiles = (n + kThreads - 1) / kThreads;
-                k_multiview_ls<TI, TC, TO, 1, 8><<<static_cast<unsigned>(tiles < cap ? tiles : cap), kThreads, 0, s>>>(
-                    args, static_cast<TO*>(x), status, n, df);
+                if (masked) go(k_multiview_ls<TI, TC, TO, 1, 8, 2, true>, kThreads);
+                else go(k_multiview_ls<TI, TC, TO, 1, 8, 2, false>, kThreads);
             }
             const int64_t ftiles = (n + kThreads - 1) / kThreads;
-            const int64_t fcap = 2 * static_cast<int64_t>(sm_count());
-            k_multiview_general<TI, TC, TO><<<static_cast<unsigned>(ftiles < fcap ? ftiles : fcap), kThreads, 0, s>>>(
-                args, static_cast<TO*>(x), n, df);
+            const int64_t fcap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
+            launch_followup(k_multiview_general<TI, TC, TO>, static_cast<unsigned>(ftiles < fcap ? ftiles : fcap), s,
+                            args, static_cast<TO*>(x), n, df);
         } else {
             rc = fail(TRGL_E_BADARG, "multi-view triangulation computes in float64");
         }

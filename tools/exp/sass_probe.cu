@@ -1,6 +1,7 @@
 // Static inspection TU: instantiates the FP64 hot kernels only, so that ptxas -v and cuobjdump -sass answer in seconds
 // (tools/sass_count.sh).
 #include "../../multiple-quadrotor-slam_b200/csrc/trgl_kernels.cuh"
+#include "../../multiple-quadrotor-slam_b200/csrc/trgl_multiview.cuh"
 using namespace trgl;
 #ifndef PROBE_EVAL
 #define PROBE_EVAL true
@@ -14,4 +15,6 @@ const void* probe_table[] = {
     reinterpret_cast<const void*>(&k_linear_eigen_general<double, double, double, 4, PreNone, PROBE_EVAL>),
     reinterpret_cast<const void*>(&k_polynomial_general<double, double, double, 4, PreNone, PROBE_EVAL>),
     reinterpret_cast<const void*>(&k_linear_ls_f32x4),
+    reinterpret_cast<const void*>(&k_multiview_ls<double, double, double, 1, 8, 1, true>),
+    reinterpret_cast<const void*>(&k_multiview_ls<double, double, double, 1, 8, 1, false>),
 };
