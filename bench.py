@@ -678,11 +678,15 @@ def run_slam(args):
                 return 1e6 * float(np.median(ts)), 1e6 * float(np.percentile(ts, 95))
             l0 = tc.launch_count()
             d_med, d_p95 = timed(dropin, args.steps)
+            tc.set_trace(1); tc.get_trace()
             f_med, f_p95 = timed(fused, args.steps)
+            tr = tc.get_trace(); tc.set_trace(0)
             launches = tc.launch_count() - l0
             assert np.array_equal(dropin(), fused())
             row = {"dropin_us": d_med, "dropin_p95_us": d_p95, "fused_us": f_med, "fused_p95_us": f_p95,
-                   "fused_points_per_sec": 2 * B / (f_med * 1e-6), "gpu_launches": launches}
+                   "fused_points_per_sec": 2 * B / (f_med * 1e-6), "gpu_launches": launches,
+                   # mean host microseconds per library call of the fused path, by phase (2 calls per keyframe)
+                   "fused_call_breakdown_us": {k: (v / max(tr["calls"], 1.0)) for k, v in tr.items() if k != "calls"}}
             if not args.no_cpu_baseline:
                 from oracle import oracle_c
                 try:

@@ -300,6 +300,11 @@ int64_t trgl_set_deferred_capacity(int64_t max_points);
  * (current device, stream) since the library was loaded (bench.py reports the deferred fraction per solver with it).
  * Synchronises the stream. */
 int trgl_deferred_total(void* stream, int64_t* total);
+/* Diagnostics of the small-batch host path (n <= 32 Ki points: the SLAM keyframe sizes).  trgl_set_trace(1) makes every such
+ * call add its host-side microseconds per phase to five accumulators -- staging memcpy in, kernel launches, stream
+ * synchronise, memcpy out, number of calls -- which trgl_get_trace copies to out5 and clears.  Returns the previous setting. */
+int trgl_set_trace(int enabled);
+int trgl_get_trace(double* out5);
 
 #ifdef __cplusplus
 }

@@ -245,13 +245,15 @@ k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_c
 // ---- linear_LS, FP32 mode: four CONSECUTIVE points per thread, 128-bit loads and stores --------------------------------
 // At 29 bytes per point the FP32 mode is bound by instruction issue, not by HBM, unless the per-point overhead goes: here a
 // thread loads its four (x,y) pairs of each view as two float4, solves them with float32 normal equations (no refinement:
-// tier-1 points only), and writes its 12 result floats as three float4
+// tier-1 points only -- kappa^2 bound below 300; the rest is deferred to k_linear_ls_general<float, double, float>, which
+// redoes it in float64 on the float32 inputs: e.g. every point of the low-parallax forward-motion rig), and writes its 12 result floats as three float4
 // and its four status bytes as one 32-bit word -- no shared-memory transposition, no per-point address arithmetic.
 // Needs 16-byte aligned u1 / u2 / x and 4-byte aligned status (the launcher checks); the last < 4 points take scalar accesses.
-// A point beyond float32 tier 1 (kappa^2 bound >= 300: low parallax, e.g. the whole forward-motion rig) is redone right here
-// with float64 normal equations on the float32 inputs -- a rig-uniform branch, out of line so that it costs the common path
-// no registers -- and only what is beyond the float64 tier 1 as well goes to the follow-up kernel.
-__device__ __noinline__ bool ls_point_f32_redo_in_double(const Cams<double>& camsd, float a, float b, float c, float d, float x[3]) {
+#ifndef TRGL_F32_REDO
+#define TRGL_F32_REDO 0
+#endif
+// Cold path of the FP32 mode (TRGL_F32_REDO): a point beyond float32 tier 1 redone with float64 normal equations in place.
+__device__ __noinline__ bool ls_point_f32_redo_in_double(const Cams<double>& camsd, float a, float b, float c, float d, float* x) {
     double xd[3];
     const bool ok = ls_point_fast<double>(camsd, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c),
                                           static_cast<double>(d), xd);
@@ -259,7 +261,7 @@ __device__ __noinline__ bool ls_point_f32_redo_in_double(const Cams<double>& cam
     return ok;
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 k_linear_ls_f32x4(const float* __restrict__ u1, const float* __restrict__ u2, const __grid_constant__ Cams<float> cams,
                   const __grid_constant__ Cams<double> camsd, float* __restrict__ x, uint8_t* __restrict__ status,
                   const int64_t n, const __grid_constant__ Deferred df) {
@@ -283,11 +285,13 @@ k_linear_ls_f32x4(const float* __restrict__ u1, const float* __restrict__ u2, co
     bool ok[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) ok[p] = ls_point_plain_f32(cams, in1[2 * p], in1[2 * p + 1], in2[2 * p], in2[2 * p + 1], xs[p]);
+#if TRGL_F32_REDO
     if (!(ok[0] && ok[1] && ok[2] && ok[3])) {
 #pragma unroll
         for (int p = 0; p < 4; ++p)
             if (!ok[p]) ok[p] = ls_point_f32_redo_in_double(camsd, in1[2 * p], in1[2 * p + 1], in2[2 * p], in2[2 * p + 1], xs[p]);
     }
+#endif
     if (full) {
         float4* dst = reinterpret_cast<float4*>(x + 3 * i0);
         __stcs(dst + 0, make_float4(xs[0][0], xs[0][1], xs[0][2], xs[1][0]));
@@ -766,8 +770,8 @@ k_linear_ls_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const 
             in[p][0] = in[p][1] = in[p][2] = in[p][3] = TC(0);
             if (idx[p] >= 0) reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, idx[p], in[p][0], in[p][1], in[p][2], in[p][3]);
         }
-#pragma unroll 1
-        for (int p = 0; p < kBatch; ++p) {
+#pragma unroll
+        for (int p = 0; p < kBatch; ++p) {       // unrolled: a run-time p would put idx[] / in[][] into local memory
             const int64_t i = idx[p];
             if (i < 0) continue;
             TC xs[3];

@@ -83,10 +83,7 @@ __device__ __forceinline__ void multiview_point_careful(const MultiViewArgs<TI, 
 // anyway) are in flight per thread before the first row is built.  The launcher picks (2, 4) for m <= 4 and (1, 8) above.
 // NGROUPS = ceil(m / GROUP) is a template parameter so that every view index is a compile-time constant: the camera
 // matrices then are constant-bank operands of the FMA instructions instead of ~100 indexed constant loads per point.
-// MASKED = false (no visibility mask given): no mask loads, no selects.  MASKED = true: a masked view's rows are SELECTED
-// to zero (not multiplied: a NaN observation of a masked view must not poison the sums) and accumulated like the others,
-// so there is no divergent region per view -- with a branch per view the 70 %-visible 8-view case ran at 0.27 of the copy
-// peak (0.69 ms per 10 M points) against 0.72 unmasked.
+// MASKED = false (no visibility mask given): no mask loads.  MASKED = true: valid[v] is non-NULL for every view.
 template <typename TI, typename TC, typename TO, int PPT, int GROUP, int NGROUPS, bool MASKED>
 __global__ void __launch_bounds__(kThreads)
 k_multiview_ls(const __grid_constant__ MultiViewArgs<TI, TC> args, TO* __restrict__ x, uint8_t* __restrict__ status,
@@ -106,12 +103,17 @@ k_multiview_ls(const __grid_constant__ MultiViewArgs<TI, TC> args, TO* __restric
 #pragma unroll
             for (int k = 0; k < 3; ++k) v3[p][k] = TC(0);
         }
-#pragma unroll
+        // one group (m <= GROUP): every view index is a compile-time constant; more groups: a run-time loop over the groups
+        // (unrolling two groups of eight views keeps 2 x 64 camera constants live: spills, 0.45 of the copy peak at m = 16)
+#pragma unroll 1
         for (int g = 0; g < NGROUPS; ++g) {
-            constexpr int kDummy = 0; (void)kDummy;
-            const int v0 = g * GROUP;
+            const int v0 = NGROUPS == 1 ? 0 : g * GROUP;
             TC in[PPT][GROUP][2];
             uint8_t ok[PPT][GROUP];
+            // Straight-line loads: a view / point outside the batch reads element 0 of view 0 instead (and is switched off
+            // below), so there is no branch between the loads and all PPT * GROUP observation loads (+ mask bytes) are in
+            // flight together.  (With an `if (live)` block per view the compiler kept every mask load and the compare that
+            // consumes it inside that block: eight dependent memory latencies per tile, 0.28 of the copy peak.)
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
                 const int64_t i = base + p * kThreads + threadIdx.x;
@@ -119,25 +121,24 @@ k_multiview_ls(const __grid_constant__ MultiViewArgs<TI, TC> args, TO* __restric
                 for (int j = 0; j < GROUP; ++j) {
                     const int v = v0 + j;
                     const bool live = i < n && v < args.m;
-                    in[p][j][0] = in[p][j][1] = TC(0);
-                    ok[p][j] = live ? 1 : 0;
-                    if (live) {
-                        load_uv<TC>(args.u[v], i, in[p][j][0], in[p][j][1]);
-                        if constexpr (MASKED) { if (args.valid[v]) ok[p][j] = __ldcs(args.valid[v] + i); }
-                    }
+                    const int64_t ii = live ? i : 0;
+                    const int vv = live ? v : 0;
+                    load_uv<TC>(args.u[vv], ii, in[p][j][0], in[p][j][1]);
+                    uint8_t mk = 1;
+                    if constexpr (MASKED) mk = __ldcs(args.valid[vv] + ii);
+                    ok[p][j] = live ? mk : uint8_t(0);
                 }
             }
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
 #pragma unroll
                 for (int j = 0; j < GROUP; ++j) {
-                    TC r0[4], r1[4];
-                    dlt_rows<TC>(args.P[v0 + j], in[p][j][0], in[p][j][1], r0, r1);
-                    const bool on = ok[p][j] != 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { r0[k] = on ? r0[k] : TC(0); r1[k] = on ? r1[k] : TC(0); }
-                    normal_add2<TC>(r0, r1, M[p], v3[p]);
-                    nviews[p] += on ? 1 : 0;
+                    if (ok[p][j]) {
+                        TC r0[4], r1[4];
+                        dlt_rows<TC>(args.P[v0 + j], in[p][j][0], in[p][j][1], r0, r1);
+                        normal_add2<TC>(r0, r1, M[p], v3[p]);
+                        ++nviews[p];
+                    }
                 }
             }
         }

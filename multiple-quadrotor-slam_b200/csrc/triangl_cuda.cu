@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -289,8 +290,8 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
         k_linear_ls_f32x4<<<grid_for((n + 3) / 4, kThreads), kThreads, 0, s>>>(a, b, cams, make_cams<double>(P1, P2), static_cast<float*>(x), status, n, df);
         const int64_t tiles = (n + kThreads - 1) / kThreads;
         const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
-        launch_followup(k_linear_ls_general<float, float, float, PreNone, false>, static_cast<unsigned>(tiles < cap ? tiles : cap), s,
-                        a, b, cams, static_cast<float*>(x), n, PreNone{}, kNoMirrors, EvalArg<false>{}, df);
+        launch_followup(k_linear_ls_general<float, double, float, PreNone, false>, static_cast<unsigned>(tiles < cap ? tiles : cap), s,
+                        a, b, make_cams<double>(P1, P2), static_cast<float*>(x), n, PreNone{}, kNoMirrors, EvalArg<false>{}, df);
         g_launches += 2;
         CK(cudaGetLastError());
         return TRGL_OK;
@@ -618,6 +619,10 @@ constexpr int kMaxHostArrays = 2 * kMaxViews + 2;     // multi-view: m observati
 // device).  Inputs are memcpy'd into the staging block by the CPU, ONE kernel reads them over PCIe and writes x / status
 // back into the same block, one stream synchronise, CPU memcpy out: 1 launch + 1 sync instead of 4 copies + launch + sync.
 constexpr int64_t kZeroCopyMax = 32768;
+// trgl_set_trace(1): accumulate the host-side time of the small-batch path per phase (staging memcpy in, kernel launches,
+// stream synchronise, memcpy out, number of calls) -- read and cleared by trgl_get_trace (bench.py --workload slam).
+std::atomic<int> g_trace{0};
+double g_trace_us[5] = {0, 0, 0, 0, 0};
 char* g_zc_buf = nullptr;
 size_t g_zc_cap = 0;
 
@@ -640,6 +645,8 @@ int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
     bool caller_device_arrays = false;
     for (int a = 0; a < narrays; ++a) caller_device_arrays = caller_device_arrays || arrays[a].dev != nullptr;
     if (n <= kZeroCopyMax && !caller_device_arrays) {
+        const bool trace = g_trace.load(std::memory_order_relaxed) != 0;
+        const auto t0 = std::chrono::steady_clock::now();
         size_t total = 0;
         for (int a = 0; a < narrays; ++a) total += align256(arrays[a].bytes_per_point * n);
         int rc = ensure_zero_copy(total);
@@ -653,11 +660,20 @@ int host_pipeline(HostArray* arrays, int narrays, int64_t n, Launch launch) {
             pos += align256(arrays[a].bytes_per_point * n);
             if (arrays[a].in) std::memcpy(dptr[a], arrays[a].in, arrays[a].bytes_per_point * n);
         }
+        const auto t1 = std::chrono::steady_clock::now();
         rc = launch(dptr, n, g_slots[0].stream, 0);
         if (rc) return rc;
+        const auto t2 = std::chrono::steady_clock::now();
         CK(cudaStreamSynchronize(g_slots[0].stream));
+        const auto t3 = std::chrono::steady_clock::now();
         for (int a = 0; a < narrays; ++a)
             if (arrays[a].out) std::memcpy(arrays[a].out, dptr[a], arrays[a].bytes_per_point * n);
+        if (trace) {
+            const auto t4 = std::chrono::steady_clock::now();
+            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            g_trace_us[0] += us(t0, t1); g_trace_us[1] += us(t1, t2); g_trace_us[2] += us(t2, t3); g_trace_us[3] += us(t3, t4);
+            g_trace_us[4] += 1.0;
+        }
         return TRGL_OK;
     }
     const int64_t chunk = n < kChunk ? n : kChunk;
@@ -973,6 +989,16 @@ int64_t trgl_set_deferred_capacity(int64_t max_points) {
     const int64_t old = g_deferred_limit.load();
     if (max_points >= 1 && max_points <= static_cast<int64_t>(kDeferredMax)) g_deferred_limit.store(static_cast<unsigned int>(max_points));
     return old;
+}
+int trgl_set_trace(int enabled) {
+    const int old = g_trace.exchange(enabled ? 1 : 0);
+    return old;
+}
+int trgl_get_trace(double* out5) {
+    if (!out5) return fail(TRGL_E_BADARG, "out5 is NULL");
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    for (int k = 0; k < 5; ++k) { out5[k] = g_trace_us[k]; g_trace_us[k] = 0.0; }
+    return TRGL_OK;
 }
 int trgl_deferred_total(void* stream, int64_t* total) {
     if (!total) return fail(TRGL_E_BADARG, "total is NULL");

@@ -34,7 +34,7 @@ EXPORTS = [
     "trgl_set_points_per_thread", "trgl_set_stream_variant", "trgl_set_two_ray", "trgl_multiview_ls", "trgl_set_deferred_capacity",
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
     "trgl_set_fused_eval", "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
-    "trgl_set_result_mirrors_f32", "trgl_set_input_retention", "trgl_deferred_total", "trgl_vector_stat",
+    "trgl_set_result_mirrors_f32", "trgl_set_input_retention", "trgl_deferred_total", "trgl_vector_stat", "trgl_set_trace", "trgl_get_trace",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -57,7 +57,7 @@ def lib():
             "there is no CPU fallback" % (LIB_PATH, os.path.join(_HERE, "csrc")))
     L = ctypes.CDLL(LIB_PATH)
     vp, i64, dbl, cint = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int
-    dp = ctypes.POINTER(ctypes.c_double)
+    dp = vp           # double* parameters take plain integer addresses: `a.ctypes.data` costs 1 us, `data_as(POINTER)` 2.5 us
     L.trgl_version.restype = cint
     L.trgl_last_error_string.restype = ctypes.c_char_p
     L.trgl_launch_count.restype = i64
@@ -285,11 +285,12 @@ def _check_device_array(a, cols, name, dtypes=_FLOAT_DTYPES):
 
 
 def _ptr(a):
+    """Address of a host array / device buffer as a plain integer (None -> NULL); every pointer parameter is a c_void_p."""
     if a is None:
         return None
     if _is_device(a):
-        return ctypes.c_void_p(a.data_ptr())
-    return ctypes.c_void_p(a.ctypes.data)
+        return a.data_ptr() or None
+    return a.ctypes.data or None
 
 
 # Device buffers of the resident pairs come from a small size-keyed pool (cudaMalloc + cudaFree of two 160 MB blocks per
@@ -394,7 +395,7 @@ def _P12(P):
 
 
 def _dp(a):
-    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    return a.ctypes.data
 
 
 _MODE = {(8, 8, 8): F64, (4, 8, 4): F32IO, (4, 4, 4): F32, (8, 8, 4): F64_OUT32, (4, 8, 8): F32_OUT64}
@@ -893,6 +894,17 @@ def set_stream_variant(v):
 def set_deferred_capacity(max_points):
     """Test knob: limit of the deferred-point list of the hot kernels (default 2**26); returns the old limit."""
     return lib().trgl_set_deferred_capacity(int(max_points))
+
+
+def set_trace(enabled):
+    return lib().trgl_set_trace(int(enabled))
+
+
+def get_trace():
+    """Per-phase host microseconds of the small-batch path since the last call: dict(stage_in, launch, sync, stage_out, calls)."""
+    out = (ctypes.c_double * 5)()
+    check(lib().trgl_get_trace(out))
+    return dict(zip(("stage_in_us", "launch_us", "sync_us", "stage_out_us", "calls"), [float(v) for v in out]))
 
 
 def deferred_total(stream=None):

@@ -17,4 +17,6 @@ const void* probe_table[] = {
     reinterpret_cast<const void*>(&k_linear_ls_f32x4),
     reinterpret_cast<const void*>(&k_multiview_ls<double, double, double, 1, 8, 1, true>),
     reinterpret_cast<const void*>(&k_multiview_ls<double, double, double, 1, 8, 1, false>),
+    reinterpret_cast<const void*>(&k_linear_ls_general<float, double, float, PreNone, false>),
+    reinterpret_cast<const void*>(&k_iterative_general<double, double, double, PreNone, PROBE_EVAL>),
 };
