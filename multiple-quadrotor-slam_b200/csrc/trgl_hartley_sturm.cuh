@@ -232,9 +232,12 @@ __device__ __forceinline__ bool hs_correct(const HSParams& hs, double x1, double
             double g = k[6], dg = 0.0;
 #pragma unroll
             for (int i = 5; i >= 0; --i) { dg = fma(dg, tp, g); g = fma(g, tp, k[i]); }
-            t = fma(-g, fast_rcp(dg), tp);
-            accepted = (fabs(t - tp) <= 1e-8 * fabs(t)) && (fabs(t) <= T0);
-            tp = t;
+            const double tn = fma(-g, fast_rcp(dg), tp);
+            if (!accepted) {        // an accepted lane keeps its iterate: the result must not depend on how long its warp goes on
+                t = tn;
+                accepted = (fabs(tn - tp) <= 1e-8 * fabs(tn)) && (fabs(tn) <= T0);
+                tp = tn;
+            }
             if (it >= 1 && __all_sync(0xffffffffu, accepted || !fast)) break;
         }
         certified = fast && accepted;

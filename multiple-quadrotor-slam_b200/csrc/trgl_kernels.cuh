@@ -994,10 +994,14 @@ __device__ __forceinline__ bool ldl4_direction(const T S[10], const T b[4], T y[
     return (d0 != T(0)) && (d1 != T(0)) && (d2 != T(0)) && (d3 == d3);
 }
 
-// All 32 lanes of the warp must call this together.  Returns true when X is certified; `straggler` = true when the point
-// has to go to the follow-up kernel (not converged within the warp's rounds, breakdown, NaN, no eigenvalue gap).
-template <typename TC, int ROWS>
-__device__ __forceinline__ bool eigen_point_warp(const Cams<TC>& cams, TC u1x, TC u1y, TC u2x, TC u2y, TC X[4]) {
+// WARP = true (hot kernel): all 32 lanes of the warp call this together and decide together when to stop.  WARP = false
+// (follow-up kernel): the same arithmetic for one point on its own, up to kEigenLoneRounds rounds.  A lane FREEZES its
+// iterate at the first round whose residual passes, so the result of a point is the same bits wherever it is computed --
+// in a warp that stopped early, in one that went on for its neighbours, or in the follow-up kernel: results do not depend
+// on how a batch is cut into shards or where a point sits in it.  Returns true when X is certified.
+constexpr int kEigenLoneRounds = 8;
+template <typename TC, int ROWS, bool WARP>
+__device__ __forceinline__ bool eigen_point_iter(const Cams<TC>& cams, TC u1x, TC u1y, TC u2x, TC u2y, TC X[4]) {
     TC G[10];
     {
         TC B[ROWS][4];
@@ -1026,17 +1030,20 @@ __device__ __forceinline__ bool eigen_point_warp(const Cams<TC>& cams, TC u1x, T
     const TC tol = TC(4) * Num<TC>::eps() * tr;
     TC lam = 0;
     bool alive = true, conv = false;
-    // one round: Rayleigh quotient of the (unit, to 1e-12) iterate, shifted solve, normalisation
+    // one round: Rayleigh quotient of the (unit, to 1e-12) iterate, shifted solve, normalisation; a converged lane keeps X
     auto rqi_round = [&](const TC (&y)[4]) {
-        lam = tfma(X[0], y[0], tfma(X[1], y[1], tfma(X[2], y[2], X[3] * y[3])));
+        const TC rho = conv ? lam : tfma(X[0], y[0], tfma(X[1], y[1], tfma(X[2], y[2], X[3] * y[3])));
         TC S[10], z[4];
 #pragma unroll
         for (int k = 0; k < 10; ++k) S[k] = G[k];
-        S[0] -= lam; S[4] -= lam; S[7] -= lam; S[9] -= lam;
-        alive = ldl4_direction<TC>(S, X, z) && alive;
+        S[0] -= rho; S[4] -= rho; S[7] -= rho; S[9] -= rho;
+        const bool usable = ldl4_direction<TC>(S, X, z);
         const TC nrm = fast_rsqrt(tfma(z[0], z[0], tfma(z[1], z[1], tfma(z[2], z[2], z[3] * z[3]))));
+        if (!conv) {
+            alive = alive && usable;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) X[k] = z[k] * nrm;
+            for (int k = 0; k < 4; ++k) X[k] = z[k] * nrm;
+        }
     };
     auto matvec = [&](TC (&y)[4]) {
         y[0] = tfma(G[0], X[0], tfma(G[1], X[1], tfma(G[2], X[2], G[3] * X[3])));
@@ -1051,14 +1058,20 @@ __device__ __forceinline__ bool eigen_point_warp(const Cams<TC>& cams, TC u1x, T
 #pragma unroll 1
     for (int round = 2;; ++round) {
         matvec(y);
-        const TC xx = tfma(X[0], X[0], tfma(X[1], X[1], tfma(X[2], X[2], X[3] * X[3])));
-        lam = tfma(X[0], y[0], tfma(X[1], y[1], tfma(X[2], y[2], X[3] * y[3]))) * fast_rcp(xx);     // exact Rayleigh quotient
-        TC rn = 0;
+        if (!conv) {
+            const TC xx = tfma(X[0], X[0], tfma(X[1], X[1], tfma(X[2], X[2], X[3] * X[3])));
+            lam = tfma(X[0], y[0], tfma(X[1], y[1], tfma(X[2], y[2], X[3] * y[3]))) * fast_rcp(xx);     // exact Rayleigh quotient
+            TC rn = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const TC r = tfma(-lam, X[k], y[k]); rn = tfma(r, r, rn); }
-        conv = rn <= tol * tol * xx;
-        const unsigned open = __ballot_sync(0xffffffffu, alive && !conv);
-        if (__popc(open) <= kEigenStragglers || round == kEigenMaxRounds) break;           // warp-uniform
+            for (int k = 0; k < 4; ++k) { const TC r = tfma(-lam, X[k], y[k]); rn = tfma(r, r, rn); }
+            conv = rn <= tol * tol * xx;
+        }
+        if constexpr (WARP) {
+            const unsigned open = __ballot_sync(0xffffffffu, alive && !conv);
+            if (__popc(open) <= kEigenStragglers || round == kEigenMaxRounds) break;           // warp-uniform
+        } else {
+            if (conv || !alive || round == kEigenLoneRounds) break;
+        }
         rqi_round(y);
     }
     // certificate: exactly one eigenvalue of G below lam + gap tr(G)   (see eigen_point_fast)
@@ -1128,7 +1141,7 @@ k_linear_eigen(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
         if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
         TC X[4], xs[3] = {0, 0, 0};
         bool good = false;
-        const bool certified = eigen_point_warp<TC, ROWS>(cams, a, b, c, d, X);      // all 32 lanes present (uniform trip count)
+        const bool certified = eigen_point_iter<TC, ROWS, true>(cams, a, b, c, d, X);      // all 32 lanes present (uniform trip count)
         if (certified) eigen_finish_fast<TC>(X, max_coord, xs, good);
         else if (i < n) defer_point(df, i);
         store_x_warp(x, tile + warp * 32, n, static_cast<TO>(xs[0]), static_cast<TO>(xs[1]),
@@ -1160,10 +1173,14 @@ k_linear_eigen_general(const TI* __restrict__ u1, const TI* __restrict__ u2, con
         TC a, b, c, d, X[4], xs[3];
         bool good;
         reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, i, a, b, c, d);
-        // the points the fixed-round hot kernel did not converge on first get the iteration with up to 5 rounds; what that
-        // does not certify either (no gap, breakdown, NaN) takes the one-sided Jacobi SVD, the path cv::SVD itself runs
-        if (!eigen_point_fast<TC, ROWS>(cams, a, b, c, d, X)) eigen_point_jacobi<TC, ROWS>(cams, a, b, c, d, X);
-        eigen_finish<TC>(X, max_coord, xs, good);
+        // the stragglers of the hot kernel's warps get the same iteration on their own (up to kEigenLoneRounds rounds); what
+        // that does not certify either (no gap, breakdown, NaN) takes the one-sided Jacobi SVD, the path cv::SVD itself runs
+        if (eigen_point_iter<TC, ROWS, false>(cams, a, b, c, d, X)) {
+            eigen_finish_fast<TC>(X, max_coord, xs, good);          // same arithmetic, hence same bits, as in the hot kernel
+        } else {
+            eigen_point_jacobi<TC, ROWS>(cams, a, b, c, d, X);
+            eigen_finish<TC>(X, max_coord, xs, good);
+        }
 #pragma unroll
         for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
         for (int m = 0; m < mir.count; ++m) {
