@@ -298,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
     d_u1, d_u2 = tc.to_device(u1), tc.to_device(u2)
     d_x = {s: tc.DeviceArray((n, 3), np.float64) for s in SOLVERS}
     d_st = {s: tc.DeviceArray((n,), STATUS_DTYPE[s]) for s in SOLVERS}
-    ev = [tc.Event() for _ in range(9)]
+    ev_scratch = [tc.Event() for _ in range(9)]
     d_sums = tc.DeviceArray((4, 4), np.float64)      # per-solver reprojection sums, finished on the device
     thr = (2.0 / 480) ** 2                           # 2 px at f = 480: the harness' reprojection threshold scale
 
@@ -308,7 +308,7 @@ def run_ours(args, rank, world, local_rank):
              if not args.separate_eval and (s != "linear_LS" or not args.separate_ls_eval)}
     d_good = {s: tc.DeviceArray((n,), np.bool_) for s in SOLVERS if s not in fused}
 
-    def solve(name, u1_, u2_, x, st, evaluate=None, nan_check=False):
+    def solve(name, u1_, u2_, x, st, evaluate=None):
         if name == "linear_eigen":
             tc.linear_eigen(u1_, P1, u2_, P2, x=x, status=st, evaluate=evaluate)
         elif name == "linear_LS":
@@ -316,12 +316,28 @@ def run_ours(args, rank, world, local_rank):
         elif name == "iterative_LS":
             tc.iterative_ls(u1_, P1, u2_, P2, x=x, status=st, evaluate=evaluate)
         else:
-            # check_all_nan: the `np.isnan(u_new).all()` test of triangulation.py:227 -- one flag read per call (synchronises)
-            return tc.polynomial(u1_, P1, u2_, P2, x=x, status=st, check_all_nan=nan_check, evaluate=evaluate)[2]
-        return False
+            tc.polynomial(u1_, P1, u2_, P2, x=x, status=st, check_all_nan=False, evaluate=evaluate)
 
-    def device_step(timed, peer=None, gather_buf=None):
+    # Results of a step -- the four solvers' reprojection sums and polynomial's all-NaN words (the np.isnan(u_new).all()
+    # test of triangulation.py:227) -- come back to the host through page-locked buffers, asynchronously: step k's are
+    # read after step k+1 has been enqueued, so the host never lets the GPU run dry between steps (two buffers in flight).
+    h_sums = [tc.pinned_empty((4, 4), np.float64) for _ in range(2)]
+    h_flags = [tc.pinned_empty((2,), np.uint32) for _ in range(2)]
+    done = [tc.Event(), tc.Event()]
+    state = {"k": 0, "pending": [False, False], "checksum": 0.0}
+
+    def collect(slot):
+        if state["pending"][slot]:
+            done[slot].synchronize()
+            assert h_flags[slot][0] != 0 and h_flags[slot][1] != 0, "polynomial: every corrected point is NaN"
+            state["checksum"] += float(h_sums[slot][:, 0:2].sum())
+            state["pending"][slot] = False
+
+    def device_step(evs, peer=None, gather_buf=None):
+        """evs: a set of 9 events of this step's own (timed steps: read after the region), or None."""
         k = 0
+        ev = evs if evs is not None else ev_scratch
+        slot = state["k"] & 1
         for si, name in enumerate(SOLVERS):
             ev[k].record(); k += 1
             x, st = d_x[name], d_st[name]
@@ -330,8 +346,9 @@ def run_ours(args, rank, world, local_rank):
                 x, st = pg.shard_outputs()
                 pg.arm()
             fe = fused.get(name)                     # evaluation in the solver's epilogue: no second pass over x, u1, u2
-            all_nan = solve(name, d_u1, d_u2, x, st, fe, nan_check=(name == "polynomial"))
-            assert not all_nan
+            solve(name, d_u1, d_u2, x, st, fe)
+            if name == "polynomial":
+                tc.polynomial_flags_async(h_flags[slot])
             if fe is None:
                 # stand-alone pass (asynchronous variant: the grid-level sums are finished inside the kernel)
                 tc.pair_reproj(x, d_u1, P1, d_u2, P2, st, 0, thr, want_errors=False, want_good=d_good[name],
@@ -341,13 +358,14 @@ def run_ours(args, rank, world, local_rank):
                 dist.all_gather_into_tensor(gather_buf[name][0], gather_buf[name][2])
                 dist.all_gather_into_tensor(gather_buf[name][1], gather_buf[name][3])
         ev[8].record()
-        sums_total = float(d_sums.to_host()[:, 0:2].sum())      # the step's result comes back to the host (synchronises)
+        d_sums.to_host(out=h_sums[slot], sync=False)
+        done[slot].record()
+        state["pending"][slot] = True
+        state["k"] += 1
+        collect(slot ^ 1)                                         # the PREVIOUS step's results (this one keeps the GPU busy)
         if peer is not None:
+            collect(slot)
             dist.barrier()                                        # every rank's stores have landed: gathered arrays valid
-        if timed is not None:
-            for i, name in enumerate(SOLVERS):
-                timed[name].append(ev[2 * i].elapsed_ms(ev[2 * i + 1]))
-        return sums_total
 
     def barrier():
         tc.synchronize()
@@ -358,14 +376,21 @@ def run_ours(args, rank, world, local_rank):
     def timed_steps(steps, warmup, per_kernel=None, **kw):
         for _ in range(warmup):
             device_step(None, **kw)
+        ev_sets = [[tc.Event() for _ in range(9)] for _ in range(steps)] if per_kernel is not None else [None] * steps
         barrier()
+        collect(0); collect(1)
         e0, e1 = tc.Event(), tc.Event()
         e0.record()
-        for _ in range(steps):
-            device_step(per_kernel, **kw)
+        for i in range(steps):
+            device_step(ev_sets[i], **kw)
+        collect(0); collect(1)                        # every step's results have been read on the host
         e1.record()
         barrier()
         ms = e0.elapsed_ms(e1)
+        if per_kernel is not None:
+            for evs in ev_sets:
+                for i, name in enumerate(SOLVERS):
+                    per_kernel[name].append(evs[2 * i].elapsed_ms(evs[2 * i + 1]))
         if dist is not None:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -85,6 +85,7 @@ int trgl_stream_synchronize(void* stream);
 int trgl_event_create(void** event);
 int trgl_event_destroy(void* event);
 int trgl_event_record(void* event, void* stream);
+int trgl_event_synchronize(void* event);
 int trgl_event_elapsed_ms(void* start, void* stop, float* ms);   /* synchronises on `stop` */
 
 /* ---- the four solvers ---- */
@@ -163,6 +164,13 @@ int trgl_multiview_ls(const void* u, const uint8_t* valid, const double* P, int 
  * Arithmetic is float64 in OpenCV's evaluation order without FMA contraction: results are bit-identical to cv2 4.13. */
 int trgl_undistort_points(const void* src, void* dst, const double* K, const double* dist, int64_t n, int in_is_f32,
                           int mem, void* stream);
+
+/* The all-NaN test of the LAST device-mode polynomial call on `stream` (np.isnan(u_new).all(), triangulation.py:227),
+ * without blocking: copies the two "some corrected point of view 1 / view 2 is not NaN" words to host_flags2 (page-locked
+ * host memory, 2 x uint32) in stream order and returns; the caller reads them after synchronising with the stream or an
+ * event (all_nan = either word == 0).  For callers that keep several batches in flight instead of passing `all_nan`,
+ * which synchronises inside the call. */
+int trgl_polynomial_flags_async(unsigned int* host_flags2, void* stream);
 
 /* The four solvers on PIXEL coordinates: px1, px2 are what the callers hand to cv2.undistortPoints, (K1,dist1) and
  * (K2,dist2) the intrinsics of the two views (the reference uses one camera for both, slam2.py:551-552).  The

@@ -144,11 +144,25 @@ __device__ __forceinline__ void mirror_put(const Mirrors& mir, int r, int64_t id
 // the compiler from interleaving the four points of a thread (measured: 0.85 -> 0.80 of the copy peak).
 struct NoMirrors { static constexpr bool kActive = false; };
 
+// Every rank lists its mirrors in the same (rank) order; if every warp walked the table from entry 0, all ranks would
+// write to the same destination GPU at the same moment and the others' links would idle.  Each warp starts at a different
+// entry instead, so that at any instant the stores of a kernel are spread over all destinations.
+__device__ __forceinline__ int mirror_rotation(int count) {
+    return count > 1 ? static_cast<int>((blockIdx.x * kWarps + (threadIdx.x >> 5)) % static_cast<unsigned>(count)) : 0;
+}
+
 template <typename TS, class M>
 __device__ __forceinline__ void store_status(TS* __restrict__ status, const M& mir, int64_t i, TS v) {
     status[i] = v;
-    if constexpr (M::kActive)
-        for (int r = 0; r < mir.count; ++r) static_cast<TS*>(mir.status[r])[i] = v;
+    if constexpr (M::kActive) {
+        if (mir.count) {
+            int r = mirror_rotation(mir.count);
+            for (int k = 0; k < mir.count; ++k) {
+                static_cast<TS*>(mir.status[r])[i] = v;
+                if (++r == mir.count) r = 0;
+            }
+        }
+    }
 }
 
 // ---- coalesced store of the (n,3) AoS result ---------------------------------------------------------------
@@ -173,11 +187,15 @@ __device__ __forceinline__ void store_x_warp(TO* __restrict__ xout, int64_t warp
         if (idx < cnt) __stcs(dst + idx, stage[idx]);
     }
     if constexpr (M::kActive) {
-        for (int r = 0; r < mir.count; ++r) {       // same three contiguous rows into every peer's gather buffer
+        if (mir.count) {                            // same three contiguous rows into every peer's gather buffer
+            int r = mirror_rotation(mir.count);
+            for (int m = 0; m < mir.count; ++m) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int idx = k * 32 + lane;
-                if (idx < cnt) mirror_put<TO>(mir, r, warp_base * 3 + idx, stage[idx]);
+                for (int k = 0; k < 3; ++k) {
+                    const int idx = k * 32 + lane;
+                    if (idx < cnt) mirror_put<TO>(mir, r, warp_base * 3 + idx, stage[idx]);
+                }
+                if (++r == mir.count) r = 0;
             }
         }
     }

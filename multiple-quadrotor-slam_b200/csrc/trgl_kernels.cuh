@@ -577,13 +577,17 @@ __device__ __forceinline__ void mirror_slice(const TO* __restrict__ x, const int
     if (base >= n) return;
     const int lane = threadIdx.x & 31;
     const int cnt = (n - base) >= 32 ? 32 : static_cast<int>(n - base);
-    for (int idx = lane; idx < cnt * 3; idx += 32) {
-        const TO v = __ldcg(x + base * 3 + idx);
-        for (int r = 0; r < mir.count; ++r) mirror_put<TO>(mir, r, base * 3 + idx, v);
-    }
-    if (lane < cnt) {
-        const int32_t v = __ldcg(status + base + lane);
-        for (int r = 0; r < mir.count; ++r) static_cast<int32_t*>(mir.status[r])[base + lane] = v;
+    TO v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = (k * 32 + lane < cnt * 3) ? __ldcg(x + base * 3 + k * 32 + lane) : TO(0);
+    const int32_t sv = lane < cnt ? __ldcg(status + base + lane) : 0;
+    int r = mirror_rotation(mir.count);
+    for (int m = 0; m < mir.count; ++m) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k * 32 + lane < cnt * 3) mirror_put<TO>(mir, r, base * 3 + k * 32 + lane, v[k]);
+        if (lane < cnt) static_cast<int32_t*>(mir.status[r])[base + lane] = sv;
+        if (++r == mir.count) r = 0;
     }
 }
 

@@ -923,6 +923,10 @@ int trgl_event_record(void* event, void* stream) {
     CK(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
     return TRGL_OK;
 }
+int trgl_event_synchronize(void* event) {
+    CK(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+    return TRGL_OK;
+}
 int trgl_event_elapsed_ms(void* start, void* stop, float* ms) {
     CK(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
     CK(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
@@ -1276,6 +1280,17 @@ int trgl_polynomial_F(const void* u1, const void* u2, const double* P1, const do
     PendingClear pending_clear;
     return impl_polynomial_F(u1, u2, P1, P2, F, x, status, u1_corr, u2_corr, all_nan, n, max_coordinate_value, rows, mode,
                              mem, stream, nullptr);
+}
+
+int trgl_polynomial_flags_async(unsigned int* host_flags2, void* stream) {
+    if (!host_flags2) return fail(TRGL_E_BADARG, "host_flags2 is NULL");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Scratch sc;
+    int rc = scratch_for(s, sc);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(host_flags2, sc.flags + 2 * kSlots, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    return TRGL_OK;
 }
 
 int trgl_polynomial(const void* u1, const void* u2, const double* P1, const double* P2, void* x, uint8_t* status,

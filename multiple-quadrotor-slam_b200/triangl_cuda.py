@@ -28,7 +28,8 @@ EXPORTS = [
     "trgl_version", "trgl_last_error_string", "trgl_device_count", "trgl_set_device", "trgl_device_synchronize",
     "trgl_device_alloc", "trgl_device_free", "trgl_host_alloc", "trgl_host_free", "trgl_memcpy_h2d",
     "trgl_memcpy_d2h", "trgl_memcpy_d2d", "trgl_memset_d", "trgl_stream_create", "trgl_stream_destroy", "trgl_stream_synchronize",
-    "trgl_event_create", "trgl_event_destroy", "trgl_event_record", "trgl_event_elapsed_ms",
+    "trgl_event_create", "trgl_event_destroy", "trgl_event_record", "trgl_event_synchronize", "trgl_event_elapsed_ms",
+    "trgl_polynomial_flags_async",
     "trgl_linear_ls", "trgl_iterative_ls", "trgl_linear_eigen", "trgl_polynomial", "trgl_polynomial_F",
     "trgl_fundamental_8point", "trgl_reproj_error", "trgl_pair_reproj", "trgl_launch_count",
     "trgl_set_points_per_thread", "trgl_set_stream_variant", "trgl_set_two_ray", "trgl_multiview_ls", "trgl_set_deferred_capacity",
@@ -75,6 +76,8 @@ def lib():
     L.trgl_event_create.argtypes = [ctypes.POINTER(vp)]
     L.trgl_event_destroy.argtypes = [vp]
     L.trgl_event_record.argtypes = [vp, vp]
+    L.trgl_event_synchronize.argtypes = [vp]
+    L.trgl_polynomial_flags_async.argtypes = [vp, vp]
     L.trgl_event_elapsed_ms.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_float)]
     L.trgl_linear_ls.argtypes = [vp, vp, dp, dp, vp, vp, i64, cint, cint, vp]
     L.trgl_iterative_ls.argtypes = [vp, vp, dp, dp, vp, vp, i64, dbl, cint, cint, cint, vp]
@@ -150,11 +153,13 @@ class DeviceArray:
         check(lib().trgl_stream_synchronize(stream))
         return self
 
-    def to_host(self, out=None, stream=None):
+    def to_host(self, out=None, stream=None, sync=True):
+        """sync=False: enqueue the copy only (out should be page-locked: pinned_empty); the caller synchronises."""
         if out is None:
             out = np.empty(self.shape, dtype=self.dtype)
         check(lib().trgl_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, stream))
-        check(lib().trgl_stream_synchronize(stream))
+        if sync:
+            check(lib().trgl_stream_synchronize(stream))
         return out
 
     def view(self, offset, shape):
@@ -644,6 +649,11 @@ def polynomial(u1, P1, u2, P2, F=None, max_coordinate_value=1.e16, rows=4, out_d
     return x, status, bool(flag.value)
 
 
+def polynomial_flags_async(host_flags2, stream=None):
+    """Enqueue the copy of the last device-mode polynomial call's two not-all-NaN words into a pinned (2,) uint32 array."""
+    check(lib().trgl_polynomial_flags_async(host_flags2.ctypes.data, stream))
+
+
 def fundamental_8point(u1, u2, compute_dtype=np.float64, stream=None):
     u1, u2, mem, n, mode, _ = _prep(u1, u2, compute_dtype, np.float32 if np.dtype(compute_dtype) == np.float32 else
                                     (np.float32 if getattr(u1, "dtype", None) == np.float32 else np.float64),
@@ -932,6 +942,9 @@ class Event:
 
     def record(self, stream=None):
         check(lib().trgl_event_record(self.ptr, stream))
+
+    def synchronize(self):
+        check(lib().trgl_event_synchronize(self.ptr))
 
     def elapsed_ms(self, stop):
         ms = ctypes.c_float(0)
