@@ -18,6 +18,9 @@
 #ifndef TRGL_LS_MINB
 #define TRGL_LS_MINB 3             // linear_LS hot kernel without the in-line SVD tier: 3 CTAs/SM of loads in flight
 #endif
+#ifndef TRGL_LS_EVAL_MINB
+#define TRGL_LS_EVAL_MINB 2        // linear_LS with the evaluation epilogue, 4 points per thread: 80 registers spill (184 B)
+#endif
 #ifndef TRGL_ITER_MINB
 #define TRGL_ITER_MINB 3          // 80 registers with the evaluation epilogue, no spills
 #endif
@@ -223,7 +226,7 @@ __device__ __forceinline__ void ls_tile(const TI* __restrict__ u1, const TI* __r
 
 template <typename TI, typename TC, typename TO, int PPT, class PRE = PreNone, bool EVAL = false, class MIR = Mirrors,
           bool DEFER = false>
-__global__ void __launch_bounds__(kThreads, DEFER ? TRGL_LS_MINB : 1)
+__global__ void __launch_bounds__(kThreads, DEFER ? (EVAL ? TRGL_LS_EVAL_MINB : TRGL_LS_MINB) : 1)
 k_linear_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
             TO* __restrict__ x, uint8_t* __restrict__ status, const int64_t n, const __grid_constant__ PRE pre,
             const __grid_constant__ MIR mir, const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df) {

@@ -19,4 +19,5 @@ const void* probe_table[] = {
     reinterpret_cast<const void*>(&k_multiview_ls<double, double, double, 1, 8, 1, false>),
     reinterpret_cast<const void*>(&k_linear_ls_general<float, double, float, PreNone, false>),
     reinterpret_cast<const void*>(&k_iterative_general<double, double, double, PreNone, PROBE_EVAL>),
+    reinterpret_cast<const void*>(&k_linear_ls<double, double, double, 4, PreNone, PROBE_EVAL, NoMirrors, true>),
 };
