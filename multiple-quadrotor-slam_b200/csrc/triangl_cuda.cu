@@ -138,10 +138,10 @@ void launch_followup(void (*kern)(KArgs...), unsigned grid, cudaStream_t s, Args
     cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
-// Grid cap of the follow-up kernels, in CTAs per SM: they loop over the deferred list with a grid stride, so a batch that
-// defers nothing pays for ceil(n / 256) (at most this many) empty CTAs, and a rig that defers most of its points (forward
-// motion: 20 % in linear_eigen, everything in FP32-mode linear_LS) still fills the machine.
-constexpr int kFollowupCtasPerSm = 8;
+// Grid cap of the follow-up kernels, in CTAs per SM: they loop over the deferred list with a grid stride.  Two per SM is what
+// is resident anyway at their 100-150 registers per thread, and an EMPTY follow-up launch costs 4 us with 2 x 148 CTAs
+// against 8-10 us with 8 x 148 (ncu launch list, profiles/r02p_launches.md) -- the common case is a list with no entry.
+constexpr int kFollowupCtasPerSm = 2;
 inline unsigned grid_for(int64_t n, int per_block) { return static_cast<unsigned>((n + per_block - 1) / per_block); }
 
 // Reduction scratch (per-block partial sums, the polynomial NaN flags, the last-block ticket) is owned per

@@ -14,25 +14,15 @@ if has smoke; then echo "== smoke"; timeout 300 python __graft_entry__.py smoke 
 if has bench; then echo "== bench default"; timeout 900 python bench.py > $OUT/bench_10M.json 2> $OUT/bench_10M.err; echo "bench rc=$?"; tail -5 $OUT/bench_10M.err; python tools/show_bench.py $OUT/bench_10M.json; fi
 if has ref; then echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cut -c1-500 $OUT/bench_reference.json; fi
 if has slam; then echo "== slam"; timeout 600 python bench.py --workload slam --steps 200 --warmup 20 > $OUT/slam_latency.json 2> $OUT/slam.err; echo "slam rc=$?"; tail -3 $OUT/slam.err; python tools/show_bench.py $OUT/slam_latency.json; fi
-if has rigs; then echo "== sweep 10M per rig"; for R in rotating translating forward general; do timeout 300 python tools/sweep_kernels.py --points 10000000 --solvers linear_LS,iterative_LS,linear_eigen,polynomial --modes f64 --variants 0 --ppts 4 --rig $R | sed "s/^{/{\"rig\": \"$R\", /" >> $OUT/sweep_rigs_10M.jsonl; done; cut -c1-160 $OUT/sweep_rigs_10M.jsonl; fi
-if has mv; then echo "== multi-view"; timeout 300 python tools/sweep_multiview.py --views 2,4,8,16 > $OUT/sweep_multiview.jsonl 2> $OUT/sweep_multiview.err; timeout 300 python tools/sweep_multiview.py --views 8 --visible 0.7 >> $OUT/sweep_multiview.jsonl; cut -c1-200 $OUT/sweep_multiview.jsonl; fi
+if has rigs; then echo "== sweep 10M per rig (with the evaluation epilogue)"; rm -f $OUT/sweep_rigs_10M.jsonl; for R in rotating translating forward general; do timeout 300 python tools/sweep_kernels.py --points 10000000 --solvers linear_LS,iterative_LS,linear_eigen,polynomial --modes f64 --variants 0 --ppts 4 --eval --rig $R | sed "s/^{/{\"rig\": \"$R\", /" >> $OUT/sweep_rigs_10M.jsonl; done; cut -c1-160 $OUT/sweep_rigs_10M.jsonl; fi
+if has mv; then echo "== multi-view"; timeout 300 python tools/sweep_multiview.py --views 2,3,4,6,8,12,16 > $OUT/sweep_multiview.jsonl 2> $OUT/sweep_multiview.err; timeout 300 python tools/sweep_multiview.py --views 4,8,16 --visible 0.7 >> $OUT/sweep_multiview.jsonl; cut -c1-200 $OUT/sweep_multiview.jsonl; fi
 if has launches; then
   echo "== ncu launch list (bench --steps 2 --warmup 1)"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-100m > $OUT/launches_bench.log 2>&1
   echo "launch list rc=$? lines=$(wc -l < $OUT/launches.csv)"
 fi
-export_rep() {
-    ncu -i $1.ncu-rep --page raw --csv > $1.raw.csv 2>/dev/null
-    ncu -i $1.ncu-rep --page source --csv > $1.source.csv 2>/dev/null
-    rm -f $1.ncu-rep
-}
 if has ncu; then
-  for K in ${NCU_KERNELS:-k_linear_ls k_iterative_ls k_linear_eigen k_polynomial}; do
-    timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^$K\$" -s 1 -c 1 -f -o $OUT/full_$K \
-        python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-100m > $OUT/full_$K.log 2>&1
-    echo "$K rc=$?"
-    export_rep $OUT/full_$K
-  done
+  bash tools/gpu_prof.sh $TAG "ls=k_linear_ls:linear_LS:10000000:f64: ls_100M=k_linear_ls:linear_LS:100000000:f64: ls_eval=k_linear_ls:linear_LS:10000000:f64:--eval iter_eval=k_iterative_ls:iterative_LS:10000000:f64:--eval eigen_eval=k_linear_eigen:linear_eigen:10000000:f64:--eval poly_eval=k_polynomial:polynomial:10000000:f64:--eval ls_f32_100M=k_linear_ls_f32x4:linear_LS:100000000:f32: mv8_masked=k_multiview_ls:mv8m:10000000::"
 fi
-ls -la $OUT | head -40
+ls -la $OUT | head -60

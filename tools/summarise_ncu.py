@@ -100,7 +100,7 @@ if os.path.isfile(ll):
     print("wrote", tag + "_launches.md")
 
 # ---- full captures ------------------------------------------------------------------------------------------------
-traffic = {}
+traffic, busy, dur = {}, {}, {}
 with open(os.path.join(dst, tag + "_ncu_full.md"), "w") as f:
     f.write("# `ncu --set full --clock-control none --import-source on` captures (%s)\n\n" % tag)
     f.write("One launch per kernel after warm-up.  Times under the profiler are not bench values.\n")
@@ -124,8 +124,10 @@ with open(os.path.join(dst, tag + "_ncu_full.md"), "w") as f:
         grid = num(v[col["launch__grid_size"]])
         tr = bytes_of("dram__bytes_read.sum") + bytes_of("dram__bytes_write.sum")
         f.write("| **DRAM traffic per launch** | %.4g | byte |\n" % tr)
-        key = os.path.basename(rep)[len("full_k_"):-len(".ncu-rep")]
+        key = os.path.basename(rep)[len("full_"):-len(".ncu-rep")]
         traffic[key] = tr
+        busy[key] = num(v[col["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]])
+        dur[key] = num(v[col["gpu__time_duration.sum"]])
         # source page: top lines by sampled stalls
         srcp = ncu_csv(rep, "source")
         while srcp and srcp[0][0] != "Address":
@@ -150,3 +152,20 @@ for fn in glob.glob(os.path.join(src, "bench_*.json")) + glob.glob(os.path.join(
     if os.path.getsize(fn) and "full_" not in os.path.basename(fn) and "launches_bench" not in fn:
         shutil.copy(fn, os.path.join(dst, tag + "_" + os.path.basename(fn)))
 print(json.dumps(traffic))
+# profiles/traffic.json: DRAM bytes per point of the kernels bench.py reports (10 M-point captures of this round)
+names = {"ls": "linear_LS", "iter_eval": "iterative_LS", "eigen_eval": "linear_eigen", "poly_eval": "polynomial"}
+if all(k in traffic for k in names):
+    tj = {"source": "profiles/%s_ncu_full.md (ncu --set full, 10 M points, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                    "/ 1e7 points; linear_LS: the plain HBM-bound kernel of the roofline entry; the three FP64-bound kernels "
+                    "with the evaluation epilogue and the good mask)" % tag}
+    for k, nme in names.items():
+        tj[nme] = traffic[k] / 1e7
+    tj["linear_LS_eval"] = traffic.get("ls_eval", 0) / 1e7
+    tj["fp64_pipe_busy"] = {"source": "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active, profiles/%s_ncu_full.md" % tag}
+    for k, nme in names.items():
+        tj["fp64_pipe_busy"][nme] = round(busy[k] / 100.0, 3)
+    if "ls_100M" in traffic:
+        tj["linear_LS_100M_bytes_per_point"] = traffic["ls_100M"] / 1e8
+    with open(os.path.join(dst, "traffic.json"), "w") as f:
+        json.dump(tj, f, indent=1)
+    print("wrote traffic.json")
