@@ -341,6 +341,17 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 __device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
 
+// 1 / sqrt(x) to working precision without the IEEE sequence: approximation + two Newton steps (the rotation parameters of
+// the Jacobi SVD need c^2 + s^2 = 1 to rounding, one step leaves 1e-13).
+__device__ __forceinline__ double full_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma((x * r) * -0.5, r, 0.5), r);
+    r = fma(r, fma((x * r) * -0.5, r, 0.5), r);
+    return r;
+}
+__device__ __forceinline__ float full_rsqrt(float x) { return 1.0f / sqrtf(x); }
+
 // Conditioning tiers of the normal-equation solve.  kappa^2(A) <= tr(M)^3 / (4 det(M)); tier 1: plain
 // adjugate solve (error ~ kappa^2 eps in theory; measured against the SVD solve on the forward-motion and small-baseline
 // rigs: <= 1.1e-11 for bounds up to 1e6, which is the limit -- at the old limit 2e4 the forward-motion rig sent 31 % of its

@@ -822,25 +822,110 @@ __device__ __forceinline__ void dlt_matrix(const Cams<TC>& cams, TC u1x, TC u1y,
     }
 }
 
-// Reference path: one-sided Jacobi SVD (what cv::SVD does for a small matrix).  Out of line: used only when the
-// fast path cannot certify its answer (points at infinity / on the baseline, NaN systems).
+// Reference path: one-sided Jacobi SVD (the method cv::SVD runs on a small matrix), preconditioned the Drmac-Veselic way.
+// Out of line: used only when the fast path cannot certify its answer (no gap at the level of G, i.e. low parallax -- 10 %
+// of the forward-motion rig --, points at infinity / on the baseline, NaN systems).
+//   B = Q R by Householder reflections (R keeps B's singular values and right singular vectors; backward stable), then
+//   the rotations orthogonalise the ROWS of R, i.e. the columns of R^T:  R^T V = U' Sigma  =>  R = V Sigma U'^T, so the
+//   right singular vectors of B are the normalised rows themselves and no V has to be accumulated; the row of smallest
+//   norm is the answer.  On the triangular factor the sweeps converge in 3 instead of 5 (12 instead of 21 rotations per
+//   point on the forward rig), and accuracy is governed by the relative gap of the singular values of B, not of G = B^T B.
+// Rotation parameters from two rsqrt (approximation + two Newton steps, full_rsqrt) instead of three IEEE sqrt and two divisions.
 template <typename TC, int ROWS>
 __device__ __noinline__ void eigen_point_jacobi(const Cams<TC>& cams, TC u1x, TC u1y, TC u2x, TC u2y, TC X[4]) {
-    TC B[ROWS][4], V[4][4];
+    TC B[ROWS][4], R[4][4];
     dlt_matrix<TC, ROWS>(cams, u1x, u1y, u2x, u2y, B);
-    jacobi_svd<TC, ROWS, 4>(B, V);
-    TC best = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        TC s = 0;
+    for (int k = 0; k < 4; ++k) {
+        TC nn = 0;
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) s = tfma(B[r][j], B[r][j], s);
-        if (j == 0 || s < best || !(s == s)) {          // smallest column norm; a NaN system yields a NaN point
-            best = s;
+        for (int r = k; r < ROWS; ++r) nn = tfma(B[r][k], B[r][k], nn);
+        const TC nrm = tsqrt(nn);
+        const TC alpha = B[k][k] > TC(0) ? -nrm : nrm;
+        const TC v0 = B[k][k] - alpha;                       // same sign: no cancellation
+        const TC half_vtv = tfma(tabs(B[k][k]), nrm, nn);    // v.v / 2
+        const TC ib = half_vtv > TC(0) ? TC(1) / half_vtv : TC(0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) X[k] = (s == s) ? V[k][j] : s;
+        for (int j = 0; j < k; ++j) R[k][j] = TC(0);
+        R[k][k] = alpha;
+#pragma unroll
+        for (int j = k + 1; j < 4; ++j) {
+            TC dot = v0 * B[k][j];
+#pragma unroll
+            for (int r = k + 1; r < ROWS; ++r) dot = tfma(B[r][k], B[r][j], dot);
+            const TC sc = dot * ib;
+            R[k][j] = tfma(-sc, v0, B[k][j]);
+#pragma unroll
+            for (int r = k + 1; r < ROWS; ++r) B[r][j] = tfma(-sc, B[r][k], B[r][j]);
         }
     }
+    const TC eps2 = Num<TC>::eps() * Num<TC>::eps();
+#pragma unroll 1
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = i + 1; j < 4; ++j) {
+                TC a = 0, b = 0, p = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    a = tfma(R[i][k], R[i][k], a);
+                    b = tfma(R[j][k], R[j][k], b);
+                    p = tfma(R[i][k], R[j][k], p);
+                }
+                if (!(p * p > eps2 * a * b)) continue;                        // also skips NaN
+                const TC p2 = p + p, beta = a - b;
+                const TC q = tfma(p2, p2, beta * beta);
+                if (!(q > Num<TC>::tiny()) || !(q < Num<TC>::big())) continue;         // rotation not representable: leave the pair
+                changed = true;
+                const TC ig = full_rsqrt(q);                                  // 1 / gamma
+                const TC h = tfma(TC(0.5) * tabs(beta), ig, TC(0.5));         // (gamma + |beta|) / (2 gamma)  in [1/2, 1]
+                const TC ih = full_rsqrt(h);
+                const TC big = h * ih, small = TC(0.5) * p2 * ig * ih;        // sqrt(h),  p / (gamma sqrt(h))
+                const TC c = beta < TC(0) ? small : big, sn = beta < TC(0) ? big : small;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const TC t0 = tfma(c, R[i][k], sn * R[j][k]);
+                    const TC t1 = tfma(c, R[j][k], -sn * R[i][k]);
+                    R[i][k] = t0; R[j][k] = t1;
+                }
+            }
+        }
+        if (!changed) break;
+    }
+    // The row of smallest norm belongs to sigma4 -- but when sigma4 is at rounding level (exact correspondences) its
+    // DIRECTION is rounding noise too, so the answer is taken as the vector orthogonal to the other three rows (4-D cross
+    // product; their mutual orthogonality makes the minors well conditioned): error ~ eps sigma1 / sigma3 at worst.
+    TC nsq[4];
+    bool nan = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        nsq[j] = tfma(R[j][0], R[j][0], tfma(R[j][1], R[j][1], tfma(R[j][2], R[j][2], R[j][3] * R[j][3])));
+        nan |= !(nsq[j] == nsq[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {                             // move the smallest row to position 3
+        if (nsq[j] < nsq[3]) {
+            const TC t = nsq[j]; nsq[j] = nsq[3]; nsq[3] = t;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const TC r = R[j][k]; R[j][k] = R[3][k]; R[3][k] = r; }
+        }
+    }
+    const TC m01 = tfma(R[1][0], R[2][1], -R[1][1] * R[2][0]), m02 = tfma(R[1][0], R[2][2], -R[1][2] * R[2][0]);
+    const TC m03 = tfma(R[1][0], R[2][3], -R[1][3] * R[2][0]), m12 = tfma(R[1][1], R[2][2], -R[1][2] * R[2][1]);
+    const TC m13 = tfma(R[1][1], R[2][3], -R[1][3] * R[2][1]), m23 = tfma(R[1][2], R[2][3], -R[1][3] * R[2][2]);
+    X[0] = -tfma(R[0][1], m23, tfma(-R[0][2], m13, R[0][3] * m12));
+    X[1] = tfma(R[0][0], m23, tfma(-R[0][2], m03, R[0][3] * m02));
+    X[2] = -tfma(R[0][0], m13, tfma(-R[0][1], m03, R[0][3] * m01));
+    X[3] = tfma(R[0][0], m12, tfma(-R[0][1], m02, R[0][2] * m01));
+    const TC xx = tfma(X[0], X[0], tfma(X[1], X[1], tfma(X[2], X[2], X[3] * X[3])));
+    // a unit vector, as the callers' tests assume; rank <= 2 (no cross product) falls back to the smallest row, and a
+    // NaN system yields a NaN point
+    const bool usable = xx > Num<TC>::tiny() && xx < Num<TC>::big();
+    const TC nrm = usable ? TC(1) / tsqrt(xx) : (nsq[3] > TC(0) ? TC(1) / tsqrt(nsq[3]) : TC(1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) X[k] = nan ? nsq[0] + nsq[1] + nsq[2] + nsq[3] : (usable ? X[k] : R[3][k]) * nrm;
 }
 
 // LDL^T (no pivoting) of the symmetric 4x4 S (order 00 01 02 03 11 12 13 22 23 33); optionally solves S y = b.
@@ -1181,7 +1266,8 @@ k_linear_eigen_general(const TI* __restrict__ u1, const TI* __restrict__ u2, con
         bool good;
         reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, i, a, b, c, d);
         // the stragglers of the hot kernel's warps get the same iteration on their own (up to kEigenLoneRounds rounds); what
-        // that does not certify either (no gap, breakdown, NaN) takes the one-sided Jacobi SVD, the path cv::SVD itself runs
+        // that does not certify either (no gap at the level of G -- low parallax --, breakdown, NaN) takes the one-sided
+        // Jacobi SVD, the path cv::SVD itself runs
         if (eigen_point_iter<TC, ROWS, false>(cams, a, b, c, d, X)) {
             eigen_finish_fast<TC>(X, max_coord, xs, good);          // same arithmetic, hence same bits, as in the hot kernel
         } else {
