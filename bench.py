@@ -585,10 +585,35 @@ def run_ours(args, rank, world, local_rank):
     per_solver = {}
     step_ms = elapsed_ms / args.steps
     static_src = "static: profiles/traffic.json (ncu --set full of the same kernel; not measured in this run)"
+    # FP64 side of the roofline ("measure with an FMA microbenchmark in the same run"): the device's DFMA rate
+    # with two and with three distinct register sources per instruction, live; the executed FP64 instructions per point are
+    # the ncu counts of the same kernels (static)
+    fp64 = None
+    try:
+        r2, r3 = tc.fp64_fma_rate(2, 8, 4), tc.fp64_fma_rate(3, 8, 4)
+        fp64 = {"fma_rate_two_register_sources": r2, "fma_rate_three_register_sources": r3, "unit": "warp FMA instructions/s",
+                "tflops_two_register_sources": r2 * 64 / 1e12, "tflops_three_register_sources": r3 * 64 / 1e12,
+                "method": "trgl_fp64_fma_rate: 8 independent chains per thread, 32 warps per SM, difference of a 4000- and a "
+                          "12000-iteration launch (CUDA events), run right after the timed steps; a DFMA with three distinct "
+                          "64-bit register sources issues every 3 cycles instead of 2 (register-file banks), "
+                          "csrc/trgl_probe.cuh"}
+    except RuntimeError as exc:                      # the probe is diagnostics only
+        fp64 = {"error": str(exc)}
+    executed = traffic.get("fp64_executed") or {}
     for s in SOLVERS:
         ms = float(np.mean(per_kernel[s]))
         gbs = ALG_BYTES[s] * n / (ms * 1e-3) / 1e9
-        per_solver[s] = {"kernel_ms": ms, "points_per_sec_per_gpu": n / (ms * 1e-3), "alg_bytes_per_point": ALG_BYTES[s],
+        ex = executed.get("linear_LS_eval" if (s == "linear_LS" and s in fused_names(args)) else s) or {}
+        fp64_rec = None
+        if ex and fp64 and "error" not in fp64:
+            warp_instr = ex["fp64_instr_per_point"] * n / 32.0
+            fp64_rec = {"fp64_instr_per_point_ncu": ex["fp64_instr_per_point"], "instr_per_point_ncu": ex["instr_per_point"],
+                        "three_source_share_ncu": ex["three_source_share"],
+                        "achieved_warp_instr_per_s": warp_instr / (ms * 1e-3),
+                        "frac_of_measured_fma_rate": warp_instr / (ms * 1e-3) / fp64["fma_rate_two_register_sources"],
+                        "frac_with_register_bank_cycles": warp_instr * ex["issue_cycles_over_minimum"] / (ms * 1e-3)
+                        / fp64["fma_rate_two_register_sources"]}
+        per_solver[s] = {"fp64": fp64_rec,"kernel_ms": ms, "points_per_sec_per_gpu": n / (ms * 1e-3), "alg_bytes_per_point": ALG_BYTES[s],
                          "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "share_of_step": ms / step_ms,
                          "includes": "solver kernel + follow-up kernel + evaluation (%s)" %
                                      ("epilogue" if s in fused_names(args) else "stand-alone pass"),
@@ -608,6 +633,7 @@ def run_ours(args, rank, world, local_rank):
                    "sharding": "contiguous point ranges; `value` has no data-path collective, the result gather is in `gather`",
                    "l2": "inputs (%.0f MB) exceed the 126 MB L2, no explicit flush" % (32.0 * n / 1e6)},
         "per_solver": per_solver,
+        "fp64_peak": fp64,
         "e2e": {"value": 4.0 * n * world * e2e_steps / res_s, "unit": UNIT, "steps": e2e_steps,
                 "h2d_bytes_per_step": h2d_res, "d2h_bytes_per_step": d2h,
                 "api": "h1, h2 = triangulation.resident(u1, u2); triangulation.*_triangulation(h1, P1, h2, P2) x 4 -- pinned host "

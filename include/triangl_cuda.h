@@ -308,6 +308,13 @@ int64_t trgl_set_deferred_capacity(int64_t max_points);
  * (current device, stream) since the library was loaded (bench.py reports the deferred fraction per solver with it).
  * Synchronises the stream. */
 int trgl_deferred_total(void* stream, int64_t* total);
+/* Diagnostics: FP64 FMA rate of the current device, measured (SURVEY.md section 8d asks for the FP64 peak from an FMA
+ * microbenchmark in the same run; the reference has no counterpart).  Every thread of ctas_per_sm x SMs CTAs of 256 threads
+ * runs `chains` (1, 2 or 8) independent chains x = fma(y, z, x); operands = 2: z comes from the constant bank (two
+ * register sources per instruction, the pipe's nominal 2 cycles per warp instruction), operands = 3: three distinct
+ * 64-bit register sources (3 cycles: register-file banking, csrc/trgl_probe.cuh).  Result: warp-level FMA instructions
+ * per second over the whole device (x 64 = flop/s).  Synchronises the device; ~10 ms. */
+int trgl_fp64_fma_rate(int operands, int chains, int ctas_per_sm, double* warp_fma_per_second);
 /* Diagnostics of the small-batch host path (n <= 32 Ki points: the SLAM keyframe sizes).  trgl_set_trace(1) makes every such
  * call add its host-side microseconds per phase to five accumulators -- staging memcpy in, kernel launches, stream
  * synchronise, memcpy out, number of calls -- which trgl_get_trace copies to out5 and clears.  Returns the previous setting. */

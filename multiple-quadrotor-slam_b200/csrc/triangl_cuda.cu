@@ -5,6 +5,7 @@
 #include "trgl_kernels.cuh"
 #include "trgl_multiview.cuh"
 #include "trgl_reproj.cuh"
+#include "trgl_probe.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -1002,6 +1003,41 @@ int trgl_get_trace(double* out5) {
     if (!out5) return fail(TRGL_E_BADARG, "out5 is NULL");
     std::lock_guard<std::mutex> lock(g_pipe_mutex);
     for (int k = 0; k < 5; ++k) { out5[k] = g_trace_us[k]; g_trace_us[k] = 0.0; }
+    return TRGL_OK;
+}
+int trgl_fp64_fma_rate(int operands, int chains, int ctas_per_sm, double* warp_fma_per_second) {
+    if (!warp_fma_per_second) return fail(TRGL_E_BADARG, "warp_fma_per_second is NULL");
+    *warp_fma_per_second = 0.0;
+    if ((operands != 2 && operands != 3) || (chains != 1 && chains != 2 && chains != 8) || ctas_per_sm < 1 || ctas_per_sm > 8)
+        return fail(TRGL_E_BADARG, "operands must be 2 or 3, chains 1, 2 or 8, ctas_per_sm 1..8");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    const int grid = sm_count() * ctas_per_sm, iters = 4000;
+    double* out = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&out), sizeof(double) * size_t(grid) * 256));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto run = [&](int it) {
+        const double a = 1.0000001;
+#define TRGL_PROBE(O, C) k_fp64_fma_rate<O, C><<<grid, 256>>>(out, it, a)
+        if (operands == 2) { if (chains == 1) TRGL_PROBE(2, 1); else if (chains == 2) TRGL_PROBE(2, 2); else TRGL_PROBE(2, 8); }
+        else { if (chains == 1) TRGL_PROBE(3, 1); else if (chains == 2) TRGL_PROBE(3, 2); else TRGL_PROBE(3, 8); }
+#undef TRGL_PROBE
+    };
+    run(100);                                   // warm-up (clocks, instruction cache)
+    float ms_short = 0.f, ms_long = 0.f;
+    cudaEventRecord(e0); run(iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms_short, e0, e1);
+    cudaEventRecord(e0); run(3 * iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms_long, e0, e1);
+    g_launches += 3;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    CK(cudaGetLastError());
+    // the difference of the two runs removes launch overhead, ramp and tail
+    const double warp_fma = 2.0 * iters * 8.0 * chains * 8.0 * grid;          // 8 warps per CTA
+    const double sec = (double(ms_long) - double(ms_short)) * 1e-3;
+    if (!(sec > 0)) return fail(TRGL_E_BADARG, "fp64 probe: non-positive time difference");
+    *warp_fma_per_second = warp_fma / sec;
     return TRGL_OK;
 }
 int trgl_deferred_total(void* stream, int64_t* total) {

@@ -36,6 +36,7 @@ EXPORTS = [
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
     "trgl_set_fused_eval", "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
     "trgl_set_result_mirrors_f32", "trgl_set_input_retention", "trgl_deferred_total", "trgl_vector_stat", "trgl_set_trace", "trgl_get_trace",
+    "trgl_fp64_fma_rate",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -915,6 +916,14 @@ def get_trace():
     out = (ctypes.c_double * 5)()
     check(lib().trgl_get_trace(out))
     return dict(zip(("stage_in_us", "launch_us", "sync_us", "stage_out_us", "calls"), [float(v) for v in out]))
+
+
+def fp64_fma_rate(operands=2, chains=8, ctas_per_sm=4):
+    """Measured FP64 FMA rate of the current device in warp instructions per second (x 64 = flop/s): `chains` independent
+    chains per thread, two (one source from the constant bank) or three distinct register sources per instruction."""
+    v = ctypes.c_double(0.0)
+    check(lib().trgl_fp64_fma_rate(int(operands), int(chains), int(ctas_per_sm), ctypes.byref(v)))
+    return float(v.value)
 
 
 def deferred_total(stream=None):

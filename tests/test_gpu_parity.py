@@ -1204,3 +1204,20 @@ def test_multiview_degenerate_and_nan(tri):
     x, st = tri.multiview_LS_triangulation(bad, Ps, valid2)
     xo, so = orc.multiview_LS_triangulation(us, Ps, valid2)
     assert np.isfinite(x).all() and rel_err(x, xo).max() < TOL64 and np.array_equal(st, so)
+
+
+@pytest.mark.gpu
+def test_fp64_fma_rate_probe():
+    """bench.py's FP64 roofline denominator: the two-register-source rate is near the nominal 64 lanes per clock and SM, and
+    a DFMA with three distinct register sources is slower by about the 2 : 3 the register-file banks allow."""
+    import triangl_cuda as tc
+    tc.require_device()
+    r2 = tc.fp64_fma_rate(2, 8, 4)
+    r3 = tc.fp64_fma_rate(3, 8, 4)
+    nominal = 148 * 2 * 1.965e9                    # warp instructions per second at the boost clock
+    assert 0.6 * nominal < r2 < 1.1 * nominal
+    assert 0.55 < r3 / r2 < 0.9
+    one_chain = tc.fp64_fma_rate(3, 1, 2)          # 16 warps per SM, one dependent chain each: latency-bound
+    assert one_chain < r3
+    with pytest.raises(RuntimeError):
+        tc.fp64_fma_rate(4, 8, 4)

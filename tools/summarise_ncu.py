@@ -5,15 +5,20 @@
      profiles/<tag>_bench_*.json    the bench lines of the same call
      profiles/traffic.json          DRAM bytes per point per solver (read by bench.py for roofline.traffic)
    python tools/summarise_ncu.py <tag>"""
+import collections
 import csv
 import glob
 import io
 import json
 import os
+import re
 import shutil
 import subprocess
 import sys
 from collections import defaultdict
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import sass_operands  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
@@ -100,7 +105,7 @@ if os.path.isfile(ll):
     print("wrote", tag + "_launches.md")
 
 # ---- full captures ------------------------------------------------------------------------------------------------
-traffic, busy, dur = {}, {}, {}
+traffic, busy, dur, fp64_exec = {}, {}, {}, {}
 with open(os.path.join(dst, tag + "_ncu_full.md"), "w") as f:
     f.write("# `ncu --set full --clock-control none --import-source on` captures (%s)\n\n" % tag)
     f.write("One launch per kernel after warm-up.  Times under the profiler are not bench values.\n")
@@ -132,6 +137,33 @@ with open(os.path.join(dst, tag + "_ncu_full.md"), "w") as f:
         srcp = ncu_csv(rep, "source")
         while srcp and srcp[0][0] != "Address":
             srcp.pop(0)
+        if srcp and "Instructions Executed" in srcp[0]:
+            # executed FP64 instructions and how many of them fetch three distinct 64-bit registers (3 issue cycles
+            # instead of 2: register-file banking, tools/sass_operands.py)
+            hh = srcp[0]
+            ci, ce = hh.index("Source"), hh.index("Instructions Executed")
+            prev, hist, all_inst = {}, collections.Counter(), 0.0
+            for r in srcp[1:]:
+                n_exec = num(r[ce]) if len(r) > ce else None
+                if not n_exec:
+                    continue
+                txt = re.sub(r"^@!?U?P\d+\s+", "", r[ci].strip())
+                mm = re.match(r"([A-Z0-9_.]+)\s+(.*)", txt)
+                if not mm:
+                    continue
+                all_inst += n_exec
+                if mm.group(1).split(".")[0] in ("DFMA", "DMUL", "DADD", "DSETP"):
+                    k3, prev = sass_operands.reads(mm.group(1), mm.group(2), prev)
+                    hist[k3] += n_exec
+                else:
+                    prev = {}
+            fp = sum(hist.values())
+            if fp:
+                fp64_exec[key] = {"warp_instr": fp, "all_warp_instr": all_inst, "three_source_share": hist[3] / fp,
+                                  "issue_cycles_over_minimum": sum(max(2, k) * c for k, c in hist.items()) / (2.0 * fp)}
+                f.write("\nExecuted: %.4g warp instructions, %.4g of them FP64 (%.1f %%); %.1f %% of the FP64 instructions read three "
+                        "distinct 64-bit registers (3 issue cycles instead of 2) -> FP64 issue cycles = %.3f x the 2-cycle minimum.\n"
+                        % (all_inst, fp, 100 * fp / all_inst, 100 * hist[3] / fp, fp64_exec[key]["issue_cycles_over_minimum"]))
         if srcp:
             hh = srcp[0]
             try:
@@ -164,6 +196,16 @@ if all(k in traffic for k in names):
     tj["fp64_pipe_busy"] = {"source": "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active, profiles/%s_ncu_full.md" % tag}
     for k, nme in names.items():
         tj["fp64_pipe_busy"][nme] = round(busy[k] / 100.0, 3)
+    if all(k in fp64_exec for k in names):
+        tj["fp64_executed"] = {"source": "executed-instruction counts of the source page of the same captures (10 M points): FP64 "
+                                         "instructions per point, and the share of them with three distinct register sources"}
+        for k, nme in list(names.items()) + [("ls_eval", "linear_LS_eval")]:
+            if k in fp64_exec:
+                e = fp64_exec[k]
+                tj["fp64_executed"][nme] = {"fp64_instr_per_point": round(e["warp_instr"] * 32 / 1e7, 1),
+                                            "instr_per_point": round(e["all_warp_instr"] * 32 / 1e7, 1),
+                                            "three_source_share": round(e["three_source_share"], 3),
+                                            "issue_cycles_over_minimum": round(e["issue_cycles_over_minimum"], 3)}
     if "ls_100M" in traffic:
         tj["linear_LS_100M_bytes_per_point"] = traffic["ls_100M"] / 1e8
     with open(os.path.join(dst, "traffic.json"), "w") as f:
