@@ -163,6 +163,8 @@ struct Deferred {
     unsigned int* ctl;            // ctl[0] = number of deferred points (may exceed cap), ctl[1] = ticket of the follow-up kernel,
                                   // ctl[2..3] = 64-bit running total of deferred points (diagnostics)
     unsigned int cap;
+    unsigned int* hint;           // page-locked host word (may be null): the follow-up kernel leaves ctl[0] there, the host sizes
+                                  // the NEXT follow-up grid of this solver with it
 };
 __device__ __forceinline__ void defer_point(const Deferred& df, int64_t i) {
     const unsigned int k = atomicAdd(&df.ctl[0], 1u);
@@ -707,6 +709,7 @@ __device__ __forceinline__ void followup_finish(const EvalArg<EVAL>& ev, const D
         if (atomicAdd(&df.ctl[1], 1u) == gridDim.x - 1) {
             // ctl[2..3]: running total of deferred points of this (device, stream), for diagnostics (trgl_deferred_total)
             *reinterpret_cast<unsigned long long*>(df.ctl + 2) += df.ctl[0];
+            if (df.hint) *reinterpret_cast<volatile unsigned int*>(df.hint) = df.ctl[0];
             df.ctl[0] = 0u; df.ctl[1] = 0u; __threadfence();
         }
     }

@@ -155,10 +155,18 @@ struct Scratch {
     int64_t* deferred = nullptr;      // deferred_cap indices: points a hot kernel hands to its follow-up kernel
     unsigned int deferred_cap = 0;    // grows with the batch size: one slot per point up to kDeferredMax
     unsigned int* deferred_ctl = nullptr;   // {count, ticket, 64-bit running total}, re-armed by the follow-up kernel
+    unsigned int* hint = nullptr;     // page-locked, device-visible: deferred count of the LAST call per solver kind (kHint*)
 };
+// How many points the last call of each solver deferred on this (device, stream): written by the follow-up kernel's last
+// block into page-locked memory, read -- without any synchronisation, it is only a hint -- when the next follow-up kernel
+// of that solver is sized.  Without it the follow-up grid is 2 CTAs per SM (an empty launch costs 4 us, 8-10 us at 8 per
+// SM); a rig that defers 10^5-10^6 points (forward motion) then runs them in 1.5-2 rounds per thread instead of one wave.
+enum { kHintLs = 0, kHintIter, kHintEigen, kHintPoly, kHintMultiview, kHintKinds = 8 };
 constexpr unsigned int kDeferredMin = 1u << 20, kDeferredMax = 1u << 26;
 std::atomic<unsigned int> g_deferred_limit{kDeferredMax};     // trgl_set_deferred_capacity (test knob)
 int scratch_for(cudaStream_t s, Scratch& out, int64_t deferred_points = 0);
+Deferred make_deferred(const Scratch& sc, int kind);
+unsigned followup_grid(const Scratch& sc, int kind, int64_t tiles);
 
 // ------------------------------------------------------------------------------------------------------------
 // Device-pointer launchers, one per solver.  MODE_SWITCH instantiates the five precision modes.
@@ -285,13 +293,11 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
         Scratch sc;
         rc = scratch_for(s, sc, n);
         if (rc) return rc;
-        const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+        const Deferred df = make_deferred(sc, kHintLs);
         const Cams<float> cams = make_cams<float>(P1, P2);
         const float* a = static_cast<const float*>(u1); const float* b = static_cast<const float*>(u2);
         k_linear_ls_f32x4<<<grid_for((n + 3) / 4, kThreads), kThreads, 0, s>>>(a, b, cams, make_cams<double>(P1, P2), static_cast<float*>(x), status, n, df);
-        const int64_t tiles = (n + kThreads - 1) / kThreads;
-        const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
-        launch_followup(k_linear_ls_general<float, double, float, PreNone, false>, static_cast<unsigned>(tiles < cap ? tiles : cap), s,
+        launch_followup(k_linear_ls_general<float, double, float, PreNone, false>, followup_grid(sc, kHintLs, (n + kThreads - 1) / kThreads), s,
                         a, b, make_cams<double>(P1, P2), static_cast<float*>(x), n, PreNone{}, kNoMirrors, EvalArg<false>{}, df);
         g_launches += 2;
         CK(cudaGetLastError());
@@ -318,12 +324,12 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
                 // float64 arithmetic with 4 points per thread (or pixel inputs): the hot kernel defers what is beyond tier 1
                 // to a follow-up kernel instead of redoing it in line (no subroutine call in the hot kernel)
                 const bool defer = sizeof(TC) == 8 && g_two_ray.load() && (pre || ev || ppt == 4);
-                Deferred df = {nullptr, nullptr, 0u};
+                Deferred df = {nullptr, nullptr, 0u, nullptr};
+                Scratch sc;
                 if (defer) {
-                    Scratch sc;
                     rc = scratch_for(s, sc, n);
                     if (rc) break;
-                    df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+                    df = make_deferred(sc, kHintLs);
                 }
                 with_eval(ev, [&](auto E, auto evarg) {
                     constexpr bool EV = decltype(E)::value;
@@ -350,9 +356,7 @@ int launch_linear_ls(const void* u1, const void* u2, const double* P1, const dou
                             k_linear_ls<TI, TC, TO, 1, PreNone, false><<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, cams, xo, status, n, PreNone{}, mir, EvalArg<false>{}, df);
                         }
                         if (defer) {
-                            const int64_t tiles = (n + kThreads - 1) / kThreads;
-                            const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
-                            const unsigned fgrid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+                            const unsigned fgrid = followup_grid(sc, kHintLs, (n + kThreads - 1) / kThreads);
                             if (pre) launch_followup(k_linear_ls_general<TI, TC, TO, PreUndistort, EV>, fgrid, s, a, b, cams, xo, n, PreUndistort{*pre}, mir, evarg, df);
                             else launch_followup(k_linear_ls_general<TI, TC, TO, PreNone, EV>, fgrid, s, a, b, cams, xo, n, PreNone{}, mir, evarg, df);
                             g_launches++;
@@ -376,7 +380,7 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
     Scratch sc;
     int rc = scratch_for(s, sc, n);
     if (rc) return rc;
-    const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+    const Deferred df = make_deferred(sc, kHintIter);
     const int py = semantics == TRGL_ITER_PY ? 1 : 0;
     int nlaunch = 0;
     MODE_SWITCH(mode, {
@@ -396,9 +400,7 @@ int launch_iterative_ls(const void* u1, const void* u2, const double* P1, const 
                         auto kern = k_iterative_ls<TI, TC, TO, PRE, EV>;
                         kern<<<persistent_grid(kern, n, smem), kThreads, smem, s>>>(
                             a, b, cams, geom, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df);
-                        const int64_t tiles = (n + kThreads - 1) / kThreads;
-                        const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
-                        launch_followup(general, static_cast<unsigned>(tiles < cap ? tiles : cap), s,
+                        launch_followup(general, followup_grid(sc, kHintIter, (n + kThreads - 1) / kThreads), s,
                                         a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(tol), py, prearg, mir, evarg, df, 0);
                         nlaunch = 2;
                     } else {
@@ -426,7 +428,7 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
     Scratch sc;
     int rc = scratch_for(s, sc, n);
     if (rc) return rc;
-    const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+    const Deferred df = make_deferred(sc, kHintEigen);
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
         const TI* a = static_cast<const TI*>(u1); const TI* b = static_cast<const TI*>(u2);
@@ -439,8 +441,7 @@ int launch_linear_eigen(const void* u1, const void* u2, const double* P1, const 
                     // hot kernel (Rayleigh-quotient iteration, certified) + follow-up over the points it deferred (Jacobi SVD)
                     auto launch = [&](auto kern, auto general) {
                         kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
-                        const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
-                        launch_followup(general, static_cast<unsigned>(tiles < cap ? tiles : cap), s, a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
+                        launch_followup(general, followup_grid(sc, kHintEigen, tiles), s, a, b, cams, static_cast<TO*>(x), status, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
                     };
                     if (rows == 4) launch(k_linear_eigen<TI, TC, TO, 4, PRE, EV>, k_linear_eigen_general<TI, TC, TO, 4, PRE, EV>);
                     else launch(k_linear_eigen<TI, TC, TO, 6, PRE, EV>, k_linear_eigen_general<TI, TC, TO, 6, PRE, EV>);
@@ -463,7 +464,7 @@ int launch_polynomial(const void* u1, const void* u2, const double* P1, const do
     Scratch sc;
     int rc = scratch_for(s, sc, n);
     if (rc) return rc;
-    const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+    const Deferred df = make_deferred(sc, kHintPoly);
     int nlaunch = 0;
     MODE_SWITCH(mode, {
         const Cams<TC> cams = make_cams<TC>(P1, P2);
@@ -480,8 +481,7 @@ int launch_polynomial(const void* u1, const void* u2, const double* P1, const do
                         if (closed_form) {
                             // hot kernel (certified correction + ray intersection) + follow-up over the points it deferred
                             kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, geom, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
-                            const int64_t cap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
-                            launch_followup(general, static_cast<unsigned>(tiles < cap ? tiles : cap), s, a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 0);
+                            launch_followup(general, followup_grid(sc, kHintPoly, tiles), s, a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 0);
                             nlaunch = 2;
                         } else {
                             // no finite camera centre / closed forms switched off: the complete per-point path for every point
@@ -543,6 +543,11 @@ int scratch_for(cudaStream_t s, Scratch& out, int64_t deferred_points) {
         CK(cudaMemset(sc.flags, 0, sizeof(unsigned int) * (kFlagWords + 8)));
         sc.counter = sc.flags + kFlagWords;
         sc.deferred_ctl = sc.flags + kFlagWords + 2;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&sc.hint), sizeof(unsigned int) * kHintKinds, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+            std::memset(sc.hint, 0, sizeof(unsigned int) * kHintKinds);
+        } else {
+            cudaGetLastError(); sc.hint = nullptr;      // no hint: fixed follow-up grids
+        }
     }
     if (deferred_points > 0) {
         // one slot per point of the batch (a rig can defer most of its points, e.g. forward motion under heavy noise)
@@ -559,6 +564,24 @@ int scratch_for(cudaStream_t s, Scratch& out, int64_t deferred_points) {
     }
     out = sc;
     return TRGL_OK;
+}
+
+Deferred make_deferred(const Scratch& sc, int kind) {
+    return Deferred{sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load()), sc.hint ? sc.hint + kind : nullptr};
+}
+unsigned followup_grid(const Scratch& sc, int kind, int64_t tiles) {
+    const int64_t sms = sm_count();
+    int64_t cap = kFollowupCtasPerSm * sms;
+    // Measured (profiles/r02u_sweep_rigs_10M.jsonl): one wave instead of 1.5-2 rounds per thread pays where a deferred point
+    // is expensive -- polynomial's Durand-Kerner sweeps, ~5e4 instructions: forward-motion rig 1.37 -> 1.20 ms per 10 M points
+    // -- and costs 3 % where it is cheap (linear_eigen, ~1e3 instructions: the larger launch outweighs the shorter tail).
+    if (sc.hint && kind == kHintPoly) {
+        const unsigned int last = reinterpret_cast<volatile unsigned int*>(sc.hint)[kind];
+        int64_t want = (static_cast<int64_t>(last) + kThreads - 1) / kThreads;
+        want += want / 8;
+        cap = std::max(cap, std::min(want, 16 * sms));
+    }
+    return static_cast<unsigned>(tiles < cap ? tiles : cap);
 }
 
 // Result mirrors / fused evaluation apply to ONE solver call: whatever that call's outcome (argument error, n == 0,
@@ -1105,7 +1128,7 @@ static int launch_multiview_ls(void* const* u, void* const* valid, const double*
     Scratch sc;
     int rc = scratch_for(s, sc, n);
     if (rc) return rc;
-    const Deferred df = {sc.deferred, sc.deferred_ctl, std::min(sc.deferred_cap, g_deferred_limit.load())};
+    const Deferred df = make_deferred(sc, kHintMultiview);
     MODE_SWITCH(mode, {
         if constexpr (sizeof(TC) == 8) {
             MultiViewArgs<TI, TC> args;
@@ -1132,9 +1155,7 @@ static int launch_multiview_ls(void* const* u, void* const* valid, const double*
                 if (masked) go(k_multiview_ls<TI, TC, TO, 1, 8, 2, true>, kThreads);
                 else go(k_multiview_ls<TI, TC, TO, 1, 8, 2, false>, kThreads);
             }
-            const int64_t ftiles = (n + kThreads - 1) / kThreads;
-            const int64_t fcap = kFollowupCtasPerSm * static_cast<int64_t>(sm_count());
-            launch_followup(k_multiview_general<TI, TC, TO>, static_cast<unsigned>(ftiles < fcap ? ftiles : fcap), s,
+            launch_followup(k_multiview_general<TI, TC, TO>, followup_grid(sc, kHintMultiview, (n + kThreads - 1) / kThreads), s,
                             args, static_cast<TO*>(x), n, df);
         } else {
             rc = fail(TRGL_E_BADARG, "multi-view triangulation computes in float64");
