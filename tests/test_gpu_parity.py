@@ -178,6 +178,31 @@ def test_deferred_list_overflow_redoes_every_point(tri):
     assert np.array_equal(st[keep], so[keep]) and rel_err(x, xo)[keep].max() < TOL64
 
 
+@pytest.mark.gpu
+def test_followup_grid_hint_does_not_change_results(tri):
+    """polynomial sizes its follow-up grid from the number of points its previous call on the same stream deferred (a
+    page-locked hint, no synchronisation).  First call: default grid; later calls: the hinted one.  Same bits."""
+    import triangl_cuda as tc
+    n = 300007
+    u1, P1, u2, P2, X = rig.make_correspondences(n, "forward", 20.0)
+    d1, d2 = tc.to_device(u1), tc.to_device(u2)
+    outs, deferred = [], []
+    for call in range(3):
+        x = tc.DeviceArray((n, 3), np.float64); st = tc.DeviceArray((n,), np.uint8)
+        before = tc.deferred_total()
+        tc.polynomial(d1, P1, d2, P2, x=x, status=st, check_all_nan=False)
+        deferred.append(tc.deferred_total() - before)
+        outs.append((x.to_host(), st.to_host()))
+    # enough deferred points for the hint to enlarge the grid beyond 2 CTAs per SM (148 x 2 x 256 = 75776 points)
+    assert min(deferred) > 80000 and len(set(deferred)) == 1, deferred
+    for x, st in outs[1:]:
+        assert np.array_equal(st, outs[0][1]) and np.array_equal(x, outs[0][0], equal_nan=True)
+    xo, so = orc.SOLVERS["polynomial"](u1, P1, u2, P2)
+    n1, n2 = orc.correct_matches(orc.fundamental_from_P(P1, P2), u1, u2)
+    ok = eigen_well_posed(n1, P1, n2, P2) & np.isfinite(xo).all(axis=1)
+    assert np.array_equal(outs[2][1].astype(bool)[ok], so[ok]) and rel_err(outs[2][0], xo)[ok].max() < TOL64
+
+
 @pytest.mark.parametrize("name", ["linear_eigen", "linear_LS", "iterative_LS", "polynomial"])
 def test_deferred_list_overflow_with_fused_evaluation(tri, name):
     """List overflow + evaluation epilogue: the follow-up kernel redoes and re-evaluates EVERY point, so the hot kernel's
