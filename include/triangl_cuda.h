@@ -308,6 +308,11 @@ int64_t trgl_set_deferred_capacity(int64_t max_points);
  * (current device, stream) since the library was loaded (bench.py reports the deferred fraction per solver with it).
  * Synchronises the stream. */
 int trgl_deferred_total(void* stream, int64_t* total);
+/* Diagnostics: how often the rare paths of polynomial's correction ran on the current device since load (or the last reset):
+ * out5 = {points through the certified real-root isolation, dyadic intervals it visited, points it could not certify,
+ * points through Durand-Kerner (cv::solvePoly's method, ~57 000 instructions each), most intervals visited for one point}.
+ * Synchronises the device. */
+int trgl_rare_path_counters(unsigned long long* out5, int reset);
 /* Diagnostics: FP64 FMA rate of the current device, measured (SURVEY.md section 8d asks for the FP64 peak from an FMA
  * microbenchmark in the same run; the reference has no counterpart).  Every thread of ctas_per_sm x SMs CTAs of 256 threads
  * runs `chains` (1, 2 or 8) independent chains x = fma(y, z, x); operands = 2: z comes from the constant bank (two

@@ -1363,13 +1363,17 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
     fused_eval_finish<EVAL>(ev, acc, df.ctl, df.cap);
 }
 
-// Follow-up kernel of k_polynomial: the complete correction (Durand-Kerner root finding as cv::solvePoly runs it) and the
-// eigen solver (Rayleigh-quotient iteration, Jacobi SVD) for the deferred points, or for every point if the list
-// overflowed / the two-ray forms are switched off (all != 0: k_polynomial is then not launched).
+// Follow-up kernel of k_polynomial: the complete correction (bracketed Newton under the monotonicity certificate, certified
+// isolation of all real roots, Durand-Kerner as cv::solvePoly runs it -- in that order) and the triangulation of the
+// corrected match (certified ray intersection, else the eigen solver) for the deferred points, or for every point if the
+// list overflowed / the two-ray forms are switched off (all != 0: k_polynomial is then not launched; no ray intersection).
+#ifndef TRGL_POLY_GENERAL_MINB
+#define TRGL_POLY_GENERAL_MINB 2
+#endif
 template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, TRGL_POLY_GENERAL_MINB)
 k_polynomial_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-                     const __grid_constant__ HSParams hs, TO* __restrict__ x, uint8_t* __restrict__ status,
+                     const __grid_constant__ RayGeom<TC> geom, const __grid_constant__ HSParams hs, TO* __restrict__ x, uint8_t* __restrict__ status,
                      TI* __restrict__ u1c, TI* __restrict__ u2c, unsigned int* __restrict__ not_nan_count, const int64_t n,
                      const TC max_coord, const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
                      const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df, const int all) {
@@ -1393,8 +1397,19 @@ k_polynomial_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const
         any1 = any1 || !(n1x != n1x) || !(n1y != n1y);
         any2 = any2 || !(n2x != n2x) || !(n2y != n2y);
         TC xs[3]; bool good;
-        eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
-                              static_cast<TC>(r2y), max_coord, xs, good);
+        // as in the hot kernel: the corrected match satisfies the epipolar constraint, so the two viewing rays meet and
+        // their certified intersection IS the smallest singular vector; the eigen solver (Rayleigh-quotient iteration,
+        // Jacobi SVD for the low-parallax points of exactly the rigs that defer here) only for what that does not certify
+        bool met = false;
+        if (!all && geom.ok) {
+            const TC res_tol = sizeof(TI) == 8 ? TC(1e-11) : TC(1e-7);
+            met = tworay_intersection<TC>(cams, geom, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
+                                          static_cast<TC>(r2y), res_tol, xs);
+            good = tmax(tmax(tabs(xs[0]), tabs(xs[1])), tabs(xs[2])) <= max_coord;     // triangulation.py:23
+        }
+        if (!met)
+            eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
+                                  static_cast<TC>(r2y), max_coord, xs, good);
 #pragma unroll
         for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
         for (int m = 0; m < mir.count; ++m) {

@@ -481,12 +481,12 @@ int launch_polynomial(const void* u1, const void* u2, const double* P1, const do
                         if (closed_form) {
                             // hot kernel (certified correction + ray intersection) + follow-up over the points it deferred
                             kern<<<persistent_grid(kern, n), kThreads, 0, s>>>(a, b, cams, geom, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df);
-                            launch_followup(general, followup_grid(sc, kHintPoly, tiles), s, a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 0);
+                            launch_followup(general, followup_grid(sc, kHintPoly, tiles), s, a, b, cams, geom, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 0);
                             nlaunch = 2;
                         } else {
                             // no finite camera centre / closed forms switched off: the complete per-point path for every point
                             if constexpr (EV) cudaMemsetAsync(evarg.e.sums_out, 0, 4 * sizeof(double), s);
-                            general<<<persistent_grid(general, n), kThreads, 0, s>>>(a, b, cams, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 1);
+                            general<<<persistent_grid(general, n), kThreads, 0, s>>>(a, b, cams, geom, hs, static_cast<TO*>(x), status, static_cast<TI*>(u1c), static_cast<TI*>(u2c), flags, n, static_cast<TC>(maxc), prearg, mir, evarg, df, 1);
                             nlaunch = 1;
                         }
                     };
@@ -1026,6 +1026,18 @@ int trgl_get_trace(double* out5) {
     if (!out5) return fail(TRGL_E_BADARG, "out5 is NULL");
     std::lock_guard<std::mutex> lock(g_pipe_mutex);
     for (int k = 0; k < 5; ++k) { out5[k] = g_trace_us[k]; g_trace_us[k] = 0.0; }
+    return TRGL_OK;
+}
+int trgl_rare_path_counters(unsigned long long* out5, int reset) {
+    unsigned long long* out4 = out5;
+    if (!out4) return fail(TRGL_E_BADARG, "out5 is NULL");
+    if (!have_device()) return fail(TRGL_E_NODEVICE, "no CUDA device available (libtriangl_cuda has no CPU fallback)");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out4, g_hs_counters, 5 * sizeof(unsigned long long)));
+    if (reset) {
+        const unsigned long long zero[5] = {0, 0, 0, 0, 0};
+        CK(cudaMemcpyToSymbol(g_hs_counters, zero, sizeof(zero)));
+    }
     return TRGL_OK;
 }
 int trgl_fp64_fma_rate(int operands, int chains, int ctas_per_sm, double* warp_fma_per_second) {

@@ -36,7 +36,7 @@ EXPORTS = [
     "trgl_eval_errors_3d", "trgl_eval_errors_2d", "trgl_median", "trgl_pair_reproj_async",
     "trgl_set_fused_eval", "trgl_set_result_mirrors", "trgl_ipc_export", "trgl_ipc_import", "trgl_ipc_close",
     "trgl_set_result_mirrors_f32", "trgl_set_input_retention", "trgl_deferred_total", "trgl_vector_stat", "trgl_set_trace", "trgl_get_trace",
-    "trgl_fp64_fma_rate",
+    "trgl_fp64_fma_rate", "trgl_rare_path_counters",
     "trgl_undistort_points", "trgl_linear_ls_px", "trgl_iterative_ls_px", "trgl_linear_eigen_px", "trgl_polynomial_px",
 ]
 
@@ -916,6 +916,13 @@ def get_trace():
     out = (ctypes.c_double * 5)()
     check(lib().trgl_get_trace(out))
     return dict(zip(("stage_in_us", "launch_us", "sync_us", "stage_out_us", "calls"), [float(v) for v in out]))
+
+
+def rare_path_counters(reset=False):
+    """dict(isolated, intervals, not_certified, durand_kerner, max_intervals): points through the rare paths of polynomial's correction."""
+    out = (ctypes.c_ulonglong * 5)()
+    check(lib().trgl_rare_path_counters(out, 1 if reset else 0))
+    return dict(zip(("isolated", "intervals", "not_certified", "durand_kerner", "max_intervals"), [int(v) for v in out]))
 
 
 def fp64_fma_rate(operands=2, chains=8, ctas_per_sm=4):

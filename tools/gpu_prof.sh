@@ -3,7 +3,7 @@
 # source pages are exported as CSV on the box (the reports themselves exceed what gpurun brings back).
 #   gpurun --timeout 900 -- 'bash tools/gpu_prof.sh <tag> "name=kernel_regex:solver:points:mode:extra_flags ..."'
 #   e.g.  "eigen_eval=k_linear_eigen:linear_eigen:10000000:f64:--eval  ls_100M=k_linear_ls:linear_LS:100000000:f64:"
-#   solver "mv8m" = masked 8-view multi-view sweep.
+#   solver "mv8m" = masked 8-view multi-view sweep; "+" inside extra_flags stands for a blank.
 set -u
 TAG=${1:-prof}
 OUT=gpurun_out/$TAG
@@ -11,6 +11,7 @@ mkdir -p $OUT
 for SPEC in ${2:-iter_eval=k_iterative_ls:iterative_LS:10000000:f64:--eval}; do
   NAME=${SPEC%%=*}; REST=${SPEC#*=}
   IFS=: read -r K S N MODE FLAGS <<< "$REST"
+  FLAGS=${FLAGS//+/ }            # "+" stands for a blank inside a spec: --eval+--rig+forward
   if [ "$S" = mv8m ]; then
     CMD="python tools/sweep_multiview.py --views 8 --visible 0.7 --iters 2 --points $N"
   else
