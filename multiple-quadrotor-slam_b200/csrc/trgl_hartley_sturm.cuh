@@ -140,7 +140,7 @@ __device__ __noinline__ double hs_select_dk(const double k[7], double a, double 
 //     |c1| > sum_{j>=2} j |c_j| h^(j-1)      -> g' keeps its sign: at most one root, present iff the end values differ in
 //                                               sign -> bracketed Newton in the shifted variable;
 //     neither                                 -> split (depth <= 24, else give up -> Durand-Kerner).
-//   Measured on 6000 points per rig / noise level against the oracle's Durand-Kerner selection (NumPy restatement of this
+//   Measured on 6000 points per rig / noise level against a CPU restatement of cv::solvePoly's selection (NumPy restatement of this
 //   function): no mismatch over 1e-9, no give-up; intervals visited: mean 1.2 / 11.7 / 23 at 0.8 / 8 / 20 px on the
 //   forward-motion rig, 1.0 elsewhere.
 // Returns false when it cannot certify (non-finite tests, depth limit, no root inside a finite T0): the caller runs
