@@ -1322,7 +1322,7 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
         if constexpr (PRE::kActive) pre_stage.template apply<TI, TC>(a, b, c, d);
         // The correction always runs in double: the degree-6 coefficients span many orders of magnitude.
         double n1x, n1y, n2x, n2y;
-        bool certified = hs_correct<false>(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c),
+        bool certified = hs_correct_fast(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c),
                                            static_cast<double>(d), n1x, n1y, n2x, n2y);
         // cv2.correctMatches returns the dtype of its input, so the corrected points are rounded to TI
         // before the triangulation (triangulation.py:224,232).
@@ -1363,61 +1363,164 @@ k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_
     fused_eval_finish<EVAL>(ev, acc, df.ctl, df.cap);
 }
 
-// Follow-up kernel of k_polynomial: the complete correction (bracketed Newton under the monotonicity certificate, certified
-// isolation of all real roots, Durand-Kerner as cv::solvePoly runs it -- in that order) and the triangulation of the
-// corrected match (certified ray intersection, else the eigen solver) for the deferred points, or for every point if the
-// list overflowed / the two-ray forms are switched off (all != 0: k_polynomial is then not launched; no ray intersection).
 #ifndef TRGL_POLY_GENERAL_MINB
 #define TRGL_POLY_GENERAL_MINB 2
 #endif
+// Shared memory of one k_polynomial_general CTA: the subdivision of hs_interval_test for the CTA's 256 points, one dyadic
+// level at a time.  Work items are intervals, not points: a point whose roots need 188 intervals (the worst of 10 M on the
+// forward-motion rig; 18.6 on average) occupies many lanes for a few levels instead of one lane for 188 rounds.
+constexpr int kIsoQueueCap = 2048;
+struct IsoSmem {
+    double p[8][kThreads];                          // k0..k6 of each thread's point; [7] = radius of its t-domain
+    unsigned int queue[2][kIsoQueueCap];            // intervals of this / the next level: point << 24 | domain << 23 | position
+    unsigned int roots[kThreads][kIsoMaxRoots];     // recorded single-root intervals: depth << 24 | domain << 23 | position
+    unsigned int nroots[kThreads], giveup[kThreads], visited[kThreads];
+    unsigned int count[2];
+};
+
+// Follow-up kernel of k_polynomial: the complete correction -- bracketed Newton under the monotonicity certificate, else
+// certified isolation of all real roots (level-synchronous over the CTA), else Durand-Kerner as cv::solvePoly runs it --
+// and the triangulation of the corrected match (certified ray intersection, else the eigen solver) for the deferred points,
+// or for every point if the list overflowed / the two-ray forms are switched off (all != 0: k_polynomial is then not
+// launched; no ray intersection).  A CTA takes 256 points at a time: phase A one point per thread (set-up, fast path),
+// phase B the subdivision of the points that need it, phase C one point per thread again (root refinement, cost scan,
+// closest points, triangulation, evaluation).
 template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
 __global__ void __launch_bounds__(kThreads, TRGL_POLY_GENERAL_MINB)
 k_polynomial_general(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
-                     const __grid_constant__ RayGeom<TC> geom, const __grid_constant__ HSParams hs, TO* __restrict__ x, uint8_t* __restrict__ status,
-                     TI* __restrict__ u1c, TI* __restrict__ u2c, unsigned int* __restrict__ not_nan_count, const int64_t n,
-                     const TC max_coord, const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
+                     const __grid_constant__ RayGeom<TC> geom, const __grid_constant__ HSParams hs, TO* __restrict__ x,
+                     uint8_t* __restrict__ status, TI* __restrict__ u1c, TI* __restrict__ u2c,
+                     unsigned int* __restrict__ not_nan_count, const int64_t n, const TC max_coord,
+                     const __grid_constant__ PRE pre_stage, const __grid_constant__ Mirrors mir,
                      const __grid_constant__ EvalArg<EVAL> ev, const __grid_constant__ Deferred df, const int all) {
     wait_for_hot_kernel();
+    __shared__ IsoSmem sm;
+    const unsigned int tid = threadIdx.x;
     const unsigned int listed = all ? 0u : df.ctl[0];
     const bool everything = all || listed > df.cap;
     const int64_t total = everything ? n : static_cast<int64_t>(listed);
+    const int64_t nchunks = (total + kThreads - 1) / kThreads;
     double acc[4] = {0, 0, 0, 0};
     bool any1 = false, any2 = false;
-    for (int64_t k = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; k < total;
-         k += static_cast<int64_t>(gridDim.x) * kThreads) {
-        const int64_t i = everything ? k : df.idx[k];
-        TC a, b, c, d;
-        reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, i, a, b, c, d);
-        double n1x, n1y, n2x, n2y;
-        hs_correct<true>(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c), static_cast<double>(d),
-                         n1x, n1y, n2x, n2y);
-        const TI r1x = static_cast<TI>(n1x), r1y = static_cast<TI>(n1y), r2x = static_cast<TI>(n2x), r2y = static_cast<TI>(n2y);
-        if (u1c) store_uv(u1c, i, r1x, r1y);
-        if (u2c) store_uv(u2c, i, r2x, r2y);
-        any1 = any1 || !(n1x != n1x) || !(n1y != n1y);
-        any2 = any2 || !(n2x != n2x) || !(n2y != n2y);
-        TC xs[3]; bool good;
-        // as in the hot kernel: the corrected match satisfies the epipolar constraint, so the two viewing rays meet and
-        // their certified intersection IS the smallest singular vector; the eigen solver (Rayleigh-quotient iteration,
-        // Jacobi SVD for the low-parallax points of exactly the rigs that defer here) only for what that does not certify
-        bool met = false;
-        if (!all && geom.ok) {
-            const TC res_tol = sizeof(TI) == 8 ? TC(1e-11) : TC(1e-7);
-            met = tworay_intersection<TC>(cams, geom, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
-                                          static_cast<TC>(r2y), res_tol, xs);
-            good = tmax(tmax(tabs(xs[0]), tabs(xs[1])), tabs(xs[2])) <= max_coord;     // triangulation.py:23
-        }
-        if (!met)
-            eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
-                                  static_cast<TC>(r2y), max_coord, xs, good);
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t kidx = chunk * kThreads + tid;
+        const bool have = kidx < total;
+        const int64_t i = have ? (everything ? kidx : df.idx[kidx]) : 0;
+        // ---- phase A: set-up and fast path, one point per thread ----
+        if (tid < 2) sm.count[tid] = 0u;
+        sm.nroots[tid] = 0u; sm.giveup[tid] = 0u; sm.visited[tid] = 0u;
+        __syncthreads();
+        TC a = 0, b = 0, c = 0, d = 0;
+        HsPoint P;
+        double kk[7];
+        double t = DBL_MAX;
+        bool subdivide = false;
+        if (have) {
+            reload_inputs<TI, TC, PRE>(u1, u2, pre_stage, i, a, b, c, d);
+            hs_setup(hs, static_cast<double>(a), static_cast<double>(b), static_cast<double>(c), static_cast<double>(d), P, kk);
+            if (P.fast) {
+                t = hs_newton_bracketed(kk, P.T0);
+            } else if (P.finite_coeffs) {
+                // certificate failed (g not monotone on [-T0, T0], or no finite T0): every real root, t in [-R0, R0] on g
+                // and, unless T0 <= 1, u = 1/t in [-1, 1] on the reversed polynomial
+                subdivide = true;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
-        for (int m = 0; m < mir.count; ++m) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) mirror_put<TO>(mir, m, 3 * i + q, static_cast<TO>(xs[q]));
+                for (int j = 0; j < 7; ++j) sm.p[j][tid] = kk[j];
+                sm.p[7][tid] = P.bounded ? fmin(P.T0, 1.0) : 1.0;
+                const bool second = !(P.bounded && P.T0 <= 1.0);
+                const unsigned int at = atomicAdd(&sm.count[0], second ? 2u : 1u);
+                sm.queue[0][at] = tid << 24;
+                if (second) sm.queue[0][at + 1] = (tid << 24) | (1u << 23);
+            }
         }
-        store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
-        fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);
+        __syncthreads();
+        // ---- phase B: level-synchronous subdivision, work items = intervals ----
+        int cur = 0;
+#pragma unroll 1
+        for (int depth = 0; depth <= kIsoMaxDepth; ++depth) {
+            const unsigned int na = sm.count[cur];
+            if (na == 0u) break;                                           // block-uniform
+            for (unsigned int q = tid; q < na; q += kThreads) {
+                const unsigned int item = sm.queue[cur][q];
+                const unsigned int prob = item >> 24, dom = (item >> 23) & 1u, pos = item & 0x7fffffu;
+                double p[7];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) p[j] = sm.p[dom ? 6 - j : j][prob];
+                const int verdict = hs_interval_test(p, dom ? 1.0 : sm.p[7][prob], depth, pos);
+                atomicAdd(&sm.visited[prob], 1u);
+                if (verdict == 2) {
+                    if (depth == kIsoMaxDepth) {
+                        sm.giveup[prob] = 1u;
+                    } else {
+                        const unsigned int at = atomicAdd(&sm.count[cur ^ 1], 2u);       // pairs: never half a slot at the cap
+                        if (at + 2u <= kIsoQueueCap) {
+                            const unsigned int child = (item & 0xff800000u) | (pos << 1);
+                            sm.queue[cur ^ 1][at] = child;
+                            sm.queue[cur ^ 1][at + 1] = child | 1u;
+                        } else {
+                            sm.giveup[prob] = 1u;
+                        }
+                    }
+                } else if (verdict == 1) {
+                    const unsigned int r = atomicAdd(&sm.nroots[prob], 1u);
+                    if (r < kIsoMaxRoots) sm.roots[prob][r] = (static_cast<unsigned int>(depth) << 24) | (item & 0xffffffu);
+                    else sm.giveup[prob] = 1u;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                if (sm.count[cur ^ 1] > kIsoQueueCap) sm.count[cur ^ 1] = kIsoQueueCap;
+                sm.count[cur] = 0u;
+            }
+            cur ^= 1;
+            __syncthreads();
+        }
+        // ---- phase C: one point per thread again ----
+        if (have) {
+            if (subdivide) {
+                const unsigned int nr = sm.nroots[tid];
+                bool ok = sm.giveup[tid] == 0u && nr <= kIsoMaxRoots;
+                if (ok) ok = hs_scan_roots(kk, sm.roots[tid], static_cast<int>(nr), sm.p[7][tid], P.bounded, P.a, P.b, P.c, P.d,
+                                           P.f1, P.f2, t);
+                atomicAdd(&g_hs_counters[0], 1ull);
+                atomicAdd(&g_hs_counters[1], static_cast<unsigned long long>(sm.visited[tid]));
+                atomicMax(&g_hs_counters[4], static_cast<unsigned long long>(sm.visited[tid]));
+                if (!ok) {
+                    atomicAdd(&g_hs_counters[2], 1ull);
+                    t = hs_select_dk(kk, P.a, P.b, P.c, P.d, P.f1, P.f2);
+                }
+            }
+            double n1x, n1y, n2x, n2y;
+            hs_finish(P, t, n1x, n1y, n2x, n2y);
+            const TI r1x = static_cast<TI>(n1x), r1y = static_cast<TI>(n1y), r2x = static_cast<TI>(n2x), r2y = static_cast<TI>(n2y);
+            if (u1c) store_uv(u1c, i, r1x, r1y);
+            if (u2c) store_uv(u2c, i, r2x, r2y);
+            any1 = any1 || !(n1x != n1x) || !(n1y != n1y);
+            any2 = any2 || !(n2x != n2x) || !(n2y != n2y);
+            TC xs[3]; bool good;
+            // as in the hot kernel: the corrected match satisfies the epipolar constraint, so the two viewing rays meet and
+            // their certified intersection IS the smallest singular vector; the eigen solver (Rayleigh-quotient iteration,
+            // Jacobi SVD for the low-parallax points of exactly the rigs that defer here) only for what that does not certify
+            bool met = false;
+            if (!all && geom.ok) {
+                const TC res_tol = sizeof(TI) == 8 ? TC(1e-11) : TC(1e-7);
+                met = tworay_intersection<TC>(cams, geom, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
+                                              static_cast<TC>(r2y), res_tol, xs);
+                good = tmax(tmax(tabs(xs[0]), tabs(xs[1])), tabs(xs[2])) <= max_coord;     // triangulation.py:23
+            }
+            if (!met)
+                eigen_point<TC, ROWS>(cams, static_cast<TC>(r1x), static_cast<TC>(r1y), static_cast<TC>(r2x),
+                                      static_cast<TC>(r2y), max_coord, xs, good);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) x[3 * i + q] = static_cast<TO>(xs[q]);
+            for (int m = 0; m < mir.count; ++m) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) mirror_put<TO>(mir, m, 3 * i + q, static_cast<TO>(xs[q]));
+            }
+            store_status(status, mir, i, static_cast<uint8_t>(good ? 1 : 0));
+            fused_eval_point<EVAL, TO, TC>(ev, true, i, a, b, c, d, xs, good ? 1 : 0, acc);
+        }
+        __syncthreads();                                   // the next chunk reuses the shared arrays
     }
     const int f1 = __syncthreads_or(any1), f2 = __syncthreads_or(any2);
     if (threadIdx.x == 0) {

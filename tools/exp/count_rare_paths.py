@@ -23,4 +23,4 @@ for name, sig, n in (("forward", 0.8, 10_000_000), ("forward", 0.8, 1_000_000), 
     for _ in range(10):
         e0.record(); tc.polynomial(d1, P1, d2, P2, x=x, status=st, check_all_nan=False); e1.record()
         ms.append(e0.elapsed_ms(e1))
-    print(name, sig, n, "deferred", deferred, cnt, "ms median %.4f" % float(np.median(ms)))
+    print("%s %.1f n %d deferred %d ms median %.4f" % (name, sig, n, deferred, float(np.median(ms))), cnt)
