@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU call: parity tests, smoke, the default bench line (N = 1), reference arm, SLAM latency.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_r02.sh r02a [phases]'      phases: tests,bench,ref,slam,launches,ncu (default: tests,bench,ref,slam)
+#   gpurun --timeout 1500 -- 'bash tools/gpu_r02.sh r02a [phases]'      phases: tests,smoke,bench,ref,slam,rigs,mv,launches,ncu,rare,probe (default: tests,bench,ref,slam)
 set -u
 TAG=${1:-r02}
 PH=${2:-tests,bench,ref,slam}
@@ -23,6 +23,13 @@ if has launches; then
   echo "launch list rc=$? lines=$(wc -l < $OUT/launches.csv)"
 fi
 if has ncu; then
-  bash tools/gpu_prof.sh $TAG "ls=k_linear_ls:linear_LS:10000000:f64: ls_100M=k_linear_ls:linear_LS:100000000:f64: ls_eval=k_linear_ls:linear_LS:10000000:f64:--eval iter_eval=k_iterative_ls:iterative_LS:10000000:f64:--eval eigen_eval=k_linear_eigen:linear_eigen:10000000:f64:--eval poly_eval=k_polynomial:polynomial:10000000:f64:--eval ls_f32_100M=k_linear_ls_f32x4:linear_LS:100000000:f32: mv8_masked=k_multiview_ls:mv8m:10000000::"
+  bash tools/gpu_prof.sh $TAG "ls=k_linear_ls:linear_LS:10000000:f64: ls_100M=k_linear_ls:linear_LS:100000000:f64: ls_eval=k_linear_ls:linear_LS:10000000:f64:--eval iter_eval=k_iterative_ls:iterative_LS:10000000:f64:--eval eigen_eval=k_linear_eigen:linear_eigen:10000000:f64:--eval poly_eval=k_polynomial:polynomial:10000000:f64:--eval ls_f32_100M=k_linear_ls_f32x4:linear_LS:100000000:f32: mv8_masked=k_multiview_ls:mv8m:10000000:: polyg_forward=k_polynomial_general:polynomial:10000000:f64:--eval+--rig+forward eigeng_forward=k_linear_eigen_general:linear_eigen:10000000:f64:--eval+--rig+forward"
+fi
+if has rare; then echo "== rare paths of polynomial"; timeout 300 python tools/exp/count_rare_paths.py > $OUT/rare_paths.txt 2>&1; cat $OUT/rare_paths.txt | cut -c1-300; fi
+if has probe; then
+  echo "== FP64 instruction-kind probe"
+  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/fp64_ops_probe tools/exp/fp64_ops_probe.cu > /dev/null 2>&1 && /tmp/fp64_ops_probe > $OUT/fp64_ops_probe.txt 2>&1
+  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/dfma_probe tools/exp/dfma_probe.cu > /dev/null 2>&1 && /tmp/dfma_probe >> $OUT/fp64_ops_probe.txt 2>&1
+  cat $OUT/fp64_ops_probe.txt
 fi
 ls -la $OUT | head -60
