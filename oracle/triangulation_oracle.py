@@ -304,6 +304,8 @@ def correct_matches(F, u1, u2, return_t=False):
         h1 = h1 / h1[:, 2:3]; h2 = h2 / h2[:, 2:3]
         n1 = np.einsum('nij,nkj,nk->ni', T1i, R1, h1)
         n2 = np.einsum('nij,nkj,nk->ni', T2i, R2, h2)
+    if return_t == 'system':      # + the per-point quantities the cost s(t) and the polynomial g(t) are made of
+        return n1[:, 0:2], n2[:, 0:2], t_min, k, (a, b, c, d, f1, f2)
     if return_t:
         return n1[:, 0:2], n2[:, 0:2], t_min, k
     return n1[:, 0:2], n2[:, 0:2]
