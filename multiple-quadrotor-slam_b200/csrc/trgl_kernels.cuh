@@ -1293,11 +1293,11 @@ k_linear_eigen_general(const TI* __restrict__ u1, const TI* __restrict__ u2, con
 // Hartley-Sturm correction of the match (cv2.correctMatches) followed by the triangulation of the corrected match, fused.
 // Hot kernel: the certified fast path of the correction, then the certified intersection of the two viewing rays (the
 // corrected match satisfies the epipolar constraint, so the rays meet and the smallest singular vector of the DLT system
-// is their intersection).  Whatever either certificate does not cover -- Durand-Kerner root finding, a correction that is
+// is their intersection).  Whatever either certificate does not cover -- a non-monotone g (root isolation), a correction that is
 // not exact after rounding to float32 storage, ill-conditioned or centre-less cameras -- is deferred to
-// k_polynomial_general, which runs the complete correction and the eigen solver per point; the hot kernel has no
-// subroutine call.  (On the forward-motion rig, where 1 % - 67 % of the points need Durand-Kerner, the slow lanes used to
-// hold their warps for ~100 sweeps: 21 ms per 10 M points before the split.)
+// k_polynomial_general, which runs the complete correction (CTA-cooperative) and the ray intersection / eigen solver per
+// point; the hot kernel has no subroutine call.  (On the forward-motion rig, where 1 % - 67 % of the points lack the certificate, the slow lanes used to
+// hold their warps for 100 Durand-Kerner sweeps: 21 ms per 10 M points before the split, 0.54 ms now.)
 template <typename TI, typename TC, typename TO, int ROWS, class PRE = PreNone, bool EVAL = false>
 __global__ void __launch_bounds__(kThreads, EVAL ? TRGL_EVAL_MINB : TRGL_POLY_MINB)
 k_polynomial(const TI* __restrict__ u1, const TI* __restrict__ u2, const __grid_constant__ Cams<TC> cams,
