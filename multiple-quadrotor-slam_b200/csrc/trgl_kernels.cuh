@@ -631,7 +631,8 @@ k_iterative_ls(const TI* __restrict__ u1, const TI* __restrict__ u2, const __gri
             int it = -1, r = -1;
             if (tworay_setup<TC>(cams, geom, a, b, c, d, R)) {
                 kap = R.kap;
-#pragma unroll 1
+#pragma unroll                                           // straight-line: no loop-carried register moves (72 instead of 78
+                                                         // registers, 0.263 instead of 0.269 ms per 10 M points)
                 for (int k = 0; k < kPhase1; ++k) {
                     r = tworay_step<TC>(R.d11, R.d12, R.d21, R.d22, kap, d1, d2, d1n, d2n, inv, kap_used, tolerance, py_semantics);
                     if (r) { if (r > 0) it = k; break; }
