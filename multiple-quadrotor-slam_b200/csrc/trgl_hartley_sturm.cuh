@@ -392,8 +392,7 @@ __device__ __forceinline__ bool hs_correct_fast(const HSParams& hs, double x1, d
         // whatever path the iteration took to get there.  Everything else is deferred.
         double tp = -k[0] * fast_rcp(k[1]);
         bool accepted = false;
-#pragma unroll 1
-        for (int it = 0; it < 4; ++it) {
+        auto newton_step = [&]() {
             double g = k[6], dg = 0.0;
 #pragma unroll
             for (int i = 5; i >= 0; --i) { dg = fma(dg, tp, g); g = fma(g, tp, k[i]); }
@@ -403,7 +402,13 @@ __device__ __forceinline__ bool hs_correct_fast(const HSParams& hs, double x1, d
                 accepted = (fabs(tn - tp) <= 1e-8 * fabs(tn)) && (fabs(tn) <= T0);
                 tp = tn;
             }
-            if (it >= 1 && __all_sync(0xffffffffu, accepted || !fast)) break;
+        };
+        newton_step();              // two steps straight-line (nobody is accepted before the second), then the warp votes
+        newton_step();
+#pragma unroll 1
+        for (int it = 2; it < 4; ++it) {
+            if (__all_sync(0xffffffffu, accepted || !fast)) break;
+            newton_step();
         }
         certified = fast && accepted;
         if (!certified) t = 0.0;
