@@ -559,6 +559,13 @@ def test_pinned_host_buffers(tri):
     xa, _ = tri.iterative_LS_triangulation(u1, P1, u2, P2)
     xb, _ = tri.iterative_LS_triangulation(p1, P1, p2, P2)
     assert np.array_equal(xa, xb)
+    # linear_LS through the chunked host pipeline (1.2 M points = 3 chunks) into a caller-provided status array
+    u1, P1, u2, P2, X = rig.make_correspondences(1_200_007, "rotating", 0.8)
+    st = np.zeros(len(u1), dtype=np.bool_)
+    x, st2 = tc.linear_ls(u1, P1, u2, P2, status=st)
+    xo, so = orc.linear_LS_triangulation(u1[::97], P1, u2[::97], P2)
+    assert st2 is st and st.all() and so.all()
+    assert rel_err(x[::97], xo).max() < TOL64
 
 
 # ---------------------------------------------------------------------------------------------------------------
