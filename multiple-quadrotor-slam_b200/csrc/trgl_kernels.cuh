@@ -175,6 +175,9 @@ __device__ __forceinline__ void defer_point(const Deferred& df, int64_t i) {
 // with the plain atomic (same registers, same occupancy -- the plain read-modify-write sits between the four
 // interleaved points of a thread), the FP64-bound kernels are 2-3 % slower with it.
 __device__ __forceinline__ void defer_point_warp(const Deferred& df, int64_t i) {
+    // Once the list has overflowed the follow-up kernel redoes every point anyway: no more appends.  (Same-address atomics
+    // run at ~1.3 G/s: a batch that defers all of its 10^8 points spent 2.4 ms on 3 M warp-level appends.)
+    if (*reinterpret_cast<volatile unsigned int*>(df.ctl) > df.cap) return;
     const unsigned mask = __activemask();
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(mask) - 1;
@@ -311,9 +314,15 @@ k_linear_ls_f32x4(const float* __restrict__ u1, const float* __restrict__ u2, co
                 status[i0 + p] = 1;
             }
     }
+    // No more appends once the list has overflowed (the follow-up kernel then redoes every point anyway): same-address
+    // atomics run at ~1.3 G/s, and a rig that defers every point (translating, forward motion) spent 2.4 of this kernel's
+    // 2.9 ms per 100 M points on them.  (Aggregating the four appends of a thread into one per warp, in line or out of
+    // line, cost the rigs that defer nothing 6-9 %: measured, profiles/README.md.)
+    if (!(ok[0] && ok[1] && ok[2] && ok[3]) && *reinterpret_cast<volatile unsigned int*>(df.ctl) <= df.cap) {
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
-        if (!ok[p] && i0 + p < n) defer_point(df, i0 + p);
+        for (int p = 0; p < 4; ++p)
+            if (!ok[p] && i0 + p < n) defer_point(df, i0 + p);
+    }
 }
 
 // ---- linear_LS, per-thread cp.async ring ---------------------------------------------------------------------------
