@@ -37,6 +37,10 @@
  *                  HBM-bound solver, has float32 arithmetic; iterative_LS (absolute 3e-5 depth tolerance at depth ~40
  *                  is 6 float ulps), linear_eigen and polynomial (smallest singular vector, degree-6 coefficients)
  *                  keep float64 registers and only halve the bytes moved -- for them TRGL_F32 == TRGL_F32IO.
+ *                  linear_LS solves a correspondence in float32 when its kappa^2 bound is below 300 (error <= 2e-5) and
+ *                  in float64 otherwise; a batch in which more than 1/8 of the correspondences are beyond that bound is
+ *                  redone in float64 as a whole.  Results are within 1e-4 of the float64 solution either way, but their
+ *                  last bits may depend on the batch a correspondence is in (the float64 modes have no such dependence).
  *   TRGL_F64_OUT32 u float64, x float32, float64 arithmetic   (output_dtype=float32 on float64 inputs)
  *   TRGL_F32_OUT64 u float32, x float64, float64 arithmetic   (float32 inputs, default output dtype)
  */
