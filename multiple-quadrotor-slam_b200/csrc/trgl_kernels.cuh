@@ -527,7 +527,10 @@ __device__ __forceinline__ int iter_point_general(const Cams<TC>& cams, TC a, TC
 //   mirrors: with result mirrors (multi-GPU gather) a 32-point slice is copied to the peers, fully coalesced, as soon as
 //            no point of it is queued any more -- FIFO order makes that "every slice before the one of the oldest queued
 //            entry" -- instead of repeating phase 2's scattered 8-byte stores over NVLink.
-constexpr int kPhase1 = 2;
+#ifndef TRGL_ITER_PHASE1
+#define TRGL_ITER_PHASE1 2
+#endif
+constexpr int kPhase1 = TRGL_ITER_PHASE1;
 constexpr int kWarpQueueCap = 64;                        // per warp: <= 31 left over + 32 pushed; power of two
 
 // Shared memory of one k_iterative_ls CTA (dynamic: above the static limit in the all-double mode).
@@ -1057,13 +1060,19 @@ __device__ __forceinline__ bool eigen_point_fast(const Cams<TC>& cams, TC u1x, T
 // runs the same number of rounds and decides together after each one (from the second on): all lanes converged -> done;
 // at most kEigenStragglers lanes left -> those are handed to the follow-up kernel (which runs the loop above, then the
 // Jacobi SVD) and the warp is done; otherwise everybody runs another round (a converged lane just stays converged), up to
-// kEigenMaxRounds.  One more round costs the warp 32 x ~95 instructions, a deferred point ~700: break-even at 4 lanes.
+// kEigenMaxRounds.  One more round costs the warp 32 x ~95 instructions, a deferred point ~700 plus its share of a
+// follow-up kernel that runs at low occupancy: measured per 10 M points with 3 / 2 / 1 / 0 stragglers allowed -- rotating rig
+// 0.385 / 0.384 / 0.384 / 0.390 ms, translating 0.478 / 0.464 / 0.464 / 0.468, forward motion 0.841 / 0.850 / 0.855 / 0.857,
+// general 0.359 / 0.359 / 0.358 / 0.355: flat, 2 is the best compromise.
 //   * the solve returns the DIRECTION d3 * (G - rho I)^-1 x: the last pivot d3 -> 0 as rho -> lam4 (that is the point of the
 //     iteration), so nothing is divided by it -- no IEEE division, no special-case path, no overflow;
 //   * normalisation uses MUFU.RSQ64H + one Newton step (1e-12): the iteration is self-correcting, and the Rayleigh
 //     quotient / residual test divide by the exact X.X.
 constexpr int kEigenMaxRounds = 4;
-constexpr int kEigenStragglers = 3;
+#ifndef TRGL_EIGEN_STRAGGLERS
+#define TRGL_EIGEN_STRAGGLERS 2
+#endif
+constexpr int kEigenStragglers = TRGL_EIGEN_STRAGGLERS;
 
 __device__ __forceinline__ double fast_rsqrt(double x) {
     double r;
